@@ -1,0 +1,292 @@
+"""CPU ORACLE (test infrastructure, not product code).
+
+A numpy/scipy restatement of the reference's NanoWrap conjugate-gradient hot path.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
+import this module; the product path (``ch_shrinkwrap_b200``) never does.
+
+Pinning: this restatement is checked against outputs of the *unmodified* reference
+(``mesh_conj_grad.py`` / ``conj_grad.py`` imported from ``/root/reference`` with its compiled
+``conj_grad_utils.c``) by ``oracle/make_golden.py``, which wrote the fixtures in
+``tests/golden/`` that ``tests/test_oracle_golden.py`` replays.  The reference has no
+tests or golden vectors of its own for this path.
+
+Third-party arithmetic on the path that is not under /root/reference:
+``scipy.spatial.cKDTree`` (scipy is unpinned by the reference; 1.18.1 here) supplies
+the nearest-centroid search exactly as at ``mesh_conj_grad.py:451-454``.
+
+Every function cites the reference lines it follows.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import scipy.spatial
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def _clib():
+    """liboracle.so: C restatement of the reference's C helpers (oracle/oracle_c.c)."""
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, 'liboracle.so')
+        if not os.path.exists(path):
+            from . import build as _b
+            _b.build_oracle_c()
+        _LIB = ctypes.CDLL(path)
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def ah_scatter(v_idx, w, fv, out):
+    """Sequential fp32 scatter-add, conj_grad_utils.c:153-162 (point order, then corner, then axis)."""
+    v_idx = np.ascontiguousarray(v_idx, dtype=np.int32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    fv = np.ascontiguousarray(fv, dtype=np.float32)
+    assert out.dtype == np.float32 and out.flags.c_contiguous
+    _clib().orc_ah_scatter(_p(v_idx, ctypes.c_int32), _p(w, ctypes.c_float), _p(fv, ctypes.c_float),
+                           _p(out, ctypes.c_float), ctypes.c_int64(v_idx.shape[0]))
+
+
+def nearest_face(points, face_centers):
+    """mesh_conj_grad.py:451-454: exact nearest centroid, fp64, all host threads."""
+    tree = scipy.spatial.cKDTree(face_centers)
+    return tree.query(points, k=1, workers=-1)
+
+
+class OracleConjGrad:
+    """Restates ``ShrinkwrapMeshConjGrad`` (mesh_conj_grad.py:19-292, 433-588, 770-820,
+    1002-1023) and ``TikhonovConjugateGradient.subsearch`` (conj_grad.py:183-229)."""
+
+    def __init__(self, mesh, points, build_point_tree=False):
+        self.mesh = mesh
+        self.points = points
+        # mesh_conj_grad.py:127-130 builds a kd-tree over the points that the active path never
+        # queries; reproduced only on request so CPU-baseline timings can include or exclude it.
+        self._tree = scipy.spatial.cKDTree(points) if build_point_tree else None
+        self._valid = mesh._vertices['halfedge'] != -1            # :44
+        self.vertices = mesh._vertices['position']                 # :46 (strided view)
+        self.faces = mesh.faces                                     # :47
+        nb = mesh._vertices['neighbors']
+        n = mesh._halfedges['vertex'][nb]                           # :50
+        n[nb == -1] = -1                                            # :51-52
+        self.vertex_neighbors = n
+        self.M = self.vertices.shape[0]
+        self.tests, self.ress, self.prefs = [], [], []              # conj_grad.py:37-39
+        self._prev_loopcount = -1
+        self.loopcount = 0
+        self.w = None
+        self.d = None
+
+    # -- weights: mesh_conj_grad.py:433-516 ------------------------------------
+    def compute_weights(self, f):
+        fv = f.reshape(-1, 3)
+        face_centers = fv[self.faces].mean(1)                      # :443 (fp32)
+        dmean, nearest = nearest_face(self.points, face_centers)   # :451-454
+        self.nearest = nearest
+        self.d = np.vstack([dmean, dmean, dmean]).T                # :483
+        v_idx = self.faces[nearest, :]                             # :488
+        d = np.zeros(v_idx.shape, 'f4')                            # :491
+        for j in range(3):
+            dv = fv[v_idx[:, j]] - self.points                     # :494
+            d[:, j] = np.sqrt(np.sum(dv * dv, 1))                  # :495
+        w = 1.0 / np.maximum(d, 1e-6)                              # :503
+        w = w / w.sum(1)[:, None]                                  # :510
+        assert not np.any(np.isnan(w))
+        return v_idx, w
+
+    def _calc_w(self):                                              # :1018-1023
+        if self._prev_loopcount < self.loopcount:
+            self._prev_loopcount = self.loopcount
+            return True
+        return False
+
+    def Afunc(self, f):                                             # :518-551
+        if self._calc_w():
+            self.w = self.compute_weights(self.f)
+        fv = f.reshape(-1, 3)
+        out = np.zeros_like(self.points)
+        v_idx, w = self.w
+        for i in range(3):
+            out += fv[v_idx[:, i]] * w[:, i][:, None]              # :544-545
+        assert not np.any(np.isnan(out))
+        return out.ravel()
+
+    def Ahfunc(self, f):                                            # :553-588
+        d = np.zeros([self.M, 3], dtype='f')
+        fv = f.reshape(-1, 3)
+        v_idx, w = self.w
+        ah_scatter(v_idx, w, fv.astype('f'), d)
+        assert not np.any(np.isnan(d))
+        return d.ravel()
+
+    def point_influence(self):                                      # _membrane_mesh.pyx:1625-1634
+        s = self.Ahfunc(np.ones_like(self.res)).reshape(self.vertices.shape)
+        return np.sqrt((s * s).sum(1))
+
+    # -- curvature prior: mesh_conj_grad.py:770-820 ----------------------------
+    def ncc(self):
+        mesh = self.mesh
+        hv = mesh._halfedges['vertex']
+        vnb = mesh.vertex_neighbors
+        vnn = hv[vnb]                                               # :777
+        mask = vnb > -1                                             # :778
+        ms = mask.sum(1)                                            # :779
+        verts, normals = mesh.vertices, mesh.vertex_normals
+        with np.errstate(invalid='ignore', divide='ignore'):
+            vc = (verts[vnn, :] * mask[:, :, None]).sum(1) / ms[:, None]      # :782
+            c_n = verts[vnn, :] - vc[:, None, :]                              # :785
+            n_n = normals[vnn, :]                                             # :788
+            n_dot_n = (n_n * normals[:, None, :]).sum(2)                      # :796
+            alpha = ((c_n * n_n).sum(2)) / np.sqrt(2 * (np.maximum(n_dot_n, 0) + 1))   # :797
+            alpha = (alpha * mask).sum(1) / ms                                # :800
+            pi = self.point_influence()                                       # :807
+            alpha = alpha * np.minimum(pi ** 2, 1)                            # :814
+            vc = vc + alpha[:, None] * normals                                # :816
+        vc[ms == 0, :] = verts[ms == 0, :]                                    # :818
+        return vc
+
+    def _stop_cond(self):                                           # :1009-1016
+        if len(self.tests) < 3:
+            return False
+        a, b, c = self.tests[-3:]
+        return (c < b) and (b < a) and (a < 1e-6)
+
+    # -- conj_grad.py:183-229 ---------------------------------------------------
+    def subsearch(self, f0, res, fdefs, lams, S):
+        n_search = S.shape[1]
+        c0 = (res * res).sum()
+        prefs = [f0 - fdefs[0]]                                     # Lfuncs == ["I"]
+        wpreds = [(p * p).sum() for p in prefs]
+        AS = np.zeros((np.size(res), n_search), 'f')
+        LS = np.zeros((len(prefs[0]), n_search, 1), 'f')
+        for k in range(n_search):
+            AS[:, k] = self.Afunc(S[:, k])[self.mask]
+            LS[:, k, 0] = S[:, k]
+        Hc = np.dot(AS.T, AS)
+        Gc = np.dot(AS.T, res)
+        Hw = np.zeros((n_search, n_search, 1))
+        Gw = np.zeros((n_search, 1))
+        H, G = Hc, Gc                                               # aliases (conj_grad.py:208)
+        ls = LS[:, :, 0]
+        Hw[:, :, 0] = np.dot(ls.T, ls)
+        Gw[:, 0] = np.dot(-ls.T, prefs[0])
+        l2 = lams[0] * lams[0]
+        H += l2 * Hw[:, :, 0]
+        G += l2 * Gw[:, 0]
+        c = np.linalg.solve(H, G)
+        cpred = c0 + np.dot(np.dot(c.T, Hc), c) - np.dot(c.T, Gc)
+        wpreds[0] += np.dot(np.dot(c.T, Hw[:, :, 0]), c) - np.dot(c.T, Gw[:, 0])
+        fnew = f0 + np.dot(S, c)
+        self.c = c
+        return fnew, cpred, wpreds
+
+    # -- mesh_conj_grad.py:150-292 ---------------------------------------------
+    def search(self, data, lams, num_iters=10, weights=None, sigma_inv=1.0, last_step=True):
+        self._prev_loopcount = -1
+        if weights is None:
+            weights = sigma_inv
+        if not np.isscalar(weights):
+            self.mask = weights > 0
+            weights = weights / weights.mean()
+        else:
+            self.mask = np.isfinite(data.ravel())
+        self.fs = self.vertices.copy()                              # start_guess :1002-1007
+        self.f = self.fs.ravel()
+        data = data.ravel()
+        self.res = 0 * data
+        n_smooth = min(1, len(lams))
+        n_search = n_smooth + 1
+        s_size = n_search + 1
+        prefs = np.zeros((np.size(self.f), n_smooth), 'f')
+        S = np.zeros((np.size(self.f), s_size), 'f')
+        self.loopcount = 0
+        while (self.loopcount < num_iters) and (not self._stop_cond()):
+            self.loopcount += 1
+            self.res[:] = weights * (data - self.Afunc(self.f))     # :222
+            defaults = [self.ncc().ravel()]                         # :224
+            w = 1.0 / (self.d.ravel() * sigma_inv / 2.0 + 1)        # :231
+            self.res *= w                                           # :248
+            S[:, 0] = self.Ahfunc(self.res)                         # :253
+            prefs[:, 0] = self.f - defaults[0]                      # :257
+            S[:, 1] = -1.0 * prefs[:, 0]                            # :258
+            test = 1.0 - abs((S[:, 0] * S[:, 1]).sum()
+                             / (np.linalg.norm(S[:, 0]) * np.linalg.norm(S[:, 1])))   # :262-265
+            self.tests.append(test)
+            self.ress.append(np.linalg.norm(self.res))
+            self.prefs.append(np.linalg.norm(prefs, axis=0))
+            fnew, self.cpred, self.wpreds = self.subsearch(self.f, self.res[self.mask], defaults,
+                                                           lams, S[:, 0:n_search])    # :274
+            if last_step:
+                S[:, s_size - 1] = fnew - self.f                    # :282
+                n_search = s_size
+            self.S = S
+            self.f[:] = fnew                                        # :288
+            self.mesh._vertices['position'][self._valid] = fnew.reshape(self.vertices.shape)[self._valid]  # :289
+            self.mesh._initialize_curvature_vectors()               # :290
+        return np.real(self.fs)
+
+
+# ---- secondary 1-ring regularisers (conj_grad_utils.c:249-710) -----------------------
+def _ring_call(name, f, nbrs, ref, out):
+    f = np.ascontiguousarray(f, dtype=np.float32)
+    nbrs = np.ascontiguousarray(nbrs, dtype=np.int32)
+    ref = np.ascontiguousarray(ref, dtype=np.float32)
+    getattr(_clib(), name)(_p(f, ctypes.c_float), _p(nbrs, ctypes.c_int32), _p(ref, ctypes.c_float),
+                           _p(out, ctypes.c_float), ctypes.c_int(nbrs.shape[0]), ctypes.c_int(nbrs.shape[1]))
+    return out
+
+
+def l_func(f, nbrs):
+    return _ring_call('orc_l_func', f, nbrs, f, np.zeros(f.size, np.float32))
+
+
+def lh_func(f, nbrs):
+    return _ring_call('orc_lh_func', f, nbrs, f, np.zeros(f.size, np.float32))
+
+
+def lw_func(f, nbrs, ref):
+    return _ring_call('orc_lw_func', f, nbrs, ref, np.zeros(f.size, np.float32))
+
+
+def lhw_func(f, nbrs, ref):
+    return _ring_call('orc_lhw_func', f, nbrs, ref, np.zeros(f.size, np.float32))
+
+
+def vertex_area_weights(ref, nbrs):
+    return _ring_call('orc_vertex_area_weights', ref, nbrs, ref, np.zeros(ref.size, np.float32))
+
+
+# ---- curvature (membrane_mesh_utils.c:915-1250) ------------------------------------
+CURV_SCALARS = ('k0', 'k1', 'H', 'K', 'dH', 'dK', 'E', 'pE', 'dE_neighbors')
+CURV_VECTORS = ('e0', 'e1', 'dEdN')
+
+
+def curvature_grad(mesh, dN=0.1, skip_prob=0.0, kc=1.0, kg=-20.0 * 0.0257, c0=0.0, jitter_u=None):
+    """C restatement of ``c_curvature_grad``.  ``jitter_u``: the uniform [0,1) numbers the
+    reference draws with ``rand()`` (3 per valid vertex, membrane_mesh_utils.c:1017); ``None`` = 0.5
+    (no jitter)."""
+    M = len(mesh._vertices)
+    out = {k: np.zeros(M, np.float32) for k in CURV_SCALARS}
+    out.update({k: np.zeros((M, 3), np.float32) for k in CURV_VECTORS})
+    verts = np.ascontiguousarray(mesh._vertices)
+    faces = np.ascontiguousarray(mesh._faces)
+    hes = np.ascontiguousarray(mesh._halfedges)
+    ju = None
+    if jitter_u is not None:
+        ju = np.ascontiguousarray(jitter_u, dtype=np.float64)
+        assert ju.size >= 3 * int((verts['halfedge'] != -1).sum())
+    fp = ctypes.POINTER(ctypes.c_float)
+    _clib().orc_curvature_grad(
+        ctypes.c_void_p(verts.ctypes.data), ctypes.c_void_p(faces.ctypes.data), ctypes.c_void_p(hes.ctypes.data),
+        ctypes.c_float(dN), ctypes.c_float(skip_prob), ctypes.c_int(M),
+        *[out[k].ctypes.data_as(fp) for k in ('k0', 'k1', 'e0', 'e1', 'H', 'K', 'dH', 'dK', 'E', 'pE', 'dE_neighbors')],
+        ctypes.c_float(kc), ctypes.c_float(kg), ctypes.c_float(c0), out['dEdN'].ctypes.data_as(fp),
+        None if ju is None else ju.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return out
