@@ -1,0 +1,157 @@
+// api.cu -- handle lifetime and the search() driver: all kernels of all iterations are enqueued on
+// one stream without host round trips; the stop rule, NaN guard and histories live on the device and
+// are read back once at the end (the reference's loop is mesh_conj_grad.py:218-290).
+#include <cmath>
+#include <cstring>
+#include "common.cuh"
+
+int nw_launch_solve_update(nw_ctx *h, int iter_index, int last_step);
+int nw_launch_influence(nw_ctx *h);
+
+extern "C" int nw_version(void) { return 100; }
+
+extern "C" int nw_create(int device, nw_ctx **out) {
+    if (!out) return NW_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return NW_ERR_CUDA;
+    nw_ctx *h = new nw_ctx();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return NW_ERR_CUDA;
+    }
+    if (cudaMalloc((void **)&h->st, sizeof(SolverState)) != cudaSuccess ||
+        cudaMalloc((void **)&h->hist, sizeof(double) * 5 * NW_MAX_ITERS) != cudaSuccess) {
+        delete h;
+        return NW_ERR_CUDA;
+    }
+    cudaMemset(h->st, 0, sizeof(SolverState));
+    h->tl.n_levels = 0;
+    *out = h;
+    return NW_OK;
+}
+
+int nw_comm_destroy(nw_ctx *h);
+
+extern "C" void nw_destroy(nw_ctx *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    nw_comm_destroy(h);
+    nw_free(&h->px); nw_free(&h->py); nw_free(&h->pz);
+    nw_free(&h->px64); nw_free(&h->py64); nw_free(&h->pz64);
+    nw_free(&h->sx); nw_free(&h->sy); nw_free(&h->sz);
+    nw_free(&h->wx); nw_free(&h->wy); nw_free(&h->wz);
+    nw_free(&h->pmask); nw_free(&h->perm); nw_free(&h->slot);
+    nw_free(&h->w0); nw_free(&h->w1); nw_free(&h->w2);
+    nw_free(&h->rx); nw_free(&h->ry); nw_free(&h->rz);
+    nw_free(&h->posq); nw_free(&h->nrmq); nw_free(&h->faces); nw_free(&h->nbrT); nw_free(&h->valence); nw_free(&h->valid);
+    nw_free(&h->sfaces); nw_free(&h->cent); nw_free(&h->boxes);
+    nw_free(&h->acc); nw_free(&h->S0); nw_free(&h->S1); nw_free(&h->S2); nw_free(&h->fdef);
+    nw_free(&h->partials); nw_free(&h->st); nw_free(&h->hist);
+    nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP); nw_free(&h->curvK);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char *nw_last_error(nw_ctx *h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int64_t nw_launch_count(nw_ctx *h) { return h ? h->launches : 0; }
+extern "C" int nw_sync(nw_ctx *h) {
+    if (!h) return NW_ERR_ARG;
+    NW_CUDA(cudaSetDevice(h->device));
+    NW_CUDA(cudaStreamSynchronize(h->stream));
+    return NW_OK;
+}
+
+static int ensure_partials(nw_ctx *h) {
+    const int want = 148 * 4;
+    const size_t need = (size_t)want * 16 + (size_t)nw_grid(h->M, 256) * 16 + 64;
+    if (h->n_partials != want || !h->partials) {
+        NW_CHECK(nw_alloc(h, &h->partials, need));
+        h->n_partials = want;
+    } else {
+        // M may have changed since the last block
+        NW_CHECK(nw_alloc(h, &h->partials, need));
+    }
+    return NW_OK;
+}
+
+static int upload_state(nw_ctx *h, const SolverState &s) {
+    NW_CUDA(cudaMemcpyAsync(h->st, &s, sizeof(SolverState), cudaMemcpyHostToDevice, h->stream));
+    return NW_OK;
+}
+
+// one full iteration, enqueued asynchronously
+static int enqueue_iteration(nw_ctx *h, int it, int last_step) {
+    NW_CHECK(nw_tree_refit(h));                 // centroids + boxes at the current f  (:443)
+    NW_CHECK(nw_set_acc_shifts(h));
+    NW_CHECK(nw_launch_sweep1(h, true));        // NN, weights, A f, residual, AH res, AH 1  (:222-253)
+    NW_CHECK(nw_allreduce_acc(h));              // N>1: vertex-gradient allreduce
+    NW_CHECK(nw_launch_mesh_prior(h, true));    // S0, ncc, prefs, S1, S^T S  (:224,253-258)
+    NW_CHECK(nw_launch_sweep2(h));              // A S_k and Gram sums  (conj_grad.py:197-203)
+    NW_CHECK(nw_allreduce_scalars(h));          // N>1: CG scalars
+    NW_CHECK(nw_launch_solve_update(h, it, last_step));
+    return NW_OK;
+}
+
+extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, const double *prev_tests, int n_prev,
+                         float *pos_out, double *tests, double *ress, double *prefs, double *cpred, double *wpred,
+                         int *n_done) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(h->M > 0, "nw_search: no topology (call nw_set_topology first)");
+    NW_ARG(h->px != nullptr || h->P == 0, "nw_search: no points (call nw_set_points first)");
+    NW_ARG(num_iters >= 0 && num_iters <= NW_MAX_ITERS, "nw_search: num_iters out of range");
+    NW_ARG(n_prev >= 0 && (n_prev == 0 || prev_tests), "nw_search: bad prev_tests");
+    NW_CUDA(cudaSetDevice(h->device));
+    NW_CHECK(ensure_partials(h));
+    SolverState s;
+    memset(&s, 0, sizeof(s));
+    s.lam = lam;
+    s.n_search = 2;
+    int np = n_prev > 3 ? 3 : n_prev;
+    for (int k = 0; k < np; ++k) s.last_tests[k] = prev_tests[n_prev - np + k];
+    s.n_tests = np;
+    if (np == 3 && s.last_tests[2] < s.last_tests[1] && s.last_tests[1] < s.last_tests[0] && s.last_tests[0] < 1e-6) s.stop = 2;
+    NW_CHECK(upload_state(h, s));
+    // S is freshly zeroed on every search() call (mesh_conj_grad.py:207)
+    NW_CUDA(cudaMemsetAsync(h->S0, 0, sizeof(float4) * h->M, h->stream));
+    NW_CUDA(cudaMemsetAsync(h->S1, 0, sizeof(float4) * h->M, h->stream));
+    NW_CUDA(cudaMemsetAsync(h->S2, 0, sizeof(float4) * h->M, h->stream));
+    NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * h->M, h->stream));
+    if (!s.stop)
+        for (int it = 0; it < num_iters; ++it) NW_CHECK(enqueue_iteration(h, it, last_step));
+    SolverState r;
+    NW_CUDA(cudaMemcpyAsync(&r, h->st, sizeof(SolverState), cudaMemcpyDeviceToHost, h->stream));
+    NW_CUDA(cudaStreamSynchronize(h->stream));
+    if (n_done) *n_done = r.n_done;
+    if (r.n_done > 0) {
+        h->weights_valid = true;
+        double *dst[5] = {tests, ress, prefs, cpred, wpred};
+        for (int k = 0; k < 5; ++k)
+            if (dst[k]) NW_CUDA(cudaMemcpy(dst[k], h->hist + (size_t)k * NW_MAX_ITERS, sizeof(double) * r.n_done, cudaMemcpyDeviceToHost));
+    }
+    if (pos_out) NW_CHECK(nw_get_positions(h, pos_out));
+    if (r.nan_flag == 2) { h->err = "nw_search: singular subspace matrix (numpy.linalg.LinAlgError in the reference)"; return NW_ERR_NAN; }
+    if (r.nan_flag) { h->err = "nw_search: non-finite value in residual / search directions / update"; return NW_ERR_NAN; }
+    return NW_OK;
+}
+
+extern "C" int nw_ncc(nw_ctx *h, double *fdef) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(h->M > 0 && h->weights_valid, "nw_ncc: weights not computed");
+    NW_CUDA(cudaSetDevice(h->device));
+    SolverState s;
+    memset(&s, 0, sizeof(s));
+    s.n_search = 2;
+    NW_CHECK(upload_state(h, s));
+    NW_CHECK(nw_set_acc_shifts(h));
+    NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * h->M, h->stream));
+    NW_CHECK(nw_launch_influence(h));
+    NW_CHECK(nw_allreduce_acc(h));
+    NW_CHECK(nw_launch_mesh_prior(h, false));
+    NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * h->M, h->stream));
+    NW_CUDA(cudaMemcpyAsync(fdef, h->fdef, sizeof(double) * 3 * h->M, cudaMemcpyDeviceToHost, h->stream));
+    NW_CUDA(cudaStreamSynchronize(h->stream));
+    return NW_OK;
+}

@@ -1,0 +1,156 @@
+// common.cuh -- handle layout, error plumbing and small device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/nanowrap.h"
+
+#define NW_LEAF 8        // sorted centroids per leaf of the Morton AABB pyramid
+#define NW_FAN 4         // children per interior node (4 x 32 B boxes = one 128 B line)
+#define NW_MAX_LEVELS 16
+#define NW_MAX_ITERS 4096
+
+struct Box { float4 lo, hi; };   // 32 B: one L2 sector per box
+
+struct TreeLevels {
+    int n_levels;                 // level 0 = leaves
+    int count[NW_MAX_LEVELS];
+    int offset[NW_MAX_LEVELS];    // into the single boxes[] buffer
+};
+
+// Scalars produced and consumed on the device inside one search() call.
+struct SolverState {
+    double c[4];                  // step coefficients of the current iteration
+    double hw[6];                 // S^T S  (00,01,11,02,12,22)
+    double gw[3];                 // -S^T prefs64
+    double hc[6], gc[3], c0, res2;
+    double last_tests[3];
+    int n_tests;                  // how many of last_tests are valid (<=3), newest last
+    int n_done;
+    int stop;                     // stop rule fired: remaining kernels become no-ops
+    int nan_flag;
+    int n_search;                 // 2 on the first iteration of a call, 3 afterwards (last_step)
+    int acc_shift;                // fixed-point fraction bits of the adjoint accumulators
+    int infl_shift;               // ditto for the AH*1 accumulator
+    float lam;
+};
+
+struct nw_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // ---- points (Morton-sorted SoA) ----
+    int64_t P = 0;
+    int64_t P_global = 0;
+    float *px = nullptr, *py = nullptr, *pz = nullptr;
+    double *px64 = nullptr, *py64 = nullptr, *pz64 = nullptr;    // only when float64 points were given
+    float *sx = nullptr, *sy = nullptr, *sz = nullptr;           // sigma_inv (NULL -> scalar)
+    float *wx = nullptr, *wy = nullptr, *wz = nullptr;           // weights when distinct from sigma_inv
+    float sinv_scalar = 1.f;
+    int weights_mode = 0;        // 0: scalar weight = sinv_scalar; 1: weights = sigma_inv array; 2: own array
+    float wmean = 1.f;           // mean of the weight array over all ranks (float32 like numpy)
+    int has_mask = 0;            // some weight <= 0
+    uint8_t *pmask = nullptr;    // 3 bits per point when has_mask
+    int *perm = nullptr;         // sorted position -> caller's index
+    int *slot = nullptr;         // nearest sorted-centroid slot per point (-1 = none yet)
+    float *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
+    float *rx = nullptr, *ry = nullptr, *rz = nullptr;
+    float bbox_pts[6] = {0, 0, 0, 0, 0, 0};
+    double wn_max = 1.0;
+    bool weights_valid = false;
+
+    // ---- mesh ----
+    int M = 0, F = 0;
+    float4 *posq = nullptr, *nrmq = nullptr;     // xyz + pad: one LDG.128 per gather
+    int *faces = nullptr;                        // (F,3) as uploaded
+    int *nbrT = nullptr;                         // neighbour table, k-major: nbrT[k*M + v]
+    int *valence = nullptr;
+    uint8_t *valid = nullptr;
+    // ---- Morton AABB pyramid over face centroids ----
+    int4 *sfaces = nullptr;                      // per sorted slot: corner ids + face id
+    float4 *cent = nullptr;                      // per sorted slot: centroid xyz + face id bits
+    Box *boxes = nullptr;
+    TreeLevels tl;
+    // ---- solver vectors ----
+    unsigned long long *acc = nullptr;           // (M,4) int64 fixed point: AH res xyz, AH 1
+    float4 *S0 = nullptr, *S1 = nullptr, *S2 = nullptr;
+    double *fdef = nullptr;                      // (M,3)
+    double *partials = nullptr;                  // per-CTA partial sums
+    int n_partials = 0;
+    SolverState *st = nullptr;                   // device
+    double *hist = nullptr;                      // device: 5 x NW_MAX_ITERS (tests, ress, prefs, cpred, wpred)
+    void *cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    float *scratchM = nullptr;                   // 3M floats
+    float *scratchP = nullptr;                   // 3P floats
+    int64_t scratchP_elems = 0;
+
+    // ---- curvature ----
+    float *curvK = nullptr;
+    int curvM = 0;
+
+    // ---- comm ----
+    void *nccl = nullptr;                        // ncclComm_t
+    int rank = 0, nranks = 1;
+};
+
+#define NW_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+            return NW_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define NW_CHECK(expr)                                                                     \
+    do {                                                                                   \
+        int r_ = (expr);                                                                   \
+        if (r_ != NW_OK) return r_;                                                        \
+    } while (0)
+
+#define NW_ARG(cond, msg)                                                                  \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            h->err = msg;                                                                  \
+            return NW_ERR_ARG;                                                             \
+        }                                                                                  \
+    } while (0)
+
+template <typename T>
+static inline int nw_alloc(nw_ctx *h, T **p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) return NW_OK;
+    NW_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+    return NW_OK;
+}
+template <typename T>
+static inline void nw_free(T **p) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+static inline int nw_grid(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+#define NW_LAUNCH_CHECK()                                                                  \
+    do {                                                                                   \
+        h->launches++;                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                               \
+        if (e_ != cudaSuccess) {                                                           \
+            h->err = std::string("kernel launch: ") + cudaGetErrorString(e_);              \
+            return NW_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+// ---- internal entry points implemented across translation units -------------------------------
+int nw_tree_build(nw_ctx *h);                 // after topology upload: Morton sort of faces
+int nw_tree_refit(nw_ctx *h);                 // every iteration: centroids + boxes at the current f
+int nw_launch_sweep1(nw_ctx *h, bool scatter);
+int nw_launch_sweep2(nw_ctx *h);
+int nw_launch_mesh_prior(nw_ctx *h, bool write_dirs);
+int nw_launch_solve_update(nw_ctx *h);
+int nw_allreduce_acc(nw_ctx *h);
+int nw_allreduce_scalars(nw_ctx *h);
+int nw_set_acc_shifts(nw_ctx *h);

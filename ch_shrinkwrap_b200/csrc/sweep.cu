@@ -1,0 +1,668 @@
+// sweep.cu -- the per-point kernels of the hot loop.
+//
+//   k_sweep1 : exact nearest face centroid (fp64 compare, Morton AABB pyramid) -> inverse-distance
+//              weights -> A f -> weighted, distance-de-weighted residual -> deterministic adjoint
+//              scatter of AH res and AH 1            (mesh_conj_grad.py:222-253, 433-516, 518-588)
+//   k_sweep2 : A applied to all search directions at once + Gram sums Hc, Gc, c0 in fp64, without
+//              materialising AS                                       (conj_grad.py:189-203)
+//   k_apply_A / k_apply_AH : the single-operator forms behind Afunc / Ahfunc.
+//
+// Determinism: the adjoint accumulates in 64-bit fixed point (integer atomics are order-independent,
+// float atomics are not); the Gram sums use a fixed thread->point assignment and a fixed two-stage tree.
+#include <cfloat>
+#include "common.cuh"
+
+namespace {
+
+// ---- exact-arithmetic helpers (never contracted into FMAs) ---------------------------------------
+__device__ __forceinline__ float sq_rd(float g) { return __fmul_rd(g, g); }
+
+struct QueryF32 {
+    float x, y, z;
+    __device__ __forceinline__ float lb_box(const float4 lo, const float4 hi) const {
+        float gx = fmaxf(fmaxf(__fsub_rd(lo.x, x), __fsub_rd(x, hi.x)), 0.f);
+        float gy = fmaxf(fmaxf(__fsub_rd(lo.y, y), __fsub_rd(y, hi.y)), 0.f);
+        float gz = fmaxf(fmaxf(__fsub_rd(lo.z, z), __fsub_rd(z, hi.z)), 0.f);
+        return __fadd_rd(__fadd_rd(sq_rd(gx), sq_rd(gy)), sq_rd(gz));
+    }
+    // scipy sqeuclidean_distance_double on float32->float64 promoted inputs: ((dx^2)+dy^2)+dz^2
+    __device__ __forceinline__ double d2(const float4 c) const {
+        double dx = (double)x - (double)c.x, dy = (double)y - (double)c.y, dz = (double)z - (double)c.z;
+        return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    }
+};
+
+struct QueryF64 {
+    double x, y, z;
+    float xl, xh, yl, yh, zl, zh;   // float32 enclosure of the float64 coordinates
+    __device__ __forceinline__ void set(double px, double py, double pz) {
+        x = px; y = py; z = pz;
+        xl = __double2float_rd(px); xh = __double2float_ru(px);
+        yl = __double2float_rd(py); yh = __double2float_ru(py);
+        zl = __double2float_rd(pz); zh = __double2float_ru(pz);
+    }
+    __device__ __forceinline__ float lb_box(const float4 lo, const float4 hi) const {
+        float gx = fmaxf(fmaxf(__fsub_rd(lo.x, xh), __fsub_rd(xl, hi.x)), 0.f);
+        float gy = fmaxf(fmaxf(__fsub_rd(lo.y, yh), __fsub_rd(yl, hi.y)), 0.f);
+        float gz = fmaxf(fmaxf(__fsub_rd(lo.z, zh), __fsub_rd(zl, hi.z)), 0.f);
+        return __fadd_rd(__fadd_rd(sq_rd(gx), sq_rd(gy)), sq_rd(gz));
+    }
+    __device__ __forceinline__ double d2(const float4 c) const {
+        double dx = x - (double)c.x, dy = y - (double)c.y, dz = z - (double)c.z;
+        return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    }
+};
+
+struct Nearest {
+    double d2;
+    float ub;      // d2 rounded up to float: prune bound for the float32 lower bounds
+    int slot, face;
+    __device__ __forceinline__ void offer(double v, int s, int f) {
+        // strict minimum; exact fp64 ties -> lowest face index (contract of SURVEY 7.3)
+        if (v < d2 || (v == d2 && f < face)) { d2 = v; slot = s; face = f; ub = __double2float_ru(v); }
+    }
+};
+
+#define NW_STACK 48
+
+template <typename Q>
+__device__ __forceinline__ void nearest_centroid(const Q &q, Nearest &best, const float4 *__restrict__ cent,
+                                                 const Box *__restrict__ boxes, const TreeLevels &tl, int F) {
+    float slb[NW_STACK];
+    int snode[NW_STACK];
+    int sp = 0;
+    const int top = tl.n_levels - 1;
+    for (int k = tl.count[top] - 1; k >= 0; --k) {
+        Box b = boxes[tl.offset[top] + k];
+        slb[sp] = q.lb_box(b.lo, b.hi);
+        snode[sp++] = (top << 26) | k;
+    }
+    while (sp > 0) {
+        --sp;
+        const float lb = slb[sp];
+        const int node = snode[sp];
+        if (lb > best.ub) continue;
+        const int level = node >> 26, idx = node & 0x3ffffff;
+        if (level == 0) {
+            const int base = idx * NW_LEAF;
+            const int n = min(NW_LEAF, F - base);
+            for (int k = 0; k < n; ++k) {
+                const float4 c = __ldg(&cent[base + k]);
+                if (q.lb_box(c, c) <= best.ub) best.offer(q.d2(c), base + k, __float_as_int(c.w));
+            }
+        } else {
+            const int cl = level - 1;
+            const int c0 = idx * NW_FAN;
+            const int n = min(NW_FAN, tl.count[cl] - c0);
+            float l[NW_FAN];
+            int id[NW_FAN];
+#pragma unroll
+            for (int k = 0; k < NW_FAN; ++k) {
+                if (k < n) {
+                    const Box *bp = &boxes[tl.offset[cl] + c0 + k];
+                    const float4 lo = __ldg(&bp->lo), hi = __ldg(&bp->hi);
+                    l[k] = q.lb_box(lo, hi);
+                } else l[k] = FLT_MAX;
+                id[k] = (cl << 26) | (c0 + k);
+            }
+            // sort descending by lower bound so the nearest child is popped first
+#define NW_CSWAP(a, b) if (l[a] < l[b]) { float tf = l[a]; l[a] = l[b]; l[b] = tf; int ti = id[a]; id[a] = id[b]; id[b] = ti; }
+            NW_CSWAP(0, 1) NW_CSWAP(2, 3) NW_CSWAP(0, 2) NW_CSWAP(1, 3) NW_CSWAP(1, 2)
+#undef NW_CSWAP
+#pragma unroll
+            for (int k = 0; k < NW_FAN; ++k)
+                if (l[k] <= best.ub && l[k] != FLT_MAX) { slb[sp] = l[k]; snode[sp++] = id[k]; }
+        }
+    }
+}
+
+__device__ __forceinline__ double pow2d(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
+
+__device__ __forceinline__ void red_fixed(unsigned long long *p, float v, double scale) {
+    long long q = __double2ll_rn((double)v * scale);
+    atomicAdd(p, (unsigned long long)q);
+}
+
+struct Sweep1Args {
+    int64_t P;
+    const float *px, *py, *pz;
+    const double *px64, *py64, *pz64;
+    const float *sx, *sy, *sz;     // sigma_inv arrays or NULL
+    const float *wx, *wy, *wz;     // weight arrays (may alias sigma_inv) or NULL
+    float sinv_scalar, wmean;
+    int *slot;
+    float *w0, *w1, *w2, *rx, *ry, *rz;
+    const float4 *cent, *posq;
+    const int4 *sfaces;
+    const Box *boxes;
+    TreeLevels tl;
+    int F;
+    unsigned long long *acc;
+    SolverState *st;
+};
+
+// MODE 0: nearest face + weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
+template <bool F64, int MODE>
+__global__ void __launch_bounds__(128) k_sweep1(const Sweep1Args a) {
+    if (MODE == 1 && a.st->stop) return;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= a.P) return;
+    const float x = a.px[i], y = a.py[i], z = a.pz[i];
+    Nearest best;
+    best.d2 = DBL_MAX * 2.0;   // +inf
+    best.ub = FLT_MAX * 2.0f;
+    best.slot = -1;
+    best.face = 0x7fffffff;
+    double xd = x, yd = y, zd = z;
+    const int seed = a.slot[i];
+    if (F64) {
+        xd = a.px64[i]; yd = a.py64[i]; zd = a.pz64[i];
+        QueryF64 q;
+        q.set(xd, yd, zd);
+        if (seed >= 0) { const float4 c = a.cent[seed]; best.offer(q.d2(c), seed, __float_as_int(c.w)); }
+        nearest_centroid(q, best, a.cent, a.boxes, a.tl, a.F);
+    } else {
+        QueryF32 q{x, y, z};
+        if (seed >= 0) { const float4 c = a.cent[seed]; best.offer(q.d2(c), seed, __float_as_int(c.w)); }
+        nearest_centroid(q, best, a.cent, a.boxes, a.tl, a.F);
+    }
+    a.slot[i] = best.slot;
+    const int4 sf = a.sfaces[best.slot];
+    const float4 v0 = __ldg(&a.posq[sf.x]), v1 = __ldg(&a.posq[sf.y]), v2 = __ldg(&a.posq[sf.z]);
+    // corner distances, mesh_conj_grad.py:491-495 (float32 points: all float32; float64 points: float64 then stored float32)
+    float d0, d1, d2;
+    if (F64) {
+        double ax = (double)v0.x - xd, ay = (double)v0.y - yd, az = (double)v0.z - zd;
+        d0 = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
+        ax = (double)v1.x - xd; ay = (double)v1.y - yd; az = (double)v1.z - zd;
+        d1 = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
+        ax = (double)v2.x - xd; ay = (double)v2.y - yd; az = (double)v2.z - zd;
+        d2 = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az)));
+    } else {
+        float ax = __fsub_rn(v0.x, x), ay = __fsub_rn(v0.y, y), az = __fsub_rn(v0.z, z);
+        d0 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+        ax = __fsub_rn(v1.x, x); ay = __fsub_rn(v1.y, y); az = __fsub_rn(v1.z, z);
+        d1 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+        ax = __fsub_rn(v2.x, x); ay = __fsub_rn(v2.y, y); az = __fsub_rn(v2.z, z);
+        d2 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+    }
+    // w = 1/max(d,1e-6); w /= w.sum(1)      (:503,510)
+    float u0 = __fdiv_rn(1.0f, fmaxf(d0, 1e-6f)), u1 = __fdiv_rn(1.0f, fmaxf(d1, 1e-6f)), u2 = __fdiv_rn(1.0f, fmaxf(d2, 1e-6f));
+    const float us = __fadd_rn(__fadd_rn(u0, u1), u2);
+    u0 = __fdiv_rn(u0, us); u1 = __fdiv_rn(u1, us); u2 = __fdiv_rn(u2, us);
+    a.w0[i] = u0; a.w1[i] = u1; a.w2[i] = u2;
+    if (MODE == 0) return;
+
+    // A f  (:544-545)
+    const float afx = __fadd_rn(__fadd_rn(__fmul_rn(v0.x, u0), __fmul_rn(v1.x, u1)), __fmul_rn(v2.x, u2));
+    const float afy = __fadd_rn(__fadd_rn(__fmul_rn(v0.y, u0), __fmul_rn(v1.y, u1)), __fmul_rn(v2.y, u2));
+    const float afz = __fadd_rn(__fadd_rn(__fmul_rn(v0.z, u0), __fmul_rn(v1.z, u1)), __fmul_rn(v2.z, u2));
+    // res = Wn (p - A f) / (D sigma_inv / 2 + 1)      (:222,231,248)
+    float s_x = a.sinv_scalar, s_y = a.sinv_scalar, s_z = a.sinv_scalar;
+    if (a.sx) { s_x = a.sx[i]; s_y = a.sy[i]; s_z = a.sz[i]; }
+    float wnx, wny, wnz;
+    if (a.wx) {
+        wnx = __fdiv_rn(a.wx == a.sx ? s_x : a.wx[i], a.wmean);
+        wny = __fdiv_rn(a.wy == a.sy ? s_y : a.wy[i], a.wmean);
+        wnz = __fdiv_rn(a.wz == a.sz ? s_z : a.wz[i], a.wmean);
+    } else wnx = wny = wnz = a.sinv_scalar;
+    const double D = sqrt(best.d2);
+    float r_x, r_y, r_z;
+    if (F64) {
+        r_x = (float)((double)wnx * (xd - (double)afx)); r_y = (float)((double)wny * (yd - (double)afy)); r_z = (float)((double)wnz * (zd - (double)afz));
+    } else {
+        r_x = __fmul_rn(wnx, __fsub_rn(x, afx)); r_y = __fmul_rn(wny, __fsub_rn(y, afy)); r_z = __fmul_rn(wnz, __fsub_rn(z, afz));
+    }
+    r_x = (float)((double)r_x * (1.0 / (D * (double)s_x / 2.0 + 1.0)));
+    r_y = (float)((double)r_y * (1.0 / (D * (double)s_y / 2.0 + 1.0)));
+    r_z = (float)((double)r_z * (1.0 / (D * (double)s_z / 2.0 + 1.0)));
+    a.rx[i] = r_x; a.ry[i] = r_y; a.rz[i] = r_z;
+    if (!(r_x == r_x && r_y == r_y && r_z == r_z && fabsf(r_x) <= FLT_MAX && fabsf(r_y) <= FLT_MAX && fabsf(r_z) <= FLT_MAX))
+        a.st->nan_flag = 1;
+    // deterministic adjoint: S0 += w_j res, influence += w_j, in fixed point (conj_grad_utils.c:153-162)
+    const double sc = pow2d(a.st->acc_shift), sci = pow2d(a.st->infl_shift);
+    const int vid[3] = {sf.x, sf.y, sf.z};
+    const float uw[3] = {u0, u1, u2};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        unsigned long long *dst = a.acc + 4 * (size_t)vid[j];
+        red_fixed(dst + 0, __fmul_rn(uw[j], r_x), sc);
+        red_fixed(dst + 1, __fmul_rn(uw[j], r_y), sc);
+        red_fixed(dst + 2, __fmul_rn(uw[j], r_z), sc);
+        red_fixed(dst + 3, uw[j], sci);
+    }
+}
+
+// ---- single-operator forms ------------------------------------------------------------------------
+// y_p = sum_j w_pj x[v_pj]   (Afunc, mesh_conj_grad.py:539-545); x packed float4 per vertex
+__global__ void __launch_bounds__(256) k_apply_A(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
+                                                 const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
+                                                 const float4 *__restrict__ xq, float *__restrict__ yx, float *__restrict__ yy, float *__restrict__ yz) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int4 sf = __ldg(&sfaces[slot[i]]);
+    const float u0 = w0[i], u1 = w1[i], u2 = w2[i];
+    const float4 a = __ldg(&xq[sf.x]), b = __ldg(&xq[sf.y]), c = __ldg(&xq[sf.z]);
+    yx[i] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, u0), __fmul_rn(b.x, u1)), __fmul_rn(c.x, u2));
+    yy[i] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, u0), __fmul_rn(b.y, u1)), __fmul_rn(c.y, u2));
+    yz[i] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u0), __fmul_rn(b.z, u1)), __fmul_rn(c.z, u2));
+}
+
+// out_v += sum w_pj r_p  (Ahfunc) into the fixed-point accumulators; acc.w untouched
+__global__ void __launch_bounds__(256) k_apply_AH(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
+                                                  const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
+                                                  const float *__restrict__ rx, const float *__restrict__ ry, const float *__restrict__ rz,
+                                                  unsigned long long *__restrict__ acc, int shift) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int4 sf = __ldg(&sfaces[slot[i]]);
+    const float uw[3] = {w0[i], w1[i], w2[i]};
+    const float r_x = rx[i], r_y = ry[i], r_z = rz[i];
+    const double sc = pow2d(shift);
+    const int vid[3] = {sf.x, sf.y, sf.z};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        unsigned long long *dst = acc + 4 * (size_t)vid[j];
+        red_fixed(dst + 0, __fmul_rn(uw[j], r_x), sc);
+        red_fixed(dst + 1, __fmul_rn(uw[j], r_y), sc);
+        red_fixed(dst + 2, __fmul_rn(uw[j], r_z), sc);
+    }
+}
+
+// influence_v += sum w_pj  (AH applied to ones, channel 3 of the accumulators)
+__global__ void __launch_bounds__(256) k_apply_infl(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
+                                                    const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
+                                                    unsigned long long *__restrict__ acc, const SolverState *__restrict__ st) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int4 sf = __ldg(&sfaces[slot[i]]);
+    const double sci = pow2d(st->infl_shift);
+    red_fixed(acc + 4 * (size_t)sf.x + 3, w0[i], sci);
+    red_fixed(acc + 4 * (size_t)sf.y + 3, w1[i], sci);
+    red_fixed(acc + 4 * (size_t)sf.z + 3, w2[i], sci);
+}
+
+// ---- Gram pass -------------------------------------------------------------------------------------
+#define NW_NSUM 11   // hc00 hc01 hc11 hc02 hc12 hc22 gc0 gc1 gc2 c0 res2
+
+__global__ void __launch_bounds__(256) k_sweep2(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
+                                                const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
+                                                const float *__restrict__ rx, const float *__restrict__ ry, const float *__restrict__ rz,
+                                                const float4 *__restrict__ S0, const float4 *__restrict__ S1, const float4 *__restrict__ S2,
+                                                const uint8_t *__restrict__ pmask, const SolverState *__restrict__ st,
+                                                double *__restrict__ partials) {
+    if (st->stop) return;
+    const bool three = st->n_search == 3;
+    double acc[NW_NSUM];
+#pragma unroll
+    for (int k = 0; k < NW_NSUM; ++k) acc[k] = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 sf = __ldg(&sfaces[slot[i]]);
+        const float u0 = w0[i], u1 = w1[i], u2 = w2[i];
+        const float r[3] = {rx[i], ry[i], rz[i]};
+        const unsigned m = pmask ? pmask[i] : 7u;
+        float as[3][3];
+        {
+            const float4 a = __ldg(&S0[sf.x]), b = __ldg(&S0[sf.y]), c = __ldg(&S0[sf.z]);
+            as[0][0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, u0), __fmul_rn(b.x, u1)), __fmul_rn(c.x, u2));
+            as[0][1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, u0), __fmul_rn(b.y, u1)), __fmul_rn(c.y, u2));
+            as[0][2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u0), __fmul_rn(b.z, u1)), __fmul_rn(c.z, u2));
+        }
+        {
+            const float4 a = __ldg(&S1[sf.x]), b = __ldg(&S1[sf.y]), c = __ldg(&S1[sf.z]);
+            as[1][0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, u0), __fmul_rn(b.x, u1)), __fmul_rn(c.x, u2));
+            as[1][1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, u0), __fmul_rn(b.y, u1)), __fmul_rn(c.y, u2));
+            as[1][2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u0), __fmul_rn(b.z, u1)), __fmul_rn(c.z, u2));
+        }
+        if (three) {
+            const float4 a = __ldg(&S2[sf.x]), b = __ldg(&S2[sf.y]), c = __ldg(&S2[sf.z]);
+            as[2][0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, u0), __fmul_rn(b.x, u1)), __fmul_rn(c.x, u2));
+            as[2][1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, u0), __fmul_rn(b.y, u1)), __fmul_rn(c.y, u2));
+            as[2][2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u0), __fmul_rn(b.z, u1)), __fmul_rn(c.z, u2));
+        } else as[2][0] = as[2][1] = as[2][2] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double rr = (double)r[c];
+            acc[10] += rr * rr;
+            if (m & (1u << c)) {     // res[mask], AS[mask]  (mesh_conj_grad.py:274, conj_grad.py:198)
+                const double a0 = as[0][c], a1 = as[1][c], a2 = as[2][c];
+                acc[0] += a0 * a0; acc[1] += a0 * a1; acc[2] += a1 * a1;
+                acc[3] += a0 * a2; acc[4] += a1 * a2; acc[5] += a2 * a2;
+                acc[6] += a0 * rr; acc[7] += a1 * rr; acc[8] += a2 * rr;
+                acc[9] += rr * rr;
+            }
+        }
+    }
+    __shared__ double sh[8][NW_NSUM];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NW_NSUM; ++k) {
+        double v = acc[k];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NW_NSUM) {
+        double v = 0.0;
+        for (int k = 0; k < 8; ++k) v += sh[k][threadIdx.x];
+        partials[(size_t)blockIdx.x * NW_NSUM + threadIdx.x] = v;
+    }
+}
+
+// fold the per-CTA partials in fixed order into the solver state
+__global__ void k_fold_partials(const double *__restrict__ partials, int n_blocks, SolverState *st) {
+    if (st->stop) return;
+    const int k = threadIdx.x;
+    if (k >= NW_NSUM) return;
+    double v = 0.0;
+    for (int b = 0; b < n_blocks; ++b) v += partials[(size_t)b * NW_NSUM + k];
+    if (k < 6) st->hc[k] = v;
+    else if (k < 9) st->gc[k - 6] = v;
+    else if (k == 9) st->c0 = v;
+    else st->res2 = v;
+}
+
+// ---- host<->device order conversion -------------------------------------------------------------
+__global__ void k_gather_sorted3(const float *__restrict__ src, const int *__restrict__ perm, int64_t P,
+                                 float *__restrict__ ox, float *__restrict__ oy, float *__restrict__ oz) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    int64_t s = perm[i];
+    ox[i] = src[3 * s]; oy[i] = src[3 * s + 1]; oz[i] = src[3 * s + 2];
+}
+__global__ void k_scatter_caller3(const float *__restrict__ ix, const float *__restrict__ iy, const float *__restrict__ iz,
+                                  const int *__restrict__ perm, int64_t P, float *__restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    int64_t s = perm[i];
+    dst[3 * s] = ix[i]; dst[3 * s + 1] = iy[i]; dst[3 * s + 2] = iz[i];
+}
+__global__ void k_scatter_vidx(const int *__restrict__ slot, const int4 *__restrict__ sfaces, const int *__restrict__ perm,
+                               int64_t P, int *__restrict__ v_idx, int *__restrict__ face) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    int64_t s = perm[i];
+    int4 sf = sfaces[slot[i]];
+    if (v_idx) { v_idx[3 * s] = sf.x; v_idx[3 * s + 1] = sf.y; v_idx[3 * s + 2] = sf.z; }
+    if (face) face[s] = sf.w;
+}
+template <bool F64>
+__global__ void k_scatter_dist(const int *__restrict__ slot, const float4 *__restrict__ cent, const int *__restrict__ perm, int64_t P,
+                               const float *__restrict__ px, const float *__restrict__ py, const float *__restrict__ pz,
+                               const double *__restrict__ px64, const double *__restrict__ py64, const double *__restrict__ pz64,
+                               double *__restrict__ dist) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float4 c = cent[slot[i]];
+    double d2;
+    if (F64) { QueryF64 q; q.set(px64[i], py64[i], pz64[i]); d2 = q.d2(c); }
+    else { QueryF32 q{px[i], py[i], pz[i]}; d2 = q.d2(c); }
+    dist[perm[i]] = sqrt(d2);
+}
+__global__ void k_pack3(const float *__restrict__ src, int M, float4 *__restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+}
+// fixed point -> float32 (one rounding), optionally clearing the accumulator
+__global__ void k_acc_to_float3(unsigned long long *__restrict__ acc, int M, int shift, float *__restrict__ out, int clear) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= M) return;
+    const float inv = (float)pow2d(-shift);
+    for (int c = 0; c < 3; ++c) {
+        out[3 * v + c] = __ll2float_rn((long long)acc[4 * (size_t)v + c]) * inv;
+        if (clear) acc[4 * (size_t)v + c] = 0ull;
+    }
+}
+
+}  // namespace
+
+// ---- launchers ------------------------------------------------------------------------------------
+static Sweep1Args make_args(nw_ctx *h) {
+    Sweep1Args a;
+    a.P = h->P;
+    a.px = h->px; a.py = h->py; a.pz = h->pz;
+    a.px64 = h->px64; a.py64 = h->py64; a.pz64 = h->pz64;
+    a.sx = h->sx; a.sy = h->sy; a.sz = h->sz;
+    if (h->weights_mode == 2) { a.wx = h->wx; a.wy = h->wy; a.wz = h->wz; }
+    else if (h->weights_mode == 1) { a.wx = h->sx; a.wy = h->sy; a.wz = h->sz; }
+    else { a.wx = a.wy = a.wz = nullptr; }
+    a.sinv_scalar = h->sinv_scalar; a.wmean = h->wmean;
+    a.slot = h->slot;
+    a.w0 = h->w0; a.w1 = h->w1; a.w2 = h->w2; a.rx = h->rx; a.ry = h->ry; a.rz = h->rz;
+    a.cent = h->cent; a.posq = h->posq; a.sfaces = h->sfaces; a.boxes = h->boxes; a.tl = h->tl; a.F = h->F;
+    a.acc = h->acc; a.st = h->st;
+    return a;
+}
+
+int nw_launch_sweep1(nw_ctx *h, bool scatter) {
+    if (h->P == 0) return NW_OK;
+    const int B = 128;
+    Sweep1Args a = make_args(h);
+    const int G = nw_grid(h->P, B);
+    if (h->px64) {
+        if (scatter) k_sweep1<true, 1><<<G, B, 0, h->stream>>>(a);
+        else k_sweep1<true, 0><<<G, B, 0, h->stream>>>(a);
+    } else {
+        if (scatter) k_sweep1<false, 1><<<G, B, 0, h->stream>>>(a);
+        else k_sweep1<false, 0><<<G, B, 0, h->stream>>>(a);
+    }
+    NW_LAUNCH_CHECK();
+    return NW_OK;
+}
+
+int nw_launch_sweep2(nw_ctx *h) {
+    const int B = 256;
+    const int G = h->n_partials;
+    k_sweep2<<<G, B, 0, h->stream>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->S0, h->S1, h->S2,
+                                      h->has_mask ? h->pmask : nullptr, h->st, h->partials);
+    NW_LAUNCH_CHECK();
+    k_fold_partials<<<1, 32, 0, h->stream>>>(h->partials, G, h->st);
+    NW_LAUNCH_CHECK();
+    return NW_OK;
+}
+
+int nw_launch_influence(nw_ctx *h) {
+    if (h->P == 0) return NW_OK;
+    k_apply_infl<<<nw_grid(h->P, 256), 256, 0, h->stream>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->acc, h->st);
+    NW_LAUNCH_CHECK();
+    return NW_OK;
+}
+
+static int ensure_scratchP(nw_ctx *h) {
+    if (h->scratchP_elems < 6 * h->P || !h->scratchP) {
+        NW_CHECK(nw_alloc(h, &h->scratchP, (size_t)6 * h->P + 8));
+        h->scratchP_elems = 6 * h->P;
+    }
+    return NW_OK;
+}
+
+static int require_weights(nw_ctx *h, const char *who) {
+    NW_ARG(h->M > 0 && h->px, "points and topology must be set first");
+    if (!h->weights_valid) {
+        h->err = std::string(who) + ": weights not computed (call nw_compute_weights or nw_search first)";
+        return NW_ERR_ARG;
+    }
+    return NW_OK;
+}
+
+extern "C" int nw_compute_weights(nw_ctx *h) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(h->M > 0 && (h->px || h->P == 0), "nw_compute_weights: points and topology must be set first");
+    NW_CUDA(cudaSetDevice(h->device));
+    NW_CHECK(nw_tree_refit(h));
+    NW_CHECK(nw_launch_sweep1(h, false));
+    NW_CUDA(cudaStreamSynchronize(h->stream));
+    h->weights_valid = true;
+    return NW_OK;
+}
+
+extern "C" int nw_get_weights(nw_ctx *h, int32_t *v_idx, float *w, double *dist, int32_t *face) {
+    if (!h) return NW_ERR_ARG;
+    NW_CHECK(require_weights(h, "nw_get_weights"));
+    NW_CUDA(cudaSetDevice(h->device));
+    const int64_t P = h->P;
+    if (P == 0) return NW_OK;
+    const int B = 256;
+    NW_CHECK(ensure_scratchP(h));
+    cudaStream_t s = h->stream;
+    if (v_idx || face) {
+        int *dv = (int *)h->scratchP, *df = dv + 3 * P;
+        k_scatter_vidx<<<nw_grid(P, B), B, 0, s>>>(h->slot, h->sfaces, h->perm, P, v_idx ? dv : nullptr, face ? df : nullptr);
+        NW_LAUNCH_CHECK();
+        if (v_idx) NW_CUDA(cudaMemcpyAsync(v_idx, dv, sizeof(int) * 3 * P, cudaMemcpyDeviceToHost, s));
+        if (face) NW_CUDA(cudaMemcpyAsync(face, df, sizeof(int) * P, cudaMemcpyDeviceToHost, s));
+        NW_CUDA(cudaStreamSynchronize(s));
+    }
+    if (w) {
+        k_scatter_caller3<<<nw_grid(P, B), B, 0, s>>>(h->w0, h->w1, h->w2, h->perm, P, h->scratchP);
+        NW_LAUNCH_CHECK();
+        NW_CUDA(cudaMemcpyAsync(w, h->scratchP, sizeof(float) * 3 * P, cudaMemcpyDeviceToHost, s));
+        NW_CUDA(cudaStreamSynchronize(s));
+    }
+    if (dist) {
+        double *dd = (double *)h->scratchP;
+        if (h->px64) k_scatter_dist<true><<<nw_grid(P, B), B, 0, s>>>(h->slot, h->cent, h->perm, P, h->px, h->py, h->pz, h->px64, h->py64, h->pz64, dd);
+        else k_scatter_dist<false><<<nw_grid(P, B), B, 0, s>>>(h->slot, h->cent, h->perm, P, h->px, h->py, h->pz, nullptr, nullptr, nullptr, dd);
+        NW_LAUNCH_CHECK();
+        NW_CUDA(cudaMemcpyAsync(dist, dd, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
+        NW_CUDA(cudaStreamSynchronize(s));
+    }
+    return NW_OK;
+}
+
+extern "C" int nw_apply_A(nw_ctx *h, const float *x, float *y) {
+    if (!h) return NW_ERR_ARG;
+    NW_CHECK(require_weights(h, "nw_apply_A"));
+    NW_CUDA(cudaSetDevice(h->device));
+    const int64_t P = h->P;
+    if (P == 0) return NW_OK;
+    const int B = 256;
+    cudaStream_t s = h->stream;
+    NW_CHECK(ensure_scratchP(h));
+    float4 *xq = nullptr;
+    NW_CHECK(nw_alloc(h, &xq, (size_t)h->M));
+    NW_CUDA(cudaMemcpyAsync(h->scratchM, x, sizeof(float) * 3 * h->M, cudaMemcpyHostToDevice, s));
+    k_pack3<<<nw_grid(h->M, B), B, 0, s>>>(h->scratchM, h->M, xq);
+    NW_LAUNCH_CHECK();
+    float *yx = h->scratchP, *yy = yx + P, *yz = yy + P, *out = yz + P;
+    k_apply_A<<<nw_grid(P, B), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, xq, yx, yy, yz);
+    NW_LAUNCH_CHECK();
+    k_scatter_caller3<<<nw_grid(P, B), B, 0, s>>>(yx, yy, yz, h->perm, P, out);
+    NW_LAUNCH_CHECK();
+    NW_CUDA(cudaMemcpyAsync(y, out, sizeof(float) * 3 * P, cudaMemcpyDeviceToHost, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+    nw_free(&xq);
+    return NW_OK;
+}
+
+int nw_apply_AH_device(nw_ctx *h, const float *rx, const float *ry, const float *rz, double bound, float *out3M) {
+    // shift from an a-priori bound on |w r| summed over every rank's points
+    const int B = 256;
+    cudaStream_t s = h->stream;
+    double tot = bound * (double)std::max<int64_t>(h->P_global, 1);
+    int e = 0;
+    frexp(tot > 0 ? tot : 1.0, &e);
+    int shift = std::max(-60, std::min(40, 61 - e));
+    NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * h->M, s));
+    if (h->P) {
+        k_apply_AH<<<nw_grid(h->P, B), B, 0, s>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, rx, ry, rz, h->acc, shift);
+        NW_LAUNCH_CHECK();
+    }
+    NW_CHECK(nw_allreduce_acc(h));
+    k_acc_to_float3<<<nw_grid(h->M, B), B, 0, s>>>(h->acc, h->M, shift, out3M, 1);
+    NW_LAUNCH_CHECK();
+    return NW_OK;
+}
+
+__global__ void k_absmax(const float *__restrict__ v, int64_t n, float *out) {
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float a = fabsf(v[i]);
+        if (!(a <= FLT_MAX)) a = FLT_MAX;
+        m = fmaxf(m, a);
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax((int *)out, __float_as_int(m));
+}
+
+int nw_comm_allreduce_host_doubles(nw_ctx *h, double *vals, int n);
+
+extern "C" int nw_apply_AH(nw_ctx *h, const float *r, float *y) {
+    if (!h) return NW_ERR_ARG;
+    NW_CHECK(require_weights(h, "nw_apply_AH"));
+    NW_CUDA(cudaSetDevice(h->device));
+    const int64_t P = h->P;
+    const int B = 256;
+    cudaStream_t s = h->stream;
+    NW_CHECK(ensure_scratchP(h));
+    float *in = h->scratchP, *rx = in + 3 * P, *ry = rx + P, *rz = ry + P;
+    float *d_max = nullptr;
+    NW_CHECK(nw_alloc(h, &d_max, 1));
+    NW_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), s));
+    if (P) {
+        NW_CUDA(cudaMemcpyAsync(in, r, sizeof(float) * 3 * P, cudaMemcpyHostToDevice, s));
+        k_gather_sorted3<<<nw_grid(P, B), B, 0, s>>>(in, h->perm, P, rx, ry, rz);
+        NW_LAUNCH_CHECK();
+        k_absmax<<<std::min(nw_grid(3 * P, B), 592), B, 0, s>>>(in, 3 * P, d_max);
+        NW_LAUNCH_CHECK();
+    }
+    float mx = 0.f;
+    NW_CUDA(cudaMemcpyAsync(&mx, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+    nw_free(&d_max);
+    double bound = mx;
+    if (h->nranks > 1) {
+        std::vector<double> slots(h->nranks, 0.0);
+        slots[h->rank] = bound;
+        NW_CHECK(nw_comm_allreduce_host_doubles(h, slots.data(), h->nranks));
+        for (double v : slots) bound = std::max(bound, v);
+    }
+    NW_CHECK(nw_apply_AH_device(h, rx, ry, rz, bound, h->scratchM));
+    NW_CUDA(cudaMemcpyAsync(y, h->scratchM, sizeof(float) * 3 * h->M, cudaMemcpyDeviceToHost, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+    return NW_OK;
+}
+
+extern "C" int nw_get_res(nw_ctx *h, float *res) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(h->px || h->P == 0, "nw_get_res: no points");
+    NW_CUDA(cudaSetDevice(h->device));
+    const int64_t P = h->P;
+    if (P == 0) return NW_OK;
+    NW_CHECK(ensure_scratchP(h));
+    k_scatter_caller3<<<nw_grid(P, 256), 256, 0, h->stream>>>(h->rx, h->ry, h->rz, h->perm, P, h->scratchP);
+    NW_LAUNCH_CHECK();
+    NW_CUDA(cudaMemcpyAsync(res, h->scratchP, sizeof(float) * 3 * P, cudaMemcpyDeviceToHost, h->stream));
+    NW_CUDA(cudaStreamSynchronize(h->stream));
+    return NW_OK;
+}
+
+// ---- measurement hook (benchhook.cu) ---------------------------------------------------------------
+int nw_bench_launch(nw_ctx *h, const char *name) {
+    const int B = 256;
+    const int64_t P = h->P;
+    cudaStream_t s = h->stream;
+    std::string n(name);
+    if (n == "apply_A") {
+        NW_CHECK(ensure_scratchP(h));
+        float *yx = h->scratchP, *yy = yx + P, *yz = yy + P;
+        k_apply_A<<<nw_grid(P, B), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->posq, yx, yy, yz);
+    } else if (n == "apply_AH") {
+        k_apply_AH<<<nw_grid(P, B), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->acc, 20);
+    } else if (n == "sweep1") {
+        return nw_launch_sweep1(h, true);
+    } else if (n == "nn_weights") {
+        return nw_launch_sweep1(h, false);
+    } else if (n == "sweep2") {
+        return nw_launch_sweep2(h);
+    } else if (n == "mesh_prior") {
+        return nw_launch_mesh_prior(h, true);
+    } else if (n == "refit") {
+        return nw_tree_refit(h);
+    } else {
+        h->err = "nw_bench_kernel: unknown kernel name " + n;
+        return NW_ERR_ARG;
+    }
+    NW_LAUNCH_CHECK();
+    return NW_OK;
+}

@@ -1,0 +1,273 @@
+// tree.cu -- mesh upload and the Morton-sorted AABB pyramid over face centroids.
+//
+// The reference finds each point's nearest face centroid with a host kd-tree rebuilt every iteration
+// (mesh_conj_grad.py:443-454).  Here the faces are Morton-sorted ONCE per remesh block (topology is
+// fixed inside a block); every iteration only re-evaluates the centroids at the current f and refits
+// the boxes: leaves are NW_LEAF consecutive sorted centroids, interior nodes are NW_FAN consecutive
+// children, so the hierarchy is implicit (no child pointers) and a node's children are one 128 B line.
+#include <cub/cub.cuh>
+#include <cfloat>
+#include "common.cuh"
+
+namespace {
+
+// centroid exactly as numpy evaluates fv[faces].mean(1) in float32: ((a+b)+c)/3
+__device__ __forceinline__ float3 centroid_f32(const float4 a, const float4 b, const float4 c) {
+    float3 r;
+    r.x = __fdiv_rn(__fadd_rn(__fadd_rn(a.x, b.x), c.x), 3.0f);
+    r.y = __fdiv_rn(__fadd_rn(__fadd_rn(a.y, b.y), c.y), 3.0f);
+    r.z = __fdiv_rn(__fadd_rn(__fadd_rn(a.z, b.z), c.z), 3.0f);
+    return r;
+}
+
+__global__ void k_pack_vec3(const float *__restrict__ src, int M, float4 *__restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+}
+
+__global__ void k_unpack_vec3(const float4 *__restrict__ src, int M, float *__restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) { float4 v = src[i]; dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z; }
+}
+
+// (M,20) row-major -> k-major + valence (entries are -1 terminated, mesh_conj_grad.py:50-54)
+__global__ void k_transpose_nbr(const int *__restrict__ nbr, int M, int *__restrict__ nbrT, int *__restrict__ valence) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= M) return;
+    int n = 0;
+    bool open = true;
+    for (int k = 0; k < NW_NEIGHBORSIZE; ++k) {
+        int t = nbr[(size_t)v * NW_NEIGHBORSIZE + k];
+        if (t < 0) open = false;
+        if (open) ++n;
+        nbrT[(size_t)k * M + v] = open ? t : -1;
+    }
+    valence[v] = n;
+}
+
+__global__ void k_face_bbox(const int *__restrict__ faces, const float4 *__restrict__ pos, int F, int *__restrict__ out6) {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        float3 c = centroid_f32(pos[faces[3 * f]], pos[faces[3 * f + 1]], pos[faces[3 * f + 2]]);
+        float v[3] = {c.x, c.y, c.z};
+        for (int a = 0; a < 3; ++a) if (v[a] == v[a]) { lo[a] = fminf(lo[a], v[a]); hi[a] = fmaxf(hi[a], v[a]); }
+    }
+    for (int a = 0; a < 3; ++a)
+        for (int o = 16; o; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int a = 0; a < 3; ++a) {
+            int l = __float_as_int(lo[a]); l = l >= 0 ? l : l ^ 0x7fffffff;
+            int u = __float_as_int(hi[a]); u = u >= 0 ? u : u ^ 0x7fffffff;
+            atomicMin(out6 + a, l);
+            atomicMax(out6 + 3 + a, u);
+        }
+}
+
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+    v &= 0x3ffu;
+    v = (v | v << 16) & 0x30000ffu;
+    v = (v | v << 8) & 0x300f00fu;
+    v = (v | v << 4) & 0x30c30c3u;
+    v = (v | v << 2) & 0x9249249u;
+    return v;
+}
+
+__global__ void k_face_keys(const int *__restrict__ faces, const float4 *__restrict__ pos, int F, float3 lo, float inv,
+                            unsigned *__restrict__ keys, int *__restrict__ idx) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    float3 c = centroid_f32(pos[faces[3 * f]], pos[faces[3 * f + 1]], pos[faces[3 * f + 2]]);
+    unsigned qx = (unsigned)fminf(fmaxf((c.x - lo.x) * inv, 0.f), 1023.f);
+    unsigned qy = (unsigned)fminf(fmaxf((c.y - lo.y) * inv, 0.f), 1023.f);
+    unsigned qz = (unsigned)fminf(fmaxf((c.z - lo.z) * inv, 0.f), 1023.f);
+    keys[f] = spread10(qx) | (spread10(qy) << 1) | (spread10(qz) << 2);
+    idx[f] = f;
+}
+
+__global__ void k_sorted_faces(const int *__restrict__ faces, const int *__restrict__ order, int F, int4 *__restrict__ sfaces) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F) return;
+    int f = order[i];
+    sfaces[i] = make_int4(faces[3 * f], faces[3 * f + 1], faces[3 * f + 2], f);
+}
+
+// centroids at the current f (sorted order) + leaf boxes: 8 lanes cooperate on one leaf
+__global__ void k_refit_leaves(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F,
+                               float4 *__restrict__ cent, Box *__restrict__ leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 c = make_float3(0.f, 0.f, 0.f);
+    bool live = i < F;
+    if (live) {
+        int4 sf = sfaces[i];
+        c = centroid_f32(pos[sf.x], pos[sf.y], pos[sf.z]);
+        cent[i] = make_float4(c.x, c.y, c.z, __int_as_float(sf.w));
+    }
+    float lo[3] = {live ? c.x : FLT_MAX, live ? c.y : FLT_MAX, live ? c.z : FLT_MAX};
+    float hi[3] = {live ? c.x : -FLT_MAX, live ? c.y : -FLT_MAX, live ? c.z : -FLT_MAX};
+    for (int a = 0; a < 3; ++a)
+        for (int o = NW_LEAF / 2; o; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    if ((threadIdx.x & (NW_LEAF - 1)) == 0 && live) {
+        Box b;
+        b.lo = make_float4(lo[0], lo[1], lo[2], 0.f);
+        b.hi = make_float4(hi[0], hi[1], hi[2], 0.f);
+        leaf[i / NW_LEAF] = b;
+    }
+}
+
+// one interior level: node i = union of children [4i, 4i+4)
+__global__ void k_refit_level(const Box *__restrict__ child, int n_child, Box *__restrict__ parent, int n_parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_parent) return;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int k = 0; k < NW_FAN; ++k) {
+        int c = NW_FAN * i + k;
+        if (c < n_child) {
+            Box b = child[c];
+            lo[0] = fminf(lo[0], b.lo.x); lo[1] = fminf(lo[1], b.lo.y); lo[2] = fminf(lo[2], b.lo.z);
+            hi[0] = fmaxf(hi[0], b.hi.x); hi[1] = fmaxf(hi[1], b.hi.y); hi[2] = fmaxf(hi[2], b.hi.z);
+        }
+    }
+    Box b;
+    b.lo = make_float4(lo[0], lo[1], lo[2], 0.f);
+    b.hi = make_float4(hi[0], hi[1], hi[2], 0.f);
+    parent[i] = b;
+}
+
+inline float ordered_to_float(int v) {
+    v = v >= 0 ? v : v ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+}
+
+}  // namespace
+
+extern "C" int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces,
+                               const int32_t *nbr, const uint8_t *valid, int M, int F) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(M > 0 && F > 0, "nw_set_topology: empty mesh");
+    NW_ARG(pos && nrm && faces && nbr, "nw_set_topology: NULL array");
+    NW_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int B = 256;
+    h->M = M; h->F = F;
+    h->weights_valid = false;
+    NW_CHECK(nw_alloc(h, &h->posq, (size_t)M)); NW_CHECK(nw_alloc(h, &h->nrmq, (size_t)M));
+    NW_CHECK(nw_alloc(h, &h->faces, (size_t)3 * F));
+    NW_CHECK(nw_alloc(h, &h->nbrT, (size_t)NW_NEIGHBORSIZE * M)); NW_CHECK(nw_alloc(h, &h->valence, (size_t)M));
+    NW_CHECK(nw_alloc(h, &h->valid, (size_t)M));
+    NW_CHECK(nw_alloc(h, &h->acc, (size_t)4 * M));
+    NW_CHECK(nw_alloc(h, &h->S0, (size_t)M)); NW_CHECK(nw_alloc(h, &h->S1, (size_t)M)); NW_CHECK(nw_alloc(h, &h->S2, (size_t)M));
+    NW_CHECK(nw_alloc(h, &h->fdef, (size_t)3 * M));
+    NW_CHECK(nw_alloc(h, &h->scratchM, (size_t)3 * M));
+    NW_CHECK(nw_alloc(h, &h->sfaces, (size_t)F)); NW_CHECK(nw_alloc(h, &h->cent, (size_t)F));
+
+    // staging: positions / normals through scratchM, neighbour table through a temporary
+    int *d_nbr = nullptr;
+    NW_CHECK(nw_alloc(h, &d_nbr, (size_t)NW_NEIGHBORSIZE * M));
+    NW_CUDA(cudaMemcpyAsync(h->scratchM, pos, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+    k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->posq);
+    NW_CUDA(cudaStreamSynchronize(s));
+    NW_CUDA(cudaMemcpyAsync(h->scratchM, nrm, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+    k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->nrmq);
+    NW_CUDA(cudaMemcpyAsync(h->faces, faces, sizeof(int) * 3 * F, cudaMemcpyHostToDevice, s));
+    NW_CUDA(cudaMemcpyAsync(d_nbr, nbr, sizeof(int) * NW_NEIGHBORSIZE * M, cudaMemcpyHostToDevice, s));
+    k_transpose_nbr<<<nw_grid(M, B), B, 0, s>>>(d_nbr, M, h->nbrT, h->valence);
+    h->launches += 3;
+    if (valid) NW_CUDA(cudaMemcpyAsync(h->valid, valid, M, cudaMemcpyHostToDevice, s));
+    else NW_CUDA(cudaMemsetAsync(h->valid, 1, M, s));
+    NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * M, s));
+    NW_CUDA(cudaMemsetAsync(h->S0, 0, sizeof(float4) * M, s));
+    NW_CUDA(cudaMemsetAsync(h->S1, 0, sizeof(float4) * M, s));
+    NW_CUDA(cudaMemsetAsync(h->S2, 0, sizeof(float4) * M, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+    nw_free(&d_nbr);
+    // nearest-face slots refer to the previous block's sort order
+    if (h->slot && h->P) NW_CUDA(cudaMemsetAsync(h->slot, 0xff, sizeof(int) * h->P, s));
+    return nw_tree_build(h);
+}
+
+int nw_tree_build(nw_ctx *h) {
+    cudaStream_t s = h->stream;
+    const int B = 256, F = h->F;
+    int *d_bbox = nullptr, *idx = nullptr, *order = nullptr;
+    unsigned *keys = nullptr, *keys2 = nullptr;
+    NW_CHECK(nw_alloc(h, &d_bbox, 6));
+    int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+    NW_CUDA(cudaMemcpyAsync(d_bbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    k_face_bbox<<<std::min(nw_grid(F, B), 148 * 4), B, 0, s>>>(h->faces, h->posq, F, d_bbox);
+    int bb[6];
+    NW_CUDA(cudaMemcpyAsync(bb, d_bbox, sizeof(bb), cudaMemcpyDeviceToHost, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = ordered_to_float(bb[a]); hi[a] = ordered_to_float(bb[3 + a]); }
+    float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    float inv = (ext > 0.f && ext < FLT_MAX) ? 1023.f / ext : 0.f;
+    NW_CHECK(nw_alloc(h, &keys, (size_t)F)); NW_CHECK(nw_alloc(h, &keys2, (size_t)F));
+    NW_CHECK(nw_alloc(h, &idx, (size_t)F)); NW_CHECK(nw_alloc(h, &order, (size_t)F));
+    k_face_keys<<<nw_grid(F, B), B, 0, s>>>(h->faces, h->posq, F, make_float3(lo[0], lo[1], lo[2]), inv, keys, idx);
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, keys2, idx, order, F, 0, 30, s);
+    if (tmp > h->cub_tmp_bytes) { NW_CHECK(nw_alloc(h, (char **)&h->cub_tmp, tmp)); h->cub_tmp_bytes = tmp; }
+    NW_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, keys, keys2, idx, order, F, 0, 30, s));
+    k_sorted_faces<<<nw_grid(F, B), B, 0, s>>>(h->faces, order, F, h->sfaces);
+    h->launches += 7;
+    // level sizes
+    TreeLevels &tl = h->tl;
+    tl.n_levels = 0;
+    int n = (F + NW_LEAF - 1) / NW_LEAF, off = 0;
+    while (true) {
+        NW_ARG(tl.n_levels < NW_MAX_LEVELS, "nw_tree_build: too many levels");
+        tl.count[tl.n_levels] = n; tl.offset[tl.n_levels] = off; tl.n_levels++;
+        off += n;
+        if (n <= NW_FAN) break;
+        n = (n + NW_FAN - 1) / NW_FAN;
+    }
+    NW_CHECK(nw_alloc(h, &h->boxes, (size_t)off));
+    NW_CUDA(cudaStreamSynchronize(s));
+    nw_free(&d_bbox); nw_free(&idx); nw_free(&order); nw_free(&keys); nw_free(&keys2);
+    return nw_tree_refit(h);
+}
+
+int nw_tree_refit(nw_ctx *h) {
+    cudaStream_t s = h->stream;
+    const int B = 256;
+    const TreeLevels &tl = h->tl;
+    k_refit_leaves<<<nw_grid(h->F, B), B, 0, s>>>(h->sfaces, h->posq, h->F, h->cent, h->boxes);
+    NW_LAUNCH_CHECK();
+    for (int l = 1; l < tl.n_levels; ++l) {
+        k_refit_level<<<nw_grid(tl.count[l], B), B, 0, s>>>(h->boxes + tl.offset[l - 1], tl.count[l - 1],
+                                                             h->boxes + tl.offset[l], tl.count[l]);
+        NW_LAUNCH_CHECK();
+    }
+    return NW_OK;
+}
+
+extern "C" int nw_set_positions(nw_ctx *h, const float *pos) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(h->M > 0, "nw_set_positions: no topology");
+    NW_CUDA(cudaSetDevice(h->device));
+    NW_CUDA(cudaMemcpyAsync(h->scratchM, pos, sizeof(float) * 3 * h->M, cudaMemcpyHostToDevice, h->stream));
+    k_pack_vec3<<<nw_grid(h->M, 256), 256, 0, h->stream>>>(h->scratchM, h->M, h->posq);
+    NW_LAUNCH_CHECK();
+    NW_CUDA(cudaStreamSynchronize(h->stream));
+    h->weights_valid = false;
+    return NW_OK;
+}
+
+extern "C" int nw_get_positions(nw_ctx *h, float *pos) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(h->M > 0, "nw_get_positions: no topology");
+    NW_CUDA(cudaSetDevice(h->device));
+    k_unpack_vec3<<<nw_grid(h->M, 256), 256, 0, h->stream>>>(h->posq, h->M, h->scratchM);
+    NW_LAUNCH_CHECK();
+    NW_CUDA(cudaMemcpyAsync(pos, h->scratchM, sizeof(float) * 3 * h->M, cudaMemcpyDeviceToHost, h->stream));
+    NW_CUDA(cudaStreamSynchronize(h->stream));
+    return NW_OK;
+}

@@ -1,0 +1,246 @@
+"""GPU parity tests proper: libnanowrap.so (through the C ABI via the ctypes shim) against the CPU
+oracle on the same seeded inputs.  Tolerances are stated per check."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import make_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _clone(mesh):
+    return copy.deepcopy(mesh)
+
+
+def _oracle(mesh, pts):
+    from oracle import nanowrap_oracle as orc
+    return orc.OracleConjGrad(mesh, pts)
+
+
+def _gpu(mesh, pts):
+    from ch_shrinkwrap_b200.mesh_conj_grad import ShrinkwrapMeshConjGrad
+    cg = ShrinkwrapMeshConjGrad(mesh, pts)
+    mesh.cg = cg
+    return cg
+
+
+def _weights_parity(mesh, pts):
+    mo, mg = _clone(mesh), _clone(mesh)
+    oc = _oracle(mo, pts)
+    oc.f = oc.vertices.copy().ravel()
+    v_idx_o, w_o = oc.compute_weights(oc.f)
+    g = _gpu(mg, pts)
+    v_idx_g, w_g = g.compute_weights()
+    face_g = g.nearest_face
+    # nearest-face index: bit-exact (fp64 ties -> any index at the same fp64 distance is accepted)
+    diff = np.flatnonzero(face_g != oc.nearest)
+    if len(diff):
+        fv = oc.f.reshape(-1, 3)
+        cen = fv[mo.faces].mean(1).astype(np.float64)
+        p64 = pts.astype(np.float64)
+        d_g = ((p64[diff] - cen[face_g[diff]]) ** 2)
+        d_o = ((p64[diff] - cen[oc.nearest[diff]]) ** 2)
+        d_g = (d_g[:, 0] + d_g[:, 1]) + d_g[:, 2]
+        d_o = (d_o[:, 0] + d_o[:, 1]) + d_o[:, 2]
+        assert np.array_equal(d_g, d_o), 'nearest-face mismatch that is not an exact fp64 tie'
+    ties = len(diff)
+    same = face_g == oc.nearest
+    assert np.array_equal(v_idx_g[same], v_idx_o[same])
+    assert np.array_equal(w_g[same], w_o[same]), 'weights must be bit-identical'      # tolerance: 0
+    assert np.array_equal(g.d[:, 0][same], oc.d[:, 0][same]), 'distances must be bit-identical (fp64)'
+    return ties
+
+
+def test_nearest_face_and_weights_f32():
+    mesh, pts, sig = make_case(n_points=20000, n_geo=10, seed=11)
+    assert _weights_parity(mesh, pts) == 0
+
+
+def test_nearest_face_and_weights_f64_points():
+    mesh, pts, sig = make_case(n_points=6000, n_geo=7, seed=12, dtype=np.float64)
+    assert pts.dtype == np.float64
+    assert _weights_parity(mesh, pts) == 0
+
+
+def test_nearest_face_far_and_inside_points():
+    # points far outside, at the centre (worst case for pruning) and on vertices
+    mesh, pts, sig = make_case(n_points=3000, n_geo=5, seed=13)
+    extra = np.array([[0, 0, 0], [1e4, -2e4, 3e4], [-1e5, 0, 0]], np.float32)
+    pts = np.concatenate([pts, extra, mesh.vertices[:50].copy()], 0)
+    _weights_parity(mesh, pts)
+
+
+def test_forward_and_adjoint():
+    mesh, pts, sig = make_case(n_points=8000, n_geo=6, seed=14)
+    mo, mg = _clone(mesh), _clone(mesh)
+    oc = _oracle(mo, pts)
+    oc.f = oc.vertices.copy().ravel()
+    oc.w = oc.compute_weights(oc.f)
+    oc._prev_loopcount = oc.loopcount
+    g = _gpu(mg, pts)
+    g.compute_weights()
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(3 * oc.M).astype(np.float32)
+    r = rng.standard_normal(3 * len(pts)).astype(np.float32)
+    # A: same float32 operations in the same order -> bit-identical
+    assert np.array_equal(g.Afunc(x), oc.Afunc(x))
+    # AH: reference sums float32 sequentially in point order; ours is an exact fixed-point sum rounded once.
+    # tolerance: |diff| <= 1e-5 * sum_p |w r| per vertex component (float32 reassociation bound)
+    ah_g, ah_o = g.Ahfunc(r), oc.Ahfunc(r)
+    v_idx, w = oc.w
+    absum = np.zeros((oc.M, 3))
+    for j in range(3):
+        np.add.at(absum, v_idx[:, j], np.abs(w[:, j][:, None] * r.reshape(-1, 3)))
+    assert np.all(np.abs(ah_g - ah_o).reshape(-1, 3) <= 1e-5 * absum + 1e-30)
+    # exact check against a float64 scatter: rounding once must be within half an ulp-ish
+    ex = np.zeros((oc.M, 3))
+    for j in range(3):
+        np.add.at(ex, v_idx[:, j], (w[:, j][:, None] * r.reshape(-1, 3)).astype(np.float32).astype(np.float64))
+    assert np.allclose(ah_g.reshape(-1, 3), ex, rtol=2e-7, atol=1e-9 * np.abs(r).max())
+    # adjointness <Ax, r> == <x, AHr> (fp64 accumulate), relative 1e-5
+    lhs = np.dot(g.Afunc(x).astype(np.float64), r.astype(np.float64))
+    rhs = np.dot(x.astype(np.float64), ah_g.astype(np.float64))
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
+    # point influence, tolerance rel 1e-5
+    pi_o = oc.point_influence() if hasattr(oc, 'res') else None
+    oc.res = np.zeros(3 * len(pts), np.float32)
+    pi_o = oc.point_influence()
+    assert np.allclose(g.point_influence(), pi_o, rtol=1e-5, atol=1e-7)
+
+
+def test_determinism_adjoint_bitwise():
+    mesh, pts, sig = make_case(n_points=30000, n_geo=6, seed=15)
+    g = _gpu(mesh, pts)
+    g.compute_weights()
+    r = np.random.default_rng(1).standard_normal(3 * len(pts)).astype(np.float32)
+    a = g.Ahfunc(r)
+    for _ in range(3):
+        assert np.array_equal(a, g.Ahfunc(r))
+
+
+def test_ncc_prior():
+    mesh, pts, sig = make_case(n_points=8000, n_geo=6, seed=16)
+    mo, mg = _clone(mesh), _clone(mesh)
+    oc = _oracle(mo, pts)
+    oc.f = oc.vertices.copy().ravel()
+    oc.w = oc.compute_weights(oc.f)
+    oc.res = np.zeros(3 * len(pts), np.float32)
+    fd_o = oc.ncc()
+    g = _gpu(mg, pts)
+    g.compute_weights()
+    fd_g = g._ncc()
+    # tolerance: relative 1e-6 of the coordinate scale (point influence differs at float32 rounding level)
+    assert np.allclose(fd_g, fd_o, rtol=0, atol=1e-6 * np.abs(fd_o).max())
+
+
+@pytest.mark.parametrize('n_iters', [1, 2, 7])
+def test_search_fixed_iterations(n_iters):
+    mesh, pts, sig = make_case(n_points=10000, n_geo=6, seed=17)
+    mo, mg = _clone(mesh), _clone(mesh)
+    s = (1.0 / sig.ravel()).astype(np.float32)
+    oc = _oracle(mo, pts)
+    vo = oc.search(pts, lams=[10.0], num_iters=n_iters, sigma_inv=s)
+    g = _gpu(mg, pts)
+    vg = g.search(pts, lams=[10.0], num_iters=n_iters, sigma_inv=s)
+    # final mesh: max vertex displacement (upper bound on symmetric Hausdorff) <= 0.01 nm
+    disp = np.sqrt(((vg.astype(np.float64) - vo) ** 2).sum(1)).max()
+    assert disp <= 1e-2, disp
+    assert np.array_equal(mg._vertices['position'], vg)
+    assert g.loopcount == n_iters
+    assert np.allclose(np.array(g.tests, np.float64), np.array(oc.tests, np.float64), rtol=1e-3, atol=1e-5)
+    assert np.allclose(g.ress, oc.ress, rtol=1e-4)
+    assert np.allclose(g.S, oc.S, rtol=1e-3, atol=1e-3 * np.abs(oc.S).max())
+    assert np.allclose(g.res, oc.res, rtol=1e-4, atol=1e-4 * np.abs(oc.res).max())
+
+
+def test_search_scalar_sigma_and_continue():
+    # scalar sigma is passed through un-inverted (_membrane_mesh.pyx:1460-1461); calling search twice continues
+    mesh, pts, sig = make_case(n_points=5000, n_geo=5, seed=18)
+    mo, mg = _clone(mesh), _clone(mesh)
+    oc = _oracle(mo, pts)
+    g = _gpu(mg, pts)
+    for _ in range(2):
+        vo = oc.search(pts, lams=[5.0], num_iters=3, sigma_inv=10.0)
+        vg = g.search(pts, lams=[5.0], num_iters=3, sigma_inv=10.0)
+    disp = np.sqrt(((vg.astype(np.float64) - vo) ** 2).sum(1)).max()
+    assert disp <= 1e-2, disp
+    assert len(g.tests) == 6
+
+
+def test_search_with_zero_weights_mask():
+    mesh, pts, sig = make_case(n_points=5000, n_geo=5, seed=19)
+    mo, mg = _clone(mesh), _clone(mesh)
+    s = (1.0 / sig.ravel()).astype(np.float32)
+    wts = s.copy()
+    wts[::7] = 0.0
+    oc = _oracle(mo, pts)
+    vo = oc.search(pts, lams=[5.0], num_iters=3, sigma_inv=s, weights=wts)
+    g = _gpu(mg, pts)
+    vg = g.search(pts, lams=[5.0], num_iters=3, sigma_inv=s, weights=wts)
+    disp = np.sqrt(((vg.astype(np.float64) - vo) ** 2).sum(1)).max()
+    assert disp <= 1e-2, disp
+
+
+def test_deleted_vertices_stay_put():
+    mesh, pts, sig = make_case(n_points=4000, n_geo=5, seed=20)
+    # append two unused (deleted) vertex rows: halfedge == -1, no neighbours (mesh_conj_grad.py:44)
+    from ch_shrinkwrap_b200.minimesh import VERTEX_DTYPE
+    extra = np.zeros(2, VERTEX_DTYPE)
+    extra['halfedge'] = -1
+    extra['neighbors'] = -1
+    extra['position'] = [[1., 2., 3.], [4., 5., 6.]]
+    mesh._vertices = np.concatenate([mesh._vertices, extra])
+    mo, mg = _clone(mesh), _clone(mesh)
+    s = (1.0 / sig.ravel()).astype(np.float32)
+    vo = _oracle(mo, pts).search(pts, lams=[5.0], num_iters=3, sigma_inv=s)
+    vg = _gpu(mg, pts).search(pts, lams=[5.0], num_iters=3, sigma_inv=s)
+    assert np.array_equal(vg[-2:], extra['position'])
+    assert np.sqrt(((vg.astype(np.float64) - vo) ** 2).sum(1)).max() <= 1e-2
+
+
+def test_curvature_sphere_and_plane_known_answers():
+    # the reference's own pins: tests/test_membrane_mesh.py:50,64,73,88
+    from ch_shrinkwrap_b200 import minimesh
+    from ch_shrinkwrap_b200.membrane_mesh import curvature_grad
+    for R, n in [(37.0, 8), (100.0, 16)]:
+        m = minimesh.sphere_mesh(R, n)
+        c = curvature_grad(m)
+        np.testing.assert_almost_equal(np.nanmean(c['H']), 1.0 / R, decimal=2)
+        np.testing.assert_almost_equal(np.nanmean(c['K']), 1.0 / R ** 2, decimal=4)
+    pl = minimesh.planar_mesh(17.0, 4)
+    c = curvature_grad(pl)
+    assert abs(np.nanmean(c['H'])) < 1e-6 and abs(np.nanmedian(c['K'])) < 1e-6
+
+
+def test_curvature_vs_oracle():
+    from ch_shrinkwrap_b200 import minimesh, synth
+    from ch_shrinkwrap_b200.membrane_mesh import curvature_grad
+    from oracle import nanowrap_oracle as orc
+    shape = synth.two_lobed()
+    m = synth.star_mesh(shape, 12, scale=1.0)
+    nv = int((m._vertices['halfedge'] != -1).sum())
+    u = np.random.default_rng(5).random(3 * nv)
+    o = orc.curvature_grad(m, jitter_u=u)
+    g = curvature_grad(m, jitter_u=u)
+    for k in ('k0', 'k1', 'e0', 'e1', 'H', 'K', 'E', 'dE_neighbors'):
+        assert np.array_equal(g[k], o[k], equal_nan=True), k          # IEEE ops only: bit-exact
+    for k in ('dH', 'dK', 'pE', 'dEdN'):                                # atan2/sin/cos/exp: rel 1e-5
+        assert np.allclose(g[k], o[k], rtol=1e-5, atol=1e-5 * np.nanmax(np.abs(o[k])), equal_nan=True), k
+
+
+def test_ring_regularisers_bitwise():
+    from oracle import nanowrap_oracle as orc
+    mesh, pts, sig = make_case(n_points=100, n_geo=5, seed=21)
+    g = _gpu(mesh, pts)
+    nb = g.vertex_neighbors
+    rng = np.random.default_rng(2)
+    f = rng.standard_normal(3 * g.M).astype(np.float32)
+    ref = mesh.vertices.astype(np.float32).ravel().copy()
+    g.f = ref
+    assert np.array_equal(g.Lfunc(f), orc.l_func(f, nb))
+    assert np.array_equal(g.Lhfunc(f), orc.lh_func(f, nb))
+    assert np.array_equal(g.Lfunc3(f), orc.lw_func(f, nb, ref))
+    assert np.array_equal(g.Lhfunc3(f), orc.lhw_func(f, nb, ref))
+    assert np.array_equal(g.wfunc(f), f * orc.vertex_area_weights(ref, nb))
