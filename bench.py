@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- NanoWrap CG shrinkwrap hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c1]
+
+A *step* is one CG iteration of ``ShrinkwrapMeshConjGrad.search`` over the rank's whole point shard
+(nearest-face rebuild included, as the reference rebuilds it every iteration; host remesh excluded,
+SURVEY 8d).  Default workload = BASELINE.json configs[2], the one the north-star target is quoted on:
+two-lobed necked shape, 10 M localisations per GPU, 501 762-vertex mesh (weak scaling: points per GPU
+fixed, mesh replicated).  Iterations run in blocks of 5 (remesh_frequency) like the reference's driver;
+each block starts from a fresh topology upload, so the nearest-face search starts cold once per block.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (points per GPU, geodesic frequency n -> 10 n^2 + 2 vertices, curvature_weight, block length)
+    'c1': dict(points=10_000, geo=8, curvature_weight=20.0, block=10, desc='config0: ~10k localisations, 642-vertex mesh'),
+    'c2': dict(points=1_000_000, geo=71, curvature_weight=10.0, block=5, desc='config1: 1M localisations, 50 412-vertex mesh'),
+    'c3': dict(points=10_000_000, geo=224, curvature_weight=10.0, block=5, desc='config2: 10M localisations, 501 762-vertex two-lobed mesh'),
+}
+REFERENCE_SAMPLE = 'c2'   # bounded CPU sample: same shape, same 20 localisations per vertex, 1/10 of c3
+STAGES = ['refit', 'shift', 'sweep1', 'allreduce_acc', 'mesh_prior', 'sweep2', 'allreduce_scalars', 'solve_update']
+
+
+def build_workload(name, seed):
+    from ch_shrinkwrap_b200 import minimesh, synth
+    from ch_shrinkwrap_b200.membrane_mesh import MembraneMesh
+    cfg = WORKLOADS[name]
+    shape = synth.two_lobed()
+    v, f = minimesh.geodesic_sphere(cfg['geo'])
+    r = synth.radial_surface(shape, v, n_bisect=32)
+    pts, sig = synth.mesh_surface_cloud(v * r[:, None], f, cfg['points'], seed=seed)
+    mesh = MembraneMesh(v * (1.2 * r)[:, None], f, kc=1.0, step_size=cfg['curvature_weight'],
+                        remesh_frequency=cfg['block'], delaunay_remesh_frequency=0)
+    return mesh, pts, sig, cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [l.strip().split(', ') for l in open(self.path) if l.strip()]
+            os.unlink(self.path)
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            reasons = set()
+            for r in rows:
+                if len(r) >= 9:
+                    for k, nme in enumerate(names):
+                        if r[5 + k].strip().lower().startswith('active'):
+                            reasons.add(nme)
+            if sm:
+                out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(rows[0][2]), reasons=sorted(reasons), samples=len(sm))
+        except Exception:
+            pass
+        return out
+
+
+def run_blocks(mesh, pts, s_inv, lam, n_iters, block, handle_profile=True):
+    """n_iters CG iterations in blocks: new solver object + topology upload per block (what
+    MembraneMesh.opt_conjugate_gradient does, _membrane_mesh.pyx:1510-1517).  Returns
+    (device ms inside nw_search summed over blocks, wall seconds of constructor+search, launches)."""
+    from ch_shrinkwrap_b200.mesh_conj_grad import ShrinkwrapMeshConjGrad
+    dev_ms, wall, done = 0.0, 0.0, 0
+    sm = ctypes.c_double(0.0)
+    cg = None
+    while done < n_iters:
+        n_it = min(block, n_iters - done)
+        t0 = time.perf_counter()
+        cg = ShrinkwrapMeshConjGrad(mesh, pts, device=getattr(mesh, '_nw_device', 0), comm=getattr(mesh, '_nw_comm', None))
+        mesh.cg = cg
+        cg.search(pts, lams=[lam], num_iters=n_it, sigma_inv=s_inv)
+        wall += time.perf_counter() - t0
+        cg._h.call('nw_get_profile', None, None, ctypes.byref(sm))
+        dev_ms += sm.value
+        done += n_it
+    return dev_ms, wall, cg
+
+
+def cpu_reference_run(steps, warmup, seed):
+    """The reference's CPU path (oracle port: numpy + scipy cKDTree(workers=-1) + the C scatter) on the bounded
+    sample.  Returns dict(value, seconds, P, M, cores)."""
+    from oracle import build as obuild
+    from oracle import nanowrap_oracle as orc
+    obuild.build_oracle_c()
+    mesh, pts, sig, cfg = build_workload(REFERENCE_SAMPLE, seed)
+    s_inv = (1.0 / sig.ravel()).astype(np.float32)
+    lam = cfg['curvature_weight'] * 1.0 / 2.0
+    oc = orc.OracleConjGrad(mesh, pts)
+    mesh.cg = oc
+    if warmup > 0:
+        oc.search(pts, lams=[lam], num_iters=warmup, sigma_inv=s_inv)
+    t0 = time.perf_counter()
+    oc.search(pts, lams=[lam], num_iters=steps, sigma_inv=s_inv)
+    dt = time.perf_counter() - t0
+    P = len(pts)
+    return dict(value=P * steps / dt, seconds=dt, P=P, M=len(mesh._vertices), cores=os.cpu_count(),
+                sample='%s, %d CG iterations after %d warm-up' % (cfg['desc'], steps, warmup))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--seed', type=int, default=1234)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-steps', type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    unit = 'localisation*iterations/s'
+    metric = 'localisation_iterations_per_s'
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        W = max(args.warmup, 1)
+        r = cpu_reference_run(args.steps, W, args.seed)
+        cfg = WORKLOADS[args.workload]
+        line = {
+            'impl': 'reference', 'metric': metric, 'value': r['value'], 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': W, 'ms_per_step': 1e3 * r['seconds'] / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32 (fp64 nearest-face compare and Gram sums)', 'data': 'synthetic',
+            'config': {'workload': cfg['desc'] + ' per GPU', 'reference_sample': r['sample'], 'points_timed': r['P'], 'vertices_timed': r['M']},
+            'cg_iters_per_s_on_sample': args.steps / r['seconds'],
+            'cpu_baseline': {'value': r['value'], 'unit': unit, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
+            'e2e': {'value': r['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    from ch_shrinkwrap_b200 import _lib
+    _lib.load()
+    dist = None
+    comm = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        uid = ctypes.create_string_buffer(128)
+        if rank == 0:
+            rc = _lib.load().nw_comm_unique_id(uid)
+            assert rc == 0, 'nw_comm_unique_id failed'
+        t = torch.frombuffer(bytearray(uid.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        comm = (rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    mesh, pts, sig, cfg = build_workload(args.workload, args.seed + 1000 * rank)
+    mesh._nw_device = local_rank
+    mesh._nw_comm = comm
+    s_inv = (1.0 / sig.ravel()).astype(np.float32)
+    lam = cfg['curvature_weight'] * 1.0 / 2.0            # lam = curvature_weight * kc / 2 (_membrane_mesh.pyx:1486)
+    P, M, F = len(pts), len(mesh._vertices), len(mesh.faces)
+    block = cfg['block']
+    W = max(args.warmup, 3)
+    K = args.steps
+    start_pos = mesh._vertices['position'].copy()
+
+    # ---- e2e: public API with HOST buffers: first block pays the point upload + Morton sort, every block the
+    #      topology H2D and the position D2H.  Timed by wall clock around constructor + search().
+    barrier()
+    t0 = time.perf_counter()
+    _, e2e_wall, cg = run_blocks(mesh, pts, s_inv, lam, K, block)
+    e2e_s = allmax(time.perf_counter() - t0)
+    h = cg._h
+    topo_bytes = M * 12 * 2 + F * 12 + M * 80 + M
+    n_blocks = -(-K // block)
+    e2e = {'value': P * world * K / e2e_s, 'unit': unit,
+           'h2d_bytes_per_step': int((P * 24 + n_blocks * (topo_bytes + M * 12)) / K),
+           'd2h_bytes_per_step': int(n_blocks * M * 12 / K),
+           'note': 'ShrinkwrapMeshConjGrad(...).search() per block of %d iterations, host numpy in/out; includes the one-off upload '
+                   'and Morton sort of the points (pageable host memory), per-block topology upload and position read-back' % block}
+
+    # ---- device-resident: points already in HBM; warm-up then K timed iterations (CUDA events inside nw_search)
+    mesh._vertices['position'][:] = start_pos
+    mesh.update_geometry()
+    run_blocks(mesh, pts, s_inv, lam, W, block)
+    mesh._vertices['position'][:] = start_pos
+    mesh.update_geometry()
+    h.call('nw_set_profile', 1)
+    launches0 = h.lib.nw_launch_count(h.h)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    h.call('nw_sync')
+    clocks.start()
+    dev_ms, _, cg = run_blocks(mesh, pts, s_inv, lam, K, block)
+    h.call('nw_sync')
+    barrier()
+    clk = clocks.stop()
+    launches = int(h.lib.nw_launch_count(h.h) - launches0)
+    dev_ms = allmax(dev_ms)
+    stage_ms = (ctypes.c_double * 8)()
+    stage_l = (ctypes.c_int64 * 8)()
+    h.call('nw_get_profile', stage_ms, stage_l, None)
+    h.call('nw_set_profile', 0)
+    value = P * world * K / (dev_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel, measured live over the timed region ----
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    alg_bytes = {
+        'sweep1': 76.0 * P + 24.0 * F + 12.0 * M,          # NN + weights + residual fused
+        'sweep2': 36.0 * P + 12.0 * 3 * M,                 # multi-RHS Gram pass, n = 3
+        'mesh_prior': 120.0 * M,                           # _ncc
+        'apply_A': 36.0 * P + 12.0 * M,
+        'apply_AH': 36.0 * P + 12.0 * M,
+    }
+    stage = {STAGES[k]: {'ms_total': stage_ms[k], 'launches': int(stage_l[k])} for k in range(8)}
+    dom = max(('sweep1', 'sweep2', 'mesh_prior'), key=lambda k: stage[k]['ms_total'])
+    dom_ms = stage[dom]['ms_total'] / K
+    achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': traffic, 'peak_source': peak_src, 'ms_per_launch': dom_ms, 'algorithmic_bytes_per_launch': alg_bytes[dom],
+                'share_of_step': stage[dom]['ms_total'] / dev_ms}
+    # isolated single-operator kernels (device resident, CUDA events)
+    kernels = {}
+    ms = ctypes.c_float(0.0)
+    for name in ('apply_A', 'apply_AH', 'sweep2', 'mesh_prior', 'sweep1'):
+        try:
+            h.call('nw_bench_kernel', name.encode(), 10, ctypes.byref(ms))
+            gbs = alg_bytes[name] / (ms.value * 1e-3) / 1e9
+            kernels[name] = {'ms': ms.value, 'achieved_gbs': gbs, 'frac': gbs / peak}
+        except Exception as e:      # noqa
+            kernels[name] = {'error': str(e)}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args.cpu_steps, 1, args.seed)
+        cpu = {'value': r['value'], 'unit': unit, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
+               'cg_iters_per_s_on_sample': args.cpu_steps / r['seconds']}
+    line = {
+        'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': dev_ms / K,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (fp64 nearest-face compare and Gram sums, int64 fixed-point adjoint)', 'data': 'synthetic',
+        'config': {'workload': cfg['desc'] + ' per GPU', 'points_per_gpu': P, 'vertices': M, 'faces': F, 'lam': lam,
+                   'block_iterations': block, 'parallelism': 'points sharded x%d, mesh replicated' % world,
+                   'l2': 'inputs larger than L2: per-point streams %.0f MB vs 126 MB L2' % (52.0 * P / 1e6)},
+        'cg_iters_per_s': K / (dev_ms * 1e-3),
+        'e2e': e2e, 'gpu_launches': launches, 'clocks': {k: clk[k] for k in ('sm_mhz', 'sm_max_mhz', 'reasons')},
+        'roofline': roofline, 'cpu_baseline': cpu, 'stages': stage, 'kernels': kernels,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

@@ -51,6 +51,8 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free(&h->acc); nw_free(&h->S0); nw_free(&h->S1); nw_free(&h->S2); nw_free(&h->fdef);
     nw_free(&h->partials); nw_free(&h->st); nw_free(&h->hist);
     nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP); nw_free(&h->curvK);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->ev_search0) { cudaEventDestroy(h->ev_search0); cudaEventDestroy(h->ev_search1); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -82,16 +84,51 @@ static int upload_state(nw_ctx *h, const SolverState &s) {
     return NW_OK;
 }
 
+// per-stage CUDA events (only when profiling is switched on)
+static int stage_begin(nw_ctx *h, int stage) {
+    if (!h->profile) return NW_OK;
+    if (h->ev_used + 2 > h->ev_pool.size()) {
+        for (int k = 0; k < 64; ++k) { cudaEvent_t e; NW_CUDA(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
+    }
+    h->ev_stage.push_back(stage);
+    NW_CUDA(cudaEventRecord(h->ev_pool[h->ev_used++], h->stream));
+    h->stage_launches[stage] -= h->launches;
+    return NW_OK;
+}
+static int stage_end(nw_ctx *h, int stage) {
+    if (!h->profile) return NW_OK;
+    NW_CUDA(cudaEventRecord(h->ev_pool[h->ev_used++], h->stream));
+    h->stage_launches[stage] += h->launches;
+    return NW_OK;
+}
+#define NW_STAGE(id, call) do { NW_CHECK(stage_begin(h, id)); NW_CHECK(call); NW_CHECK(stage_end(h, id)); } while (0)
+
 // one full iteration, enqueued asynchronously
 static int enqueue_iteration(nw_ctx *h, int it, int last_step) {
-    NW_CHECK(nw_tree_refit(h));                 // centroids + boxes at the current f  (:443)
-    NW_CHECK(nw_set_acc_shifts(h));
-    NW_CHECK(nw_launch_sweep1(h, true));        // NN, weights, A f, residual, AH res, AH 1  (:222-253)
-    NW_CHECK(nw_allreduce_acc(h));              // N>1: vertex-gradient allreduce
-    NW_CHECK(nw_launch_mesh_prior(h, true));    // S0, ncc, prefs, S1, S^T S  (:224,253-258)
-    NW_CHECK(nw_launch_sweep2(h));              // A S_k and Gram sums  (conj_grad.py:197-203)
-    NW_CHECK(nw_allreduce_scalars(h));          // N>1: CG scalars
-    NW_CHECK(nw_launch_solve_update(h, it, last_step));
+    NW_STAGE(0, nw_tree_refit(h));                 // centroids + boxes at the current f  (:443)
+    NW_STAGE(1, nw_set_acc_shifts(h));
+    NW_STAGE(2, nw_launch_sweep1(h, true));        // NN, weights, A f, residual, AH res, AH 1  (:222-253)
+    if (h->nranks > 1) NW_STAGE(3, nw_allreduce_acc(h));   // N>1: vertex-gradient allreduce
+    NW_STAGE(4, nw_launch_mesh_prior(h, true));    // S0, ncc, prefs, S1, S^T S  (:224,253-258)
+    NW_STAGE(5, nw_launch_sweep2(h));              // A S_k and Gram sums  (conj_grad.py:197-203)
+    if (h->nranks > 1) NW_STAGE(6, nw_allreduce_scalars(h));   // N>1: CG scalars
+    NW_STAGE(7, nw_launch_solve_update(h, it, last_step));
+    return NW_OK;
+}
+
+extern "C" int nw_set_profile(nw_ctx *h, int on) {
+    if (!h) return NW_ERR_ARG;
+    h->profile = on;
+    for (int k = 0; k < NW_N_STAGES; ++k) { h->stage_ms[k] = 0.0; h->stage_launches[k] = 0; }
+    return NW_OK;
+}
+extern "C" int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms) {
+    if (!h) return NW_ERR_ARG;
+    for (int k = 0; k < NW_N_STAGES; ++k) {
+        if (stage_ms) stage_ms[k] = h->stage_ms[k];
+        if (stage_launches) stage_launches[k] = h->stage_launches[k];
+    }
+    if (search_ms) *search_ms = h->last_search_ms;
     return NW_OK;
 }
 
@@ -119,11 +156,26 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     NW_CUDA(cudaMemsetAsync(h->S1, 0, sizeof(float4) * h->M, h->stream));
     NW_CUDA(cudaMemsetAsync(h->S2, 0, sizeof(float4) * h->M, h->stream));
     NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * h->M, h->stream));
+    if (!h->ev_search0) { NW_CUDA(cudaEventCreate(&h->ev_search0)); NW_CUDA(cudaEventCreate(&h->ev_search1)); }
+    h->ev_used = 0;
+    h->ev_stage.clear();
+    NW_CUDA(cudaEventRecord(h->ev_search0, h->stream));
     if (!s.stop)
         for (int it = 0; it < num_iters; ++it) NW_CHECK(enqueue_iteration(h, it, last_step));
+    NW_CUDA(cudaEventRecord(h->ev_search1, h->stream));
     SolverState r;
     NW_CUDA(cudaMemcpyAsync(&r, h->st, sizeof(SolverState), cudaMemcpyDeviceToHost, h->stream));
     NW_CUDA(cudaStreamSynchronize(h->stream));
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_search0, h->ev_search1);
+        h->last_search_ms = ms;
+        for (size_t k = 0; k + 1 < h->ev_used; k += 2) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, h->ev_pool[k], h->ev_pool[k + 1]);
+            h->stage_ms[h->ev_stage[k / 2]] += t;
+        }
+    }
     if (n_done) *n_done = r.n_done;
     if (r.n_done > 0) {
         h->weights_valid = true;

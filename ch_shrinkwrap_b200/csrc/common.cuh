@@ -10,6 +10,7 @@
 #define NW_FAN 4         // children per interior node (4 x 32 B boxes = one 128 B line)
 #define NW_MAX_LEVELS 16
 #define NW_MAX_ITERS 4096
+#define NW_N_STAGES 8    // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update
 
 struct Box { float4 lo, hi; };   // 32 B: one L2 sector per box
 
@@ -91,6 +92,16 @@ struct nw_ctx {
     // ---- curvature ----
     float *curvK = nullptr;
     int curvM = 0;
+
+    // ---- measurement: CUDA events on the handle's stream ----
+    int profile = 0;                             // 1: per-stage events inside nw_search
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_stage;                   // stage id of interval [2k, 2k+1]
+    size_t ev_used = 0;
+    double stage_ms[NW_N_STAGES] = {0};
+    int64_t stage_launches[NW_N_STAGES] = {0};
+    cudaEvent_t ev_search0 = nullptr, ev_search1 = nullptr;
+    double last_search_ms = 0.0;
 
     // ---- comm ----
     void *nccl = nullptr;                        // ncclComm_t

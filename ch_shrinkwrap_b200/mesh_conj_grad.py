@@ -110,7 +110,7 @@ class ShrinkwrapMeshConjGrad(object):
         self._sigma_inv, self._weights = 1.0, None
         self.f = None
         self.fs = None
-        self.mask = None
+        self._mask_src = None
 
     # -- device plumbing ---------------------------------------------------------------------------
     @property
@@ -151,11 +151,7 @@ class ShrinkwrapMeshConjGrad(object):
             if np.shape(data) != np.shape(self._points) or not np.array_equal(data, self._points):
                 self._points = data
         self._sigma_inv, self._weights = sigma_inv, weights
-        w_eff = sigma_inv if weights is None else weights
-        if not np.isscalar(w_eff):
-            self.mask = np.asarray(w_eff).reshape(-1) > 0              # :161
-        else:
-            self.mask = np.isfinite(np.asarray(data).reshape(-1))     # :164
+        self._mask_src = (sigma_inv if weights is None else weights, data)   # mask is built lazily (3P bools)
         self._ensure_ready()
         # positions may have been edited on the host since the upload (remesh happens between blocks,
         # which builds a new object, so this only matters for repeated search() calls)
@@ -186,7 +182,6 @@ class ShrinkwrapMeshConjGrad(object):
     # -- operators -----------------------------------------------------------------------------------
     def _ensure_weights(self):
         self._ensure_ready()
-        ok = ctypes.c_int(0)
         # nw_apply_* fail if no weights exist yet: compute them at the current f like calc_w() does (:1018-1023)
         try:
             self._h.call('nw_get_weights', None, None, None, None)
@@ -268,6 +263,15 @@ class ShrinkwrapMeshConjGrad(object):
         return self.f if self.f is not None else _lib.as_f32(self.mesh._vertices['position']).ravel()
 
     # -- read-backs (lazy: these are 3P-sized) -----------------------------------------------------------
+    @property
+    def mask(self):
+        if self._mask_src is None:
+            return None
+        w_eff, data = self._mask_src
+        if not np.isscalar(w_eff):
+            return np.asarray(w_eff).reshape(-1) > 0               # :161
+        return np.isfinite(np.asarray(data).reshape(-1))          # :164
+
     @property
     def res(self):
         r = np.empty(3 * self._session.P, np.float32)

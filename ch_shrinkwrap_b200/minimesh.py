@@ -129,8 +129,9 @@ class MiniMesh:
         self._faces['normal'] = fn.astype(np.float32)
         self._faces['area'] = area.astype(np.float32)
         vn = np.zeros((len(pos), 3), np.float64)
-        for k in range(3):
-            np.add.at(vn, faces[:, k], n)  # area-weighted
+        for k in range(3):            # area-weighted sum of face normals (bincount: add.at is 20x slower)
+            for a in range(3):
+                vn[:, a] += np.bincount(faces[:, k], weights=n[:, a], minlength=len(pos))
         vnn = np.sqrt((vn * vn).sum(1))
         with np.errstate(invalid='ignore', divide='ignore'):
             vn = np.where(vnn[:, None] > 0, vn / vnn[:, None], 0.0)

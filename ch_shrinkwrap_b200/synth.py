@@ -181,3 +181,49 @@ def star_mesh(shape, n, scale=1.2):
     v, f = geodesic_sphere(n)
     r = radial_surface(shape, v)
     return MiniMesh(v * (scale * r)[:, None], f)
+
+
+def mesh_surface_cloud(verts, faces, n_points, seed=0, noise_fraction=0.1, chunk=1 << 20, threads=None,
+                       psf_width=(280.0, 280.0, 840.0), mean_photon_count=600.0, bg_photon_count=20.0):
+    """Large float32 clouds for the bench: uniform samples on a fine triangulation of the shape, jittered with
+    the exponential-photon precision model, plus uniform background.  Chunked with one child seed per chunk,
+    so the result does not depend on the number of worker threads."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    verts = np.asarray(verts, dtype=np.float32)
+    faces = np.asarray(faces)
+    v0, v1, v2 = verts[faces[:, 0]], verts[faces[:, 1]], verts[faces[:, 2]]
+    area = 0.5 * np.sqrt((np.cross((v1 - v0).astype(np.float64), (v2 - v0).astype(np.float64)) ** 2).sum(1))
+    cdf = np.cumsum(area)
+    cdf /= cdf[-1]
+    lo, hi = verts.min(0), verts.max(0)
+    c, half = 0.5 * (lo + hi), 0.5 * (hi - lo) * 1.2
+    psf = (np.asarray(psf_width, np.float32) / np.float32(2.355))
+    pts = np.empty((n_points, 3), np.float32)
+    sig = np.empty((n_points, 3), np.float32)
+    starts = list(range(0, n_points, chunk))
+    seeds = np.random.SeedSequence(seed).spawn(len(starts))
+
+    def work(k):
+        s = starts[k]
+        e = min(n_points, s + chunk)
+        m = e - s
+        rng = np.random.default_rng(seeds[k])
+        f = np.minimum(np.searchsorted(cdf, rng.random(m)), len(faces) - 1)
+        r1 = np.sqrt(rng.random(m, dtype=np.float32))
+        r2 = rng.random(m, dtype=np.float32)
+        a, b = (1 - r1)[:, None], (r1 * (1 - r2))[:, None]
+        p = a * v0[f] + b * v1[f] + (1 - a - b) * v2[f]
+        l = rng.exponential(mean_photon_count, (m, 3)).astype(np.float32)
+        l = np.maximum(l, np.float32(bg_photon_count))       # clamp instead of reject: keeps chunks independent
+        sg = psf / np.sqrt(l)
+        p += sg * rng.standard_normal((m, 3), dtype=np.float32)
+        bgm = rng.random(m) < noise_fraction
+        nb = int(bgm.sum())
+        p[bgm] = c + half * (rng.random((nb, 3), dtype=np.float32) * 2 - 1)
+        pts[s:e] = p
+        sig[s:e] = sg
+
+    with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 8)) as ex:
+        list(ex.map(work, range(len(starts))))
+    return pts, sig

@@ -129,6 +129,12 @@ int nw_neck_candidates(nw_ctx *h, float low, float high, int32_t *idx, int *n);
 /* device-resident single-kernel launches on the handle's stream, for CUDA-event timing */
 int nw_bench_kernel(nw_ctx *h, const char *name, int reps, float *ms_per_launch);
 int nw_sync(nw_ctx *h);
+/* CUDA-event timing on the handle's stream: on = 1 brackets every stage of every iteration inside
+ * nw_search.  nw_get_profile returns accumulated ms and kernel launches per stage (8 stages: refit,
+ * shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update) and the event-
+ * timed duration of the last nw_search call (first kernel to last kernel). */
+int nw_set_profile(nw_ctx *h, int on);
+int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms);
 /* kernels launched by this handle since creation (for bench.py's gpu_launches) */
 int64_t nw_launch_count(nw_ctx *h);
 
