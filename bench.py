@@ -35,7 +35,7 @@ WORKLOADS = {
     'c3': dict(points=10_000_000, geo=224, curvature_weight=10.0, block=5, desc='config2: 10M localisations, 501 762-vertex two-lobed mesh'),
 }
 REFERENCE_SAMPLE = 'c2'   # bounded CPU sample: same shape, same 20 localisations per vertex, 1/10 of c3
-STAGES = ['refit', 'shift', 'sweep1', 'allreduce_acc', 'mesh_prior', 'sweep2', 'allreduce_scalars', 'solve_update']
+STAGES = ['refit', 'shift', 'sweep1', 'allreduce_acc', 'mesh_prior', 'sweep2', 'allreduce_scalars', 'solve_update', 'seed_leaders']
 
 
 def build_workload(name, seed):
@@ -251,8 +251,8 @@ def main():
     clk = clocks.stop()
     launches = int(h.lib.nw_launch_count(h.h) - launches0)
     dev_ms = allmax(dev_ms)
-    stage_ms = (ctypes.c_double * 8)()
-    stage_l = (ctypes.c_int64 * 8)()
+    stage_ms = (ctypes.c_double * 9)()
+    stage_l = (ctypes.c_int64 * 9)()
     h.call('nw_get_profile', stage_ms, stage_l, None)
     h.call('nw_set_profile', 0)
     value = P * world * K / (dev_ms * 1e-3)
@@ -270,7 +270,7 @@ def main():
         'apply_A': 36.0 * P + 12.0 * M,
         'apply_AH': 36.0 * P + 12.0 * M,
     }
-    stage = {STAGES[k]: {'ms_total': stage_ms[k], 'launches': int(stage_l[k])} for k in range(8)}
+    stage = {STAGES[k]: {'ms_total': stage_ms[k], 'launches': int(stage_l[k])} for k in range(9)}
     dom = max(('sweep1', 'sweep2', 'mesh_prior'), key=lambda k: stage[k]['ms_total'])
     dom_ms = stage[dom]['ms_total'] / K
     achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9

@@ -9,7 +9,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnanowrap.so')
+LIB_PATH = os.environ.get('NANOWRAP_LIB', os.path.join(_HERE, 'libnanowrap.so'))   # override is for kernel-variant experiments
 
 NW_OK, NW_ERR_CUDA, NW_ERR_ARG, NW_ERR_NAN, NW_ERR_COMM = 0, 1, 2, 3, 4
 
@@ -48,6 +48,7 @@ SIGNATURES = {
     'nw_sync': (c_int, [c_void_p]),
     'nw_set_profile': (c_int, [c_void_p, c_int]),
     'nw_get_profile': (c_int, [c_void_p, _d, POINTER(c_int64), _d]),
+    'nw_get_traversal_stats': (c_int, [c_void_p, POINTER(c_uint64)]),
     'nw_launch_count': (c_int64, [c_void_p]),
 }
 

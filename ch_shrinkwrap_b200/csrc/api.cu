@@ -107,6 +107,7 @@ static int stage_end(nw_ctx *h, int stage) {
 static int enqueue_iteration(nw_ctx *h, int it, int last_step) {
     NW_STAGE(0, nw_tree_refit(h));                 // centroids + boxes at the current f  (:443)
     NW_STAGE(1, nw_set_acc_shifts(h));
+    if (h->seeds_cold) NW_STAGE(8, nw_launch_seed_leaders(h));   // first iteration after a topology upload only
     NW_STAGE(2, nw_launch_sweep1(h, true));        // NN, weights, A f, residual, AH res, AH 1  (:222-253)
     if (h->nranks > 1) NW_STAGE(3, nw_allreduce_acc(h));   // N>1: vertex-gradient allreduce
     NW_STAGE(4, nw_launch_mesh_prior(h, true));    // S0, ncc, prefs, S1, S^T S  (:224,253-258)
@@ -120,6 +121,13 @@ extern "C" int nw_set_profile(nw_ctx *h, int on) {
     if (!h) return NW_ERR_ARG;
     h->profile = on;
     for (int k = 0; k < NW_N_STAGES; ++k) { h->stage_ms[k] = 0.0; h->stage_launches[k] = 0; }
+    return NW_OK;
+}
+extern "C" int nw_get_traversal_stats(nw_ctx *h, uint64_t out[4]) {
+    if (!h || !out) return NW_ERR_ARG;
+    SolverState r;
+    NW_CUDA(cudaMemcpy(&r, h->st, sizeof(SolverState), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; ++k) out[k] = r.trav[k];
     return NW_OK;
 }
 extern "C" int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms) {

@@ -6,14 +6,23 @@
 #include <vector>
 #include "../../include/nanowrap.h"
 
-#define NW_LEAF 8        // sorted centroids per leaf of the Morton AABB pyramid
-#define NW_FAN 4         // children per interior node (4 x 32 B boxes = one 128 B line)
-#define NW_MAX_LEVELS 16
+#ifndef NW_LEAF
+#define NW_LEAF 8        // sorted centroids per leaf of the Hilbert-sorted box pyramid
+#endif
+#ifndef NW_FAN
+#define NW_FAN 4         // children per interior node
+#endif
+#define NW_MAX_LEVELS 28
 #define NW_MAX_ITERS 4096
-#define NW_N_STAGES 8    // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update
+#define NW_N_STAGES 9    // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders
 
-struct Box { float4 lo, hi; };   // 32 B: one L2 sector per box
-
+// Node bound = ORIENTED box: a surface patch is thin along its normal and tilted against the coordinate axes, so an
+// axis-aligned box is mostly empty space.  Axes: n (patch normal), t1 (stored), t2 = n x t1; one interval per axis.
+struct Box {
+    float4 a;   // n.x n.y n.z | t1.x
+    float4 b;   // t1.y t1.z | n-interval min, max
+    float4 c;   // t1-interval min, max | t2-interval min, max
+};              // 48 B
 struct TreeLevels {
     int n_levels;                 // level 0 = leaves
     int count[NW_MAX_LEVELS];
@@ -34,7 +43,9 @@ struct SolverState {
     int n_search;                 // 2 on the first iteration of a call, 3 afterwards (last_step)
     int acc_shift;                // fixed-point fraction bits of the adjoint accumulators
     int infl_shift;               // ditto for the AH*1 accumulator
+    float coord_l1;               // bound on |x|+|y|+|z| over vertices and points (rounding slack of the box tests)
     float lam;
+    unsigned long long trav[4];   // traversal statistics: node tests, leaf visits, exact fp64 evaluations, max node tests of one point
 };
 
 struct nw_ctx {
@@ -75,6 +86,7 @@ struct nw_ctx {
     float4 *cent = nullptr;                      // per sorted slot: centroid xyz + face id bits
     Box *boxes = nullptr;
     TreeLevels tl;
+    bool seeds_cold = true;                      // no nearest-face seeds yet for this topology
     // ---- solver vectors ----
     unsigned long long *acc = nullptr;           // (M,4) int64 fixed point: AH res xyz, AH 1
     float4 *S0 = nullptr, *S1 = nullptr, *S2 = nullptr;
@@ -155,10 +167,30 @@ static inline int nw_grid(int64_t n, int block) { return (int)((n + block - 1) /
         }                                                                                  \
     } while (0)
 
+// 3-D Hilbert index (Skilling's transpose algorithm): unlike Morton order, every contiguous key range is a connected,
+// compact blob, so fixed-size chunks of the sorted order make tight tree nodes and coherent warps.
+template <typename U>
+__host__ __device__ __forceinline__ void hilbert_axes_to_transpose(U &x, U &y, U &z, int bits) {
+    U X[3] = {x, y, z};
+    const U M = (U)1 << (bits - 1);
+    for (U Q = M; Q > 1; Q >>= 1) {
+        const U P = Q - 1;
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const U t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0]; X[2] ^= X[1];
+    U t = 0;
+    for (U Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    x = X[0] ^ t; y = X[1] ^ t; z = X[2] ^ t;
+}
+
 // ---- internal entry points implemented across translation units -------------------------------
 int nw_tree_build(nw_ctx *h);                 // after topology upload: Morton sort of faces
 int nw_tree_refit(nw_ctx *h);                 // every iteration: centroids + boxes at the current f
 int nw_launch_sweep1(nw_ctx *h, bool scatter);
+int nw_launch_seed_leaders(nw_ctx *h);
 int nw_launch_sweep2(nw_ctx *h);
 int nw_launch_mesh_prior(nw_ctx *h, bool write_dirs);
 int nw_launch_solve_update(nw_ctx *h);

@@ -36,11 +36,14 @@ __global__ void k_shift(const float4 *__restrict__ pos, int M, float plo_x, floa
     __syncthreads();
     if (threadIdx.x == 0) {
         double ext = 0.0;
+        float l1 = 0.f;
         for (int a = 0; a < 3; ++a) {
             float l = slo[a][0], u = shi[a][0];
             for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { l = fminf(l, slo[a][k]); u = fmaxf(u, shi[a][k]); }
             ext = fmax(ext, (double)u - (double)l);
+            l1 += fmaxf(fabsf(l), fabsf(u));
         }
+        st->coord_l1 = l1;
         // |w_j res_c| <= Wn_max * extent ; a vertex sums at most P_global of them
         double bound = fmax(wn_max * ext, 1e-30) * fmax(p_global, 1.0);
         int e;

@@ -56,7 +56,8 @@ __global__ void k_point_keys(const T *__restrict__ pts, int64_t P, float3 lo, fl
     unsigned long long qx = (unsigned long long)fminf(fmaxf(x, 0.f), top);
     unsigned long long qy = (unsigned long long)fminf(fmaxf(y, 0.f), top);
     unsigned long long qz = (unsigned long long)fminf(fmaxf(z, 0.f), top);
-    keys[i] = spread21(qx) | (spread21(qy) << 1) | (spread21(qz) << 2);
+    hilbert_axes_to_transpose(qx, qy, qz, 21);
+    keys[i] = (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
     idx[i] = (int)i;
 }
 
@@ -147,6 +148,7 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
 
     h->P = P;
     h->weights_valid = false;
+    h->seeds_cold = true;
     NWX(nw_alloc(h, &d_pts, (size_t)3 * P));
     NWC(cudaMemcpyAsync(d_pts, pts_host, sizeof(T) * 3 * P, cudaMemcpyHostToDevice, s));
     NWX(nw_alloc(h, &d_bbox, 6));

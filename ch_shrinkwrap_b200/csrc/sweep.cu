@@ -10,6 +10,7 @@
 // Determinism: the adjoint accumulates in 64-bit fixed point (integer atomics are order-independent,
 // float atomics are not); the Gram sums use a fixed thread->point assignment and a fixed two-stage tree.
 #include <cfloat>
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
@@ -19,6 +20,9 @@ __device__ __forceinline__ float sq_rd(float g) { return __fmul_rd(g, g); }
 
 struct QueryF32 {
     float x, y, z;
+    __device__ __forceinline__ float fx() const { return x; }
+    __device__ __forceinline__ float fy() const { return y; }
+    __device__ __forceinline__ float fz() const { return z; }
     __device__ __forceinline__ float lb_box(const float4 lo, const float4 hi) const {
         float gx = fmaxf(fmaxf(__fsub_rd(lo.x, x), __fsub_rd(x, hi.x)), 0.f);
         float gy = fmaxf(fmaxf(__fsub_rd(lo.y, y), __fsub_rd(y, hi.y)), 0.f);
@@ -35,6 +39,9 @@ struct QueryF32 {
 struct QueryF64 {
     double x, y, z;
     float xl, xh, yl, yh, zl, zh;   // float32 enclosure of the float64 coordinates
+    __device__ __forceinline__ float fx() const { return xl; }
+    __device__ __forceinline__ float fy() const { return yl; }
+    __device__ __forceinline__ float fz() const { return zl; }
     __device__ __forceinline__ void set(double px, double py, double pz) {
         x = px; y = py; z = pz;
         xl = __double2float_rd(px); xh = __double2float_ru(px);
@@ -63,64 +70,127 @@ struct Nearest {
     }
 };
 
-#define NW_STACK 48
+// Conservative lower bound of the squared distance from the query to anything inside a node's oriented box:
+// sum over the three axes of (interval gap - eps)^2.  Projections are float32 dot products, so every gap is shrunk
+// by an absolute slack eps (>= 4x the worst-case rounding error of both projections, DESIGN.md "exactness") and the
+// sum by a relative 1e-5 (axes are orthonormal only to float32 accuracy).  A node is skipped only if this bound
+// exceeds the best exact fp64 distance, so skipping can never change the answer.
+template <typename Q>
+__device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps) {
+    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
+    const float x = q.fx(), y = q.fy(), z = q.fz();
+    const float t2x = a.y * b.y - a.z * b.x, t2y = a.z * a.w - a.x * b.y, t2z = a.x * b.x - a.y * a.w;
+    const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
+    const float p1 = fmaf(a.w, x, fmaf(b.x, y, b.y * z));
+    const float p2 = fmaf(t2x, x, fmaf(t2y, y, t2z * z));
+    const float g0 = fmaxf(fmaxf(fmaxf(b.z - pn, pn - b.w), 0.f) - eps, 0.f);
+    const float g1 = fmaxf(fmaxf(fmaxf(c.x - p1, p1 - c.y), 0.f) - eps, 0.f);
+    const float g2 = fmaxf(fmaxf(fmaxf(c.z - p2, p2 - c.w), 0.f) - eps, 0.f);
+    return __fmul_rd(__fadd_rd(__fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1)), __fmul_rd(g2, g2)), 0.99999f);
+}
+
+#define NW_STACK 96
 
 template <typename Q>
-__device__ __forceinline__ void nearest_centroid(const Q &q, Nearest &best, const float4 *__restrict__ cent,
-                                                 const Box *__restrict__ boxes, const TreeLevels &tl, int F) {
+struct Traversal {
+    const Q &q;
+    Nearest &best;
+    const float4 *__restrict__ cent;
+    const Box *__restrict__ boxes;
+    const TreeLevels &tl;
+    int F;
+    float eps;
     float slb[NW_STACK];
     int snode[NW_STACK];
-    int sp = 0;
-    const int top = tl.n_levels - 1;
-    for (int k = tl.count[top] - 1; k >= 0; --k) {
-        Box b = boxes[tl.offset[top] + k];
-        slb[sp] = q.lb_box(b.lo, b.hi);
-        snode[sp++] = (top << 26) | k;
-    }
-    while (sp > 0) {
-        --sp;
-        const float lb = slb[sp];
-        const int node = snode[sp];
-        if (lb > best.ub) continue;
-        const int level = node >> 26, idx = node & 0x3ffffff;
-        if (level == 0) {
-            const int base = idx * NW_LEAF;
-            const int n = min(NW_LEAF, F - base);
-            for (int k = 0; k < n; ++k) {
-                const float4 c = __ldg(&cent[base + k]);
-                if (q.lb_box(c, c) <= best.ub) best.offer(q.d2(c), base + k, __float_as_int(c.w));
-            }
-        } else {
-            const int cl = level - 1;
-            const int c0 = idx * NW_FAN;
-            const int n = min(NW_FAN, tl.count[cl] - c0);
-            float l[NW_FAN];
-            int id[NW_FAN];
-#pragma unroll
-            for (int k = 0; k < NW_FAN; ++k) {
-                if (k < n) {
-                    const Box *bp = &boxes[tl.offset[cl] + c0 + k];
-                    const float4 lo = __ldg(&bp->lo), hi = __ldg(&bp->hi);
-                    l[k] = q.lb_box(lo, hi);
-                } else l[k] = FLT_MAX;
-                id[k] = (cl << 26) | (c0 + k);
-            }
-            // sort descending by lower bound so the nearest child is popped first
-#define NW_CSWAP(a, b) if (l[a] < l[b]) { float tf = l[a]; l[a] = l[b]; l[b] = tf; int ti = id[a]; id[a] = id[b]; id[b] = ti; }
-            NW_CSWAP(0, 1) NW_CSWAP(2, 3) NW_CSWAP(0, 2) NW_CSWAP(1, 3) NW_CSWAP(1, 2)
-#undef NW_CSWAP
-#pragma unroll
-            for (int k = 0; k < NW_FAN; ++k)
-                if (l[k] <= best.ub && l[k] != FLT_MAX) { slb[sp] = l[k]; snode[sp++] = id[k]; }
+    int sp;
+    unsigned n_tests = 0, n_leaves = 0, n_exact = 0;
+    unsigned budget = 0xffffffffu;   // seeds only: stop refining after this many node tests (the result is then approximate)
+
+    __device__ __forceinline__ Traversal(const Q &q_, Nearest &b_, const float4 *c_, const Box *bx_, const TreeLevels &tl_, int F_, float eps_)
+        : q(q_), best(b_), cent(c_), boxes(bx_), tl(tl_), F(F_), eps(eps_), sp(0) {}
+
+    __device__ __forceinline__ void leaf(int idx) {
+        const int base = idx * NW_LEAF;
+        const int n = min(NW_LEAF, F - base);
+        ++n_leaves;
+        for (int k = 0; k < n; ++k) {
+            const float4 c = __ldg(&cent[base + k]);
+            if (q.lb_box(c, c) <= best.ub) { ++n_exact; best.offer(q.d2(c), base + k, __float_as_int(c.w)); }
         }
     }
-}
+    // test the children [c0, c0+n) of level cl, push the survivors nearest-last; `skip` = child not to visit
+    __device__ __forceinline__ void expand(int cl, int c0, int n, int skip) {
+        float l[NW_FAN];
+        int id[NW_FAN];
+#pragma unroll
+        for (int k = 0; k < NW_FAN; ++k) {
+            l[k] = (k < n && c0 + k != skip) ? node_lb(q, &boxes[tl.offset[cl] + c0 + k], eps) : FLT_MAX;
+            n_tests += (k < n && c0 + k != skip);
+            id[k] = (cl << 26) | (c0 + k);
+        }
+#define NW_CSWAP(a, b) if (l[a] < l[b]) { float tf = l[a]; l[a] = l[b]; l[b] = tf; int ti = id[a]; id[a] = id[b]; id[b] = ti; }
+#if NW_FAN == 4
+        NW_CSWAP(0, 1) NW_CSWAP(2, 3) NW_CSWAP(0, 2) NW_CSWAP(1, 3) NW_CSWAP(1, 2)
+#elif NW_FAN == 2
+        NW_CSWAP(0, 1)
+#else
+#error "NW_FAN must be 2 or 4"
+#endif
+#undef NW_CSWAP
+#pragma unroll
+        for (int k = 0; k < NW_FAN; ++k)
+            if (l[k] <= best.ub && l[k] != FLT_MAX && sp < NW_STACK) { slb[sp] = l[k]; snode[sp++] = id[k]; }
+    }
+    __device__ __forceinline__ void run() {
+        while (sp > 0) {
+            if (n_tests > budget) { sp = 0; break; }
+            --sp;
+            const float lb = slb[sp];
+            const int node = snode[sp];
+            if (lb > best.ub) continue;
+            const int level = node >> 26, idx = node & 0x3ffffff;
+            if (level == 0) leaf(idx);
+            else expand(level - 1, idx * NW_FAN, min(NW_FAN, tl.count[level - 1] - idx * NW_FAN), -1);
+        }
+    }
+    // cold query: from the top level down
+    __device__ __forceinline__ void top_down() {
+        const int top = tl.n_levels - 1;
+        expand(top, 0, tl.count[top], -1);
+        run();
+    }
+    // warm query: start at the seed's leaf and climb; at every level only the siblings are tested
+    __device__ __forceinline__ void from_seed(int seed_slot) {
+        int node = seed_slot / NW_LEAF;
+        leaf(node);
+        const int top = tl.n_levels - 1;
+        for (int level = 0; level < top; ++level) {
+            const int parent = node / NW_FAN, c0 = parent * NW_FAN;
+            expand(level, c0, min(NW_FAN, tl.count[level] - c0), node);
+            run();
+            node = parent;
+        }
+        expand(top, 0, tl.count[top], node);
+        run();
+    }
+};
 
 __device__ __forceinline__ double pow2d(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
 
+__device__ __forceinline__ long long to_fixed(float v, double scale) { return __double2ll_rn((double)v * scale); }
 __device__ __forceinline__ void red_fixed(unsigned long long *p, float v, double scale) {
-    long long q = __double2ll_rn((double)v * scale);
-    atomicAdd(p, (unsigned long long)q);
+    atomicAdd(p, (unsigned long long)to_fixed(v, scale));
+}
+
+// Sum of a 64-bit fixed-point value over the lanes in `mask` (all of which hold the same key): the value is
+// split into three limbs so the 32-bit REDUX unit can add them without overflow (<= 32 lanes x 22 bits);
+// recombination is exact modulo 2^64, i.e. exact two's-complement addition.
+__device__ __forceinline__ unsigned long long group_sum(unsigned mask, long long v) {
+    const unsigned long long u = (unsigned long long)v;
+    const unsigned l0 = __reduce_add_sync(mask, (unsigned)(u & 0x3fffffu));
+    const unsigned l1 = __reduce_add_sync(mask, (unsigned)((u >> 22) & 0x1fffffu));
+    const unsigned l2 = __reduce_add_sync(mask, (unsigned)(u >> 43));
+    return (unsigned long long)l0 + ((unsigned long long)l1 << 22) + ((unsigned long long)l2 << 43);
 }
 
 struct Sweep1Args {
@@ -141,33 +211,90 @@ struct Sweep1Args {
     SolverState *st;
 };
 
+template <bool F64>
+__device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, bool active, float x, float y, float z,
+                                             double xd, double yd, double zd, Nearest &best) {
+    const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;   // 2^-20 * L1 magnitude
+    typename std::conditional<F64, QueryF64, QueryF32>::type q;
+    if constexpr (F64) q.set(xd, yd, zd);
+    else { q.x = x; q.y = y; q.z = z; }
+    Traversal<decltype(q)> tr(q, best, a.cent, a.boxes, a.tl, a.F, eps);
+    int seed = active ? a.slot[i] : 0;
+    // Cold start (first iteration after a topology upload): lanes without a seed borrow one from a lane that has it
+    // (k_seed_leaders searched lane 0's point from the root) -- Hilbert-sorted neighbours share (nearly) the same
+    // nearest face, and a seed only has to be close, not right.  If no lane has one, the first lane searches from
+    // the root now.
+    const unsigned cold = __ballot_sync(0xffffffffu, active && seed < 0);
+    if (cold) {
+        const unsigned warm = __ballot_sync(0xffffffffu, active && seed >= 0);
+        int donor;
+        if (warm) donor = __ffs(warm) - 1;
+        else {
+            donor = __ffs(cold) - 1;
+            if ((threadIdx.x & 31) == donor) { tr.top_down(); seed = best.slot; }
+        }
+        const int s0 = __shfl_sync(0xffffffffu, seed, donor);
+        if (seed < 0) seed = s0;
+    }
+    if (active && best.slot < 0) {
+        const float4 c = a.cent[seed];
+        best.offer(q.d2(c), seed, __float_as_int(c.w));
+        tr.from_seed(seed);
+    }
+    // traversal statistics (one atomic per warp and counter)
+    const unsigned t = __reduce_add_sync(0xffffffffu, tr.n_tests), l = __reduce_add_sync(0xffffffffu, tr.n_leaves),
+                   e = __reduce_add_sync(0xffffffffu, tr.n_exact), m = __reduce_max_sync(0xffffffffu, tr.n_tests);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&a.st->trav[0], (unsigned long long)t); atomicAdd(&a.st->trav[1], (unsigned long long)l);
+        atomicAdd(&a.st->trav[2], (unsigned long long)e); atomicMax(&a.st->trav[3], (unsigned long long)m);
+    }
+}
+
+// Cold-start pre-pass: the first point of every 32 (= lane 0 of each warp of k_sweep1) gets an APPROXIMATE nearest
+// face from a root search that stops refining after a fixed number of node tests (a seed only has to be close, the
+// exact search happens in k_sweep1; bounding the effort removes the long tail of near-equidistant queries).
+template <bool F64>
+__global__ void __launch_bounds__(128) k_seed_leaders(const Sweep1Args a) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = t * 32;
+    if (i >= a.P || a.slot[i] >= 0) return;
+    Nearest best;
+    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
+    const float x = a.px[i], y = a.py[i], z = a.pz[i];
+    const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
+    typename std::conditional<F64, QueryF64, QueryF32>::type q;
+    if constexpr (F64) q.set(a.px64[i], a.py64[i], a.pz64[i]);
+    else { q.x = x; q.y = y; q.z = z; }
+    Traversal<decltype(q)> tr(q, best, a.cent, a.boxes, a.tl, a.F, eps);
+    tr.budget = 512;
+    tr.top_down();
+    a.slot[i] = best.slot;     // >= 0: the first descent always reaches a leaf before the budget can run out
+}
+
 // MODE 0: nearest face + weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
 template <bool F64, int MODE>
 __global__ void __launch_bounds__(128) k_sweep1(const Sweep1Args a) {
     if (MODE == 1 && a.st->stop) return;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= a.P) return;
-    const float x = a.px[i], y = a.py[i], z = a.pz[i];
+    const bool active = i < a.P;
+    float x = 0.f, y = 0.f, z = 0.f;
+    double xd = 0.0, yd = 0.0, zd = 0.0;
+    if (active) {
+        x = a.px[i]; y = a.py[i]; z = a.pz[i];
+        xd = x; yd = y; zd = z;
+        if (F64) { xd = a.px64[i]; yd = a.py64[i]; zd = a.pz64[i]; }
+    }
     Nearest best;
     best.d2 = DBL_MAX * 2.0;   // +inf
     best.ub = FLT_MAX * 2.0f;
     best.slot = -1;
     best.face = 0x7fffffff;
-    double xd = x, yd = y, zd = z;
-    const int seed = a.slot[i];
-    if (F64) {
-        xd = a.px64[i]; yd = a.py64[i]; zd = a.pz64[i];
-        QueryF64 q;
-        q.set(xd, yd, zd);
-        if (seed >= 0) { const float4 c = a.cent[seed]; best.offer(q.d2(c), seed, __float_as_int(c.w)); }
-        nearest_centroid(q, best, a.cent, a.boxes, a.tl, a.F);
-    } else {
-        QueryF32 q{x, y, z};
-        if (seed >= 0) { const float4 c = a.cent[seed]; best.offer(q.d2(c), seed, __float_as_int(c.w)); }
-        nearest_centroid(q, best, a.cent, a.boxes, a.tl, a.F);
-    }
+    find_nearest<F64>(a, i, active, x, y, z, xd, yd, zd, best);
+    float u0 = 0.f, u1 = 0.f, u2 = 0.f, r_x = 0.f, r_y = 0.f, r_z = 0.f;
+    int4 sf = make_int4(0, 0, 0, 0);
+    if (active) {
     a.slot[i] = best.slot;
-    const int4 sf = a.sfaces[best.slot];
+    sf = a.sfaces[best.slot];
     const float4 v0 = __ldg(&a.posq[sf.x]), v1 = __ldg(&a.posq[sf.y]), v2 = __ldg(&a.posq[sf.z]);
     // corner distances, mesh_conj_grad.py:491-495 (float32 points: all float32; float64 points: float64 then stored float32)
     float d0, d1, d2;
@@ -187,12 +314,11 @@ __global__ void __launch_bounds__(128) k_sweep1(const Sweep1Args a) {
         d2 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
     }
     // w = 1/max(d,1e-6); w /= w.sum(1)      (:503,510)
-    float u0 = __fdiv_rn(1.0f, fmaxf(d0, 1e-6f)), u1 = __fdiv_rn(1.0f, fmaxf(d1, 1e-6f)), u2 = __fdiv_rn(1.0f, fmaxf(d2, 1e-6f));
+    u0 = __fdiv_rn(1.0f, fmaxf(d0, 1e-6f)); u1 = __fdiv_rn(1.0f, fmaxf(d1, 1e-6f)); u2 = __fdiv_rn(1.0f, fmaxf(d2, 1e-6f));
     const float us = __fadd_rn(__fadd_rn(u0, u1), u2);
     u0 = __fdiv_rn(u0, us); u1 = __fdiv_rn(u1, us); u2 = __fdiv_rn(u2, us);
     a.w0[i] = u0; a.w1[i] = u1; a.w2[i] = u2;
-    if (MODE == 0) return;
-
+    if (MODE == 1) {
     // A f  (:544-545)
     const float afx = __fadd_rn(__fadd_rn(__fmul_rn(v0.x, u0), __fmul_rn(v1.x, u1)), __fmul_rn(v2.x, u2));
     const float afy = __fadd_rn(__fadd_rn(__fmul_rn(v0.y, u0), __fmul_rn(v1.y, u1)), __fmul_rn(v2.y, u2));
@@ -207,7 +333,6 @@ __global__ void __launch_bounds__(128) k_sweep1(const Sweep1Args a) {
         wnz = __fdiv_rn(a.wz == a.sz ? s_z : a.wz[i], a.wmean);
     } else wnx = wny = wnz = a.sinv_scalar;
     const double D = sqrt(best.d2);
-    float r_x, r_y, r_z;
     if (F64) {
         r_x = (float)((double)wnx * (xd - (double)afx)); r_y = (float)((double)wny * (yd - (double)afy)); r_z = (float)((double)wnz * (zd - (double)afz));
     } else {
@@ -217,19 +342,29 @@ __global__ void __launch_bounds__(128) k_sweep1(const Sweep1Args a) {
     r_y = (float)((double)r_y * (1.0 / (D * (double)s_y / 2.0 + 1.0)));
     r_z = (float)((double)r_z * (1.0 / (D * (double)s_z / 2.0 + 1.0)));
     a.rx[i] = r_x; a.ry[i] = r_y; a.rz[i] = r_z;
-    if (!(r_x == r_x && r_y == r_y && r_z == r_z && fabsf(r_x) <= FLT_MAX && fabsf(r_y) <= FLT_MAX && fabsf(r_z) <= FLT_MAX))
-        a.st->nan_flag = 1;
-    // deterministic adjoint: S0 += w_j res, influence += w_j, in fixed point (conj_grad_utils.c:153-162)
+    if (!(fabsf(r_x) <= FLT_MAX && fabsf(r_y) <= FLT_MAX && fabsf(r_z) <= FLT_MAX)) a.st->nan_flag = 1;
+    }
+    }
+    if (MODE == 0) return;
+    // ---- deterministic adjoint: S0 += w_j res, influence += w_j, in 64-bit fixed point (conj_grad_utils.c:153-162).
+    // Lanes whose point landed on the same face are summed inside the warp first (exact integer sums), so a face
+    // costs 12 global RED.64 per warp instead of 12 per point and the lanes of a warp never collide on an address.
     const double sc = pow2d(a.st->acc_shift), sci = pow2d(a.st->infl_shift);
-    const int vid[3] = {sf.x, sf.y, sf.z};
+    const int key = active ? best.slot : -1 - (int)(threadIdx.x & 31);
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const bool lead = active && ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1));
     const float uw[3] = {u0, u1, u2};
+    const int vid[3] = {sf.x, sf.y, sf.z};
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        unsigned long long *dst = a.acc + 4 * (size_t)vid[j];
-        red_fixed(dst + 0, __fmul_rn(uw[j], r_x), sc);
-        red_fixed(dst + 1, __fmul_rn(uw[j], r_y), sc);
-        red_fixed(dst + 2, __fmul_rn(uw[j], r_z), sc);
-        red_fixed(dst + 3, uw[j], sci);
+        const unsigned long long gx = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
+        const unsigned long long gy = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
+        const unsigned long long gz = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
+        const unsigned long long gi = group_sum(grp, to_fixed(uw[j], sci));
+        if (lead) {
+            unsigned long long *dst = a.acc + 4 * (size_t)vid[j];
+            atomicAdd(dst + 0, gx); atomicAdd(dst + 1, gy); atomicAdd(dst + 2, gz); atomicAdd(dst + 3, gi);
+        }
     }
 }
 
@@ -248,24 +383,36 @@ __global__ void __launch_bounds__(256) k_apply_A(int64_t P, const int *__restric
     yz[i] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u0), __fmul_rn(b.z, u1)), __fmul_rn(c.z, u2));
 }
 
-// out_v += sum w_pj r_p  (Ahfunc) into the fixed-point accumulators; acc.w untouched
+// out_v += sum w_pj r_p  (Ahfunc) into the fixed-point accumulators; acc.w untouched.  Same warp-level
+// pre-aggregation by face as k_sweep1.
 __global__ void __launch_bounds__(256) k_apply_AH(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
                                                   const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
                                                   const float *__restrict__ rx, const float *__restrict__ ry, const float *__restrict__ rz,
                                                   unsigned long long *__restrict__ acc, int shift) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const int4 sf = __ldg(&sfaces[slot[i]]);
-    const float uw[3] = {w0[i], w1[i], w2[i]};
-    const float r_x = rx[i], r_y = ry[i], r_z = rz[i];
+    const bool active = i < P;
+    int sl = -1 - (int)(threadIdx.x & 31);
+    int4 sf = make_int4(0, 0, 0, 0);
+    float uw[3] = {0.f, 0.f, 0.f}, r_x = 0.f, r_y = 0.f, r_z = 0.f;
+    if (active) {
+        sl = slot[i];
+        sf = __ldg(&sfaces[sl]);
+        uw[0] = w0[i]; uw[1] = w1[i]; uw[2] = w2[i];
+        r_x = rx[i]; r_y = ry[i]; r_z = rz[i];
+    }
     const double sc = pow2d(shift);
+    const unsigned grp = __match_any_sync(0xffffffffu, sl);
+    const bool lead = active && ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1));
     const int vid[3] = {sf.x, sf.y, sf.z};
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        unsigned long long *dst = acc + 4 * (size_t)vid[j];
-        red_fixed(dst + 0, __fmul_rn(uw[j], r_x), sc);
-        red_fixed(dst + 1, __fmul_rn(uw[j], r_y), sc);
-        red_fixed(dst + 2, __fmul_rn(uw[j], r_z), sc);
+        const unsigned long long gx = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
+        const unsigned long long gy = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
+        const unsigned long long gz = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
+        if (lead) {
+            unsigned long long *dst = acc + 4 * (size_t)vid[j];
+            atomicAdd(dst + 0, gx); atomicAdd(dst + 1, gy); atomicAdd(dst + 2, gz);
+        }
     }
 }
 
@@ -434,11 +581,24 @@ static Sweep1Args make_args(nw_ctx *h) {
     return a;
 }
 
+int nw_launch_seed_leaders(nw_ctx *h) {
+    if (h->P == 0 || !h->seeds_cold) return NW_OK;
+    const int B = 128;
+    Sweep1Args a = make_args(h);
+    const int GL = nw_grid((h->P + 31) / 32, B);
+    if (h->px64) k_seed_leaders<true><<<GL, B, 0, h->stream>>>(a);
+    else k_seed_leaders<false><<<GL, B, 0, h->stream>>>(a);
+    NW_LAUNCH_CHECK();
+    h->seeds_cold = false;
+    return NW_OK;
+}
+
 int nw_launch_sweep1(nw_ctx *h, bool scatter) {
     if (h->P == 0) return NW_OK;
     const int B = 128;
     Sweep1Args a = make_args(h);
     const int G = nw_grid(h->P, B);
+    NW_CHECK(nw_launch_seed_leaders(h));
     if (h->px64) {
         if (scatter) k_sweep1<true, 1><<<G, B, 0, h->stream>>>(a);
         else k_sweep1<true, 0><<<G, B, 0, h->stream>>>(a);
@@ -489,7 +649,9 @@ extern "C" int nw_compute_weights(nw_ctx *h) {
     if (!h) return NW_ERR_ARG;
     NW_ARG(h->M > 0 && (h->px || h->P == 0), "nw_compute_weights: points and topology must be set first");
     NW_CUDA(cudaSetDevice(h->device));
+    NW_CUDA(cudaMemsetAsync(h->st, 0, sizeof(SolverState), h->stream));
     NW_CHECK(nw_tree_refit(h));
+    NW_CHECK(nw_set_acc_shifts(h));             // also refreshes the coordinate bound used by the box tests
     NW_CHECK(nw_launch_sweep1(h, false));
     NW_CUDA(cudaStreamSynchronize(h->stream));
     h->weights_valid = true;

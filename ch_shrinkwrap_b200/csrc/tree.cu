@@ -83,7 +83,8 @@ __global__ void k_face_keys(const int *__restrict__ faces, const float4 *__restr
     unsigned qx = (unsigned)fminf(fmaxf((c.x - lo.x) * inv, 0.f), 1023.f);
     unsigned qy = (unsigned)fminf(fmaxf((c.y - lo.y) * inv, 0.f), 1023.f);
     unsigned qz = (unsigned)fminf(fmaxf((c.z - lo.z) * inv, 0.f), 1023.f);
-    keys[f] = spread10(qx) | (spread10(qy) << 1) | (spread10(qz) << 2);
+    hilbert_axes_to_transpose(qx, qy, qz, 10);
+    keys[f] = (spread10(qx) << 2) | (spread10(qy) << 1) | spread10(qz);
     idx[f] = f;
 }
 
@@ -94,49 +95,147 @@ __global__ void k_sorted_faces(const int *__restrict__ faces, const int *__restr
     sfaces[i] = make_int4(faces[3 * f], faces[3 * f + 1], faces[3 * f + 2], f);
 }
 
-// centroids at the current f (sorted order) + leaf boxes: 8 lanes cooperate on one leaf
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// orthonormal completion of a unit vector (Duff et al. 2017, branchless): returns t1; t2 = n x t1 everywhere
+__device__ __forceinline__ float3 tangent_of(const float3 n) {
+    const float sg = copysignf(1.0f, n.z);
+    const float a = -1.0f / (sg + n.z);
+    const float b = n.x * n.y * a;
+    return make_float3(1.0f + sg * n.x * n.x * a, sg * b, -sg * n.x);
+}
+__device__ __forceinline__ float3 unit_or_z(float3 n) {
+    const float nn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    if (nn > 1e-20f && nn <= FLT_MAX) return make_float3(n.x / nn, n.y / nn, n.z / nn);
+    return make_float3(0.f, 0.f, 1.f);
+}
+__device__ __forceinline__ void project3(const float3 n, const float3 t1, const float4 c, float &pn, float &p1, float &p2) {
+    const float3 t2 = make_float3(n.y * t1.z - n.z * t1.y, n.z * t1.x - n.x * t1.z, n.x * t1.y - n.y * t1.x);
+    pn = fmaf(n.x, c.x, fmaf(n.y, c.y, n.z * c.z));
+    p1 = fmaf(t1.x, c.x, fmaf(t1.y, c.y, t1.z * c.z));
+    p2 = fmaf(t2.x, c.x, fmaf(t2.y, c.y, t2.z * c.z));
+}
+
+// centroids at the current f (sorted order) + leaf boxes: 8 lanes cooperate on one leaf.
+// Leaf normal = normalised sum of the member faces' area-weighted normals.
 __global__ void k_refit_leaves(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F,
                                float4 *__restrict__ cent, Box *__restrict__ leaf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float3 c = make_float3(0.f, 0.f, 0.f);
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    float3 fn = make_float3(0.f, 0.f, 0.f);
     bool live = i < F;
     if (live) {
         int4 sf = sfaces[i];
-        c = centroid_f32(pos[sf.x], pos[sf.y], pos[sf.z]);
-        cent[i] = make_float4(c.x, c.y, c.z, __int_as_float(sf.w));
+        const float4 a = pos[sf.x], b = pos[sf.y], d = pos[sf.z];
+        const float3 cc = centroid_f32(a, b, d);
+        c = make_float4(cc.x, cc.y, cc.z, __int_as_float(sf.w));
+        cent[i] = c;
+        const float ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, vx = d.x - a.x, vy = d.y - a.y, vz = d.z - a.z;
+        fn = make_float3(uy * vz - uz * vy, uz * vx - ux * vz, ux * vy - uy * vx);
+        if (!(fabsf(fn.x) <= FLT_MAX && fabsf(fn.y) <= FLT_MAX && fabsf(fn.z) <= FLT_MAX)) fn = make_float3(0.f, 0.f, 0.f);
     }
-    float lo[3] = {live ? c.x : FLT_MAX, live ? c.y : FLT_MAX, live ? c.z : FLT_MAX};
-    float hi[3] = {live ? c.x : -FLT_MAX, live ? c.y : -FLT_MAX, live ? c.z : -FLT_MAX};
-    for (int a = 0; a < 3; ++a)
+    for (int o = NW_LEAF / 2; o; o >>= 1) {
+        fn.x += __shfl_xor_sync(0xffffffffu, fn.x, o); fn.y += __shfl_xor_sync(0xffffffffu, fn.y, o); fn.z += __shfl_xor_sync(0xffffffffu, fn.z, o);
+    }
+    const float3 n = unit_or_z(fn);
+    const float3 t1 = tangent_of(n);
+    float p[3];
+    project3(n, t1, c, p[0], p[1], p[2]);
+    float mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) {
+        const bool ok = live && (p[k] == p[k]);
+        mn[k] = ok ? p[k] : FLT_MAX; mx[k] = ok ? p[k] : -FLT_MAX;
         for (int o = NW_LEAF / 2; o; o >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
         }
+    }
     if ((threadIdx.x & (NW_LEAF - 1)) == 0 && live) {
         Box b;
-        b.lo = make_float4(lo[0], lo[1], lo[2], 0.f);
-        b.hi = make_float4(hi[0], hi[1], hi[2], 0.f);
+        b.a = make_float4(n.x, n.y, n.z, t1.x);
+        b.b = make_float4(t1.y, t1.z, mn[0], mx[0]);
+        b.c = make_float4(mn[1], mx[1], mn[2], mx[2]);
         leaf[i / NW_LEAF] = b;
     }
 }
 
-// one interior level: node i = union of children [4i, 4i+4)
+// one interior level: node i covers children [4i, 4i+4); normal = normalised sum of child normals.  Intervals start
+// empty (ordered-int encoding) and are filled by k_box_extents.
 __global__ void k_refit_level(const Box *__restrict__ child, int n_child, Box *__restrict__ parent, int n_parent) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_parent) return;
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float3 n = make_float3(0.f, 0.f, 0.f);
     for (int k = 0; k < NW_FAN; ++k) {
         int c = NW_FAN * i + k;
-        if (c < n_child) {
-            Box b = child[c];
-            lo[0] = fminf(lo[0], b.lo.x); lo[1] = fminf(lo[1], b.lo.y); lo[2] = fminf(lo[2], b.lo.z);
-            hi[0] = fmaxf(hi[0], b.hi.x); hi[1] = fmaxf(hi[1], b.hi.y); hi[2] = fmaxf(hi[2], b.hi.z);
+        if (c < n_child) { const float4 a = child[c].a; n.x += a.x; n.y += a.y; n.z += a.z; }
+    }
+    const float nn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    n = (nn > 1e-3f) ? unit_or_z(n) : make_float3(0.f, 0.f, 1.f);
+    const float3 t1 = tangent_of(n);
+    const float e0 = __int_as_float(f2ord(FLT_MAX)), e1 = __int_as_float(f2ord(-FLT_MAX));
+    Box b;
+    b.a = make_float4(n.x, n.y, n.z, t1.x);
+    b.b = make_float4(t1.y, t1.z, e0, e1);
+    b.c = make_float4(e0, e1, e0, e1);
+    parent[i] = b;
+}
+
+// box extents of interior levels: every centroid projects onto its ancestors' axes.  A level-l node covers
+// NW_LEAF * NW_FAN^l consecutive slots: below 32 the reduction is a sub-warp shuffle, from 32 a warp shuffle (one
+// atomic pair per warp and axis), from 256 (one CTA inside one node) it goes through shared memory (one pair per CTA).
+__global__ void __launch_bounds__(256) k_box_extents(const float4 *__restrict__ cent, int F, Box *__restrict__ boxes, TreeLevels tl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < F;
+    const float4 c = live ? cent[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ float smn[3][8], smx[3][8];
+    int node = i / NW_LEAF;
+    int span = NW_LEAF;
+    for (int l = 1; l < tl.n_levels; ++l) {
+        node /= NW_FAN;
+        span = min(span * NW_FAN, 1 << 20);
+        const int nd = min(node, tl.count[l] - 1);          // lanes past F still take part in the shuffles
+        Box *b = &boxes[tl.offset[l] + nd];
+        const float4 ba = b->a, bb = b->b;
+        float p[3];
+        project3(make_float3(ba.x, ba.y, ba.z), make_float3(ba.w, bb.x, bb.y), c, p[0], p[1], p[2]);
+        float mn[3], mx[3];
+        const int width = min(span, 32);
+        for (int k = 0; k < 3; ++k) {
+            const bool ok = live && (p[k] == p[k]);
+            mn[k] = ok ? p[k] : FLT_MAX; mx[k] = ok ? p[k] : -FLT_MAX;
+            for (int o = width / 2; o; o >>= 1) {
+                mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+                mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+            }
+        }
+        int *dmin[3] = {(int *)&b->b.z, (int *)&b->c.x, (int *)&b->c.z};
+        int *dmax[3] = {(int *)&b->b.w, (int *)&b->c.y, (int *)&b->c.w};
+        if (span < 256) {
+            if ((lane & (width - 1)) == 0)
+                for (int k = 0; k < 3; ++k) if (mn[k] <= mx[k]) { atomicMin(dmin[k], f2ord(mn[k])); atomicMax(dmax[k], f2ord(mx[k])); }
+        } else {
+            __syncthreads();
+            if (lane == 0) for (int k = 0; k < 3; ++k) { smn[k][wid] = mn[k]; smx[k][wid] = mx[k]; }
+            __syncthreads();
+            if (threadIdx.x < 3) {
+                const int k = threadIdx.x;
+                float a = smn[k][0], z = smx[k][0];
+                for (int w = 1; w < 8; ++w) { a = fminf(a, smn[k][w]); z = fmaxf(z, smx[k][w]); }
+                if (a <= z) { atomicMin(dmin[k], f2ord(a)); atomicMax(dmax[k], f2ord(z)); }
+            }
         }
     }
-    Box b;
-    b.lo = make_float4(lo[0], lo[1], lo[2], 0.f);
-    b.hi = make_float4(hi[0], hi[1], hi[2], 0.f);
-    parent[i] = b;
+}
+// ordered-int -> float for the extents written by k_box_extents
+__global__ void k_box_decode(Box *__restrict__ boxes, int first, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Box *b = &boxes[first + i];
+    b->b.z = ord2f(__float_as_int(b->b.z)); b->b.w = ord2f(__float_as_int(b->b.w));
+    b->c.x = ord2f(__float_as_int(b->c.x)); b->c.y = ord2f(__float_as_int(b->c.y));
+    b->c.z = ord2f(__float_as_int(b->c.z)); b->c.w = ord2f(__float_as_int(b->c.w));
 }
 
 inline float ordered_to_float(int v) {
@@ -190,6 +289,7 @@ extern "C" int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, co
     nw_free(&d_nbr);
     // nearest-face slots refer to the previous block's sort order
     if (h->slot && h->P) NW_CUDA(cudaMemsetAsync(h->slot, 0xff, sizeof(int) * h->P, s));
+    h->seeds_cold = true;
     return nw_tree_build(h);
 }
 
@@ -209,6 +309,7 @@ int nw_tree_build(nw_ctx *h) {
     for (int a = 0; a < 3; ++a) { lo[a] = ordered_to_float(bb[a]); hi[a] = ordered_to_float(bb[3 + a]); }
     float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     float inv = (ext > 0.f && ext < FLT_MAX) ? 1023.f / ext : 0.f;
+
     NW_CHECK(nw_alloc(h, &keys, (size_t)F)); NW_CHECK(nw_alloc(h, &keys2, (size_t)F));
     NW_CHECK(nw_alloc(h, &idx, (size_t)F)); NW_CHECK(nw_alloc(h, &order, (size_t)F));
     k_face_keys<<<nw_grid(F, B), B, 0, s>>>(h->faces, h->posq, F, make_float3(lo[0], lo[1], lo[2]), inv, keys, idx);
@@ -244,6 +345,13 @@ int nw_tree_refit(nw_ctx *h) {
     for (int l = 1; l < tl.n_levels; ++l) {
         k_refit_level<<<nw_grid(tl.count[l], B), B, 0, s>>>(h->boxes + tl.offset[l - 1], tl.count[l - 1],
                                                              h->boxes + tl.offset[l], tl.count[l]);
+        NW_LAUNCH_CHECK();
+    }
+    if (tl.n_levels > 1) {
+        k_box_extents<<<nw_grid(h->F, B), B, 0, s>>>(h->cent, h->F, h->boxes, tl);
+        NW_LAUNCH_CHECK();
+        const int first = tl.offset[1], count = tl.offset[tl.n_levels - 1] + tl.count[tl.n_levels - 1] - tl.offset[1];
+        k_box_decode<<<nw_grid(count, B), B, 0, s>>>(h->boxes, first, count);
         NW_LAUNCH_CHECK();
     }
     return NW_OK;

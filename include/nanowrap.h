@@ -130,11 +130,14 @@ int nw_neck_candidates(nw_ctx *h, float low, float high, int32_t *idx, int *n);
 int nw_bench_kernel(nw_ctx *h, const char *name, int reps, float *ms_per_launch);
 int nw_sync(nw_ctx *h);
 /* CUDA-event timing on the handle's stream: on = 1 brackets every stage of every iteration inside
- * nw_search.  nw_get_profile returns accumulated ms and kernel launches per stage (8 stages: refit,
- * shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update) and the event-
+ * nw_search.  nw_get_profile returns accumulated ms and kernel launches per stage (9 stages: refit,
+ * shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders) and the event-
  * timed duration of the last nw_search call (first kernel to last kernel). */
 int nw_set_profile(nw_ctx *h, int on);
 int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms);
+/* nearest-face traversal statistics accumulated since the last nw_search / nw_ncc / nw_bench_kernel state reset:
+ * node bound tests, leaf visits, exact fp64 distance evaluations, largest node-test count of a single point */
+int nw_get_traversal_stats(nw_ctx *h, uint64_t out[4]);
 /* kernels launched by this handle since creation (for bench.py's gpu_launches) */
 int64_t nw_launch_count(nw_ctx *h);
 
