@@ -1,0 +1,112 @@
+"""Host-side logic: mini-mesh invariants, synthetic generators, facade schedule, shim argument handling."""
+import numpy as np
+import pytest
+
+from conftest import make_case
+
+
+def test_minimesh_halfedge_invariants():
+    from ch_shrinkwrap_b200 import minimesh
+    m = minimesh.sphere_mesh(10.0, 5)
+    he, v, f = m._halfedges, m._vertices, m._faces
+    assert len(v) == 10 * 25 + 2 and len(f) == 20 * 25
+    assert np.all(he['twin'][he['twin']] == np.arange(len(he)))          # closed surface: twins pair up
+    assert np.all(he['next'][he['prev']] == np.arange(len(he)))
+    # face corner order: prev.vertex, h.vertex, next.vertex == mesh.faces rows (membrane_mesh_utils.c:1271-1274)
+    h = f['halfedge']
+    rec = np.stack([he['vertex'][he['prev'][h]], he['vertex'][h], he['vertex'][he['next'][h]]], 1)
+    assert np.array_equal(rec, m.faces)
+    # neighbours are OUTGOING half-edges, ring ordered, -1 terminated; valence 5 or 6 on a geodesic sphere
+    nb = v['neighbors']
+    val = (nb != -1).sum(1)
+    assert set(np.unique(val)) <= {5, 6} and np.array_equal(val, v['valence'])
+    src = he['vertex'][he['prev']]
+    for i in (0, 7, 100):
+        hs = nb[i][nb[i] != -1]
+        assert np.all(src[hs] == i)
+        assert len(set(he['vertex'][hs])) == len(hs)
+    assert abs(m.area() - 4 * np.pi * 100.0) / (4 * np.pi * 100.0) < 0.02
+    assert np.allclose(np.linalg.norm(m.vertex_normals, axis=1), 1.0, atol=1e-5)
+    assert np.all((m.vertex_normals * m.vertices).sum(1) > 0)              # outward
+
+
+def test_minimesh_open_boundary():
+    from ch_shrinkwrap_b200 import minimesh
+    m = minimesh.planar_mesh(4.0, 4)
+    assert (m._halfedges['twin'] == -1).sum() == 16
+    assert np.all(m._vertices['valence'] >= 1)
+    nv = m.neighbor_vertices()
+    assert nv.shape == (25, 20) and nv.max() < 25
+
+
+def test_geodesic_counts():
+    from ch_shrinkwrap_b200 import minimesh
+    for n in (1, 2, 3, 7):
+        v, f = minimesh.geodesic_sphere(n)
+        assert len(v) == 10 * n * n + 2 and len(f) == 20 * n * n
+        assert np.allclose(np.linalg.norm(v, axis=1), 1.0)
+        e = set()
+        for a, b, c in f:
+            e |= {(a, b), (b, c), (c, a)}
+        assert all((b, a) in e for a, b in e)                              # consistently oriented, closed
+
+
+def test_synth_cloud_is_seeded_and_on_surface():
+    from ch_shrinkwrap_b200 import synth
+    shape = synth.two_lobed()
+    p1, s1 = synth.smlm_cloud(shape, 2000, seed=4)
+    p2, s2 = synth.smlm_cloud(shape, 2000, seed=4)
+    assert np.array_equal(p1, p2) and np.array_equal(s1, s2)
+    d = np.abs(shape.sdf(p1.astype(np.float64)))
+    assert np.median(d) < 15.0                       # jitter ~ localisation precision
+    assert (d > 60).mean() > 0.03                    # ~10 % background
+    assert 3.0 < np.median(s1[:, 0]) < 9.0 and np.median(s1[:, 2]) > 2.5 * np.median(s1[:, 0])
+    v, f = __import__('ch_shrinkwrap_b200.minimesh', fromlist=['x']).geodesic_sphere(12)
+    r = synth.radial_surface(shape, v)
+    a, _ = synth.mesh_surface_cloud(v * r[:, None], f, 5000, seed=1, threads=1)
+    b, _ = synth.mesh_surface_cloud(v * r[:, None], f, 5000, seed=1, threads=4)
+    assert np.array_equal(a, b)
+
+
+def test_facade_block_schedule_matches_reference_driver():
+    """opt_conjugate_gradient block structure (_membrane_mesh.pyx:1430-1517) with the solver stubbed out."""
+    from ch_shrinkwrap_b200 import membrane_mesh as mm
+    from ch_shrinkwrap_b200 import minimesh
+    calls = []
+
+    class FakeCG:
+        def __init__(self, mesh, points, **kw):
+            calls.append(['new'])
+
+        def search(self, points, lams, num_iters, sigma_inv, weights):
+            calls[-1] += [num_iters, lams, np.isscalar(sigma_inv) or sigma_inv.shape]
+    real = mm.ShrinkwrapMeshConjGrad
+    mm.ShrinkwrapMeshConjGrad = FakeCG
+    try:
+        v, f = minimesh.geodesic_sphere(3)
+        m = mm.MembraneMesh(v * 100, f, kc=1.0, step_size=20.0, remesh_frequency=5, delaunay_remesh_frequency=0, max_iter=12)
+        pts = np.zeros((10, 3), np.float32)
+        n = m.shrink_wrap(pts, np.full((10, 3), 2.0, np.float32), minimum_edge_length=5)
+        assert n == 12 and [c[1] for c in calls] == [5, 5, 2]
+        assert calls[0][2] == [10.0] and calls[0][3] == (30,)             # lam = step_size*kc/2 ; sigma (P,3) -> 1/sigma raveled
+        calls.clear()
+        m.remesh_frequency = 0
+        m.shrink_wrap(pts, 7.0, max_iter=4)                                # scalar sigma passes through un-inverted (:1460)
+        assert [c[1] for c in calls] == [4] and calls[0][3] is True
+        with pytest.raises(ValueError):
+            m.shrink_wrap(pts, np.ones((3, 2)), max_iter=2)
+        calls.clear()
+        m.truncate_at = 3
+        m.shrink_wrap(pts, 7.0, max_iter=10)
+        assert sum(c[1] for c in calls) == 3
+    finally:
+        mm.ShrinkwrapMeshConjGrad = real
+
+
+def test_recipe_module_surface():
+    from ch_shrinkwrap_b200.recipe_modules.surface_fitting import ShrinkwrapMembrane
+    mod = ShrinkwrapMembrane()
+    # trait names and defaults of the reference module (surface_fitting.py:13-42)
+    assert mod.max_iters == 39 and mod.curvature_weight == 20.0 and mod.remesh_frequency == 5
+    assert mod.neck_threshold_low == -1e-3 and mod.neck_threshold_high == 1e-2 and mod.neck_first_iter == 9
+    assert mod.kc == 1.0 and mod.minimum_edge_length == 5 and mod.sigma_x == 'error_x'

@@ -1,0 +1,103 @@
+"""N>1 host logic on CPU (gloo, world_size 2): points are sharded, the mesh is replicated, one iteration exchanges the
+vertex accumulators and a handful of scalars.  The oracle stands in for the per-rank compute so the
+sharding / reduction logic can run without a GPU; the GPU library performs the same exchange with NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def shard_bounds(P, rank, world):
+    """Contiguous shards of the caller's point order (what bench.py / a multi-GPU caller hands each rank)."""
+    base, rem = divmod(P, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import make_case
+    from oracle import nanowrap_oracle as orc
+    mesh, pts, sig = make_case(n_points=3001, n_geo=4, seed=77)
+    s_inv = (1.0 / sig.ravel()).astype(np.float32)
+    lo, hi = shard_bounds(len(pts), rank, world)
+    # global weight mean: weights / weights.mean() spans ALL ranks (mesh_conj_grad.py:162)
+    t = torch.tensor([float(s_inv[3 * lo:3 * hi].astype(np.float64).sum()), float(3 * (hi - lo))], dtype=torch.float64)
+    dist.all_reduce(t)
+    wmean = np.float32(t[0].item() / t[1].item())
+    oc = orc.OracleConjGrad(mesh, pts[lo:hi])
+    oc.f = oc.vertices.copy().ravel()
+    oc.w = oc.compute_weights(oc.f)
+    oc._prev_loopcount = oc.loopcount
+    data = pts[lo:hi].ravel()
+    res = (s_inv[3 * lo:3 * hi] / wmean) * (data - oc.Afunc(oc.f))
+    res = (res * (1.0 / (oc.d.ravel() * s_inv[3 * lo:3 * hi] / 2.0 + 1))).astype(np.float32)
+    # per-rank partial adjoints in exact integer arithmetic (what the GPU does in 64-bit fixed point)
+    v_idx, w = oc.w
+    shift = 20
+    acc = np.zeros((oc.M, 4), np.int64)
+    prod = (w[:, :, None] * res.reshape(-1, 3)[:, None, :]).astype(np.float32)       # (P,3 corners,3 axes)
+    fx = np.rint(prod.astype(np.float64) * 2.0 ** shift).astype(np.int64)
+    for j in range(3):
+        np.add.at(acc[:, :3], v_idx[:, j], fx[:, j, :])
+        np.add.at(acc[:, 3], v_idx[:, j], np.rint(w[:, j].astype(np.float64) * 2.0 ** 30).astype(np.int64))
+    ta = torch.from_numpy(acc)
+    dist.all_reduce(ta)
+    c0 = torch.tensor([float((res.astype(np.float64) ** 2).sum())], dtype=torch.float64)
+    dist.all_reduce(c0)
+    if rank == 0:
+        q.put((ta.numpy().copy(), float(c0.item()), float(wmean)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_everything():
+    for P in (0, 1, 7, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(P, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == P
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_sharded_adjoint_and_scalars_equal_unsharded():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    port = _free_port()
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    acc2, c02, wmean2 = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # world_size 1, same code path
+    port = _free_port()
+    q1 = ctx.Queue()
+    p1 = ctx.Process(target=_worker, args=(0, 1, port, q1))
+    p1.start()
+    acc1, c01, wmean1 = q1.get(timeout=180)
+    p1.join(60)
+    assert wmean1 == pytest.approx(wmean2, rel=1e-7)
+    # integer accumulators: sharding-invariant bit for bit when the global mean is the same float32
+    if wmean1 == wmean2:
+        assert np.array_equal(acc1, acc2)
+    else:
+        assert np.allclose(acc1 / 2.0 ** 20, acc2 / 2.0 ** 20, rtol=1e-5, atol=1e-3)
+    assert c01 == pytest.approx(c02, rel=1e-6)
