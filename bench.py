@@ -295,6 +295,9 @@ def main():
         except Exception as e:      # noqa
             kernels[name] = {'error': str(e)}
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     cpu = None

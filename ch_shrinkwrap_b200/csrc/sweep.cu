@@ -159,19 +159,37 @@ struct Traversal {
         expand(top, 0, tl.count[top], -1);
         run();
     }
-    // warm query: start at the seed's leaf and climb; at every level only the siblings are tested
+    // Stackless depth-first search of the subtree rooted at (L, I).  The hierarchy is implicit (children of node i
+    // are 4i..4i+3), so "next node" is index arithmetic and no per-thread stack (local memory) is needed.  Children
+    // are visited in index order: with a seed the bound is already (nearly) exact, so nearest-first ordering would
+    // buy nothing.
+    __device__ __forceinline__ void dfs_subtree(int L, int I) {
+        int level = L, idx = I;
+        while (true) {
+            ++n_tests;
+            if (node_lb(q, &boxes[tl.offset[level] + idx], eps) <= best.ub) {
+                if (level == 0) leaf(idx);
+                else { --level; idx *= NW_FAN; continue; }
+            }
+            while (true) {
+                if (level == L) return;
+                if ((idx % NW_FAN) != NW_FAN - 1 && idx + 1 < tl.count[level]) { ++idx; break; }
+                ++level; idx /= NW_FAN;
+            }
+        }
+    }
+    // warm query: start at the seed's leaf and climb; at every level only the sibling subtrees are searched
     __device__ __forceinline__ void from_seed(int seed_slot) {
         int node = seed_slot / NW_LEAF;
         leaf(node);
         const int top = tl.n_levels - 1;
-        for (int level = 0; level < top; ++level) {
-            const int parent = node / NW_FAN, c0 = parent * NW_FAN;
-            expand(level, c0, min(NW_FAN, tl.count[level] - c0), node);
-            run();
-            node = parent;
+        for (int level = 0; level <= top; ++level) {
+            const int c0 = (level < top) ? (node / NW_FAN) * NW_FAN : 0;
+            const int n = min(NW_FAN, tl.count[level] - c0);
+            for (int k = 0; k < n; ++k)
+                if (c0 + k != node) dfs_subtree(level, c0 + k);
+            node /= NW_FAN;
         }
-        expand(top, 0, tl.count[top], node);
-        run();
     }
 };
 
