@@ -48,7 +48,7 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free(&h->rx); nw_free(&h->ry); nw_free(&h->rz);
     nw_free(&h->posq); nw_free(&h->nrmq); nw_free(&h->faces); nw_free(&h->nbrT); nw_free(&h->valence); nw_free(&h->valid);
     nw_free(&h->sfaces); nw_free(&h->cent); nw_free(&h->boxes);
-    nw_free(&h->acc); nw_free(&h->S0); nw_free(&h->S1); nw_free(&h->S2); nw_free(&h->fdef);
+    nw_free(&h->acc); nw_free(&h->Sq); nw_free(&h->fdef);
     nw_free(&h->partials); nw_free(&h->st); nw_free(&h->hist);
     nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP); nw_free(&h->curvK);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -67,15 +67,11 @@ extern "C" int nw_sync(nw_ctx *h) {
 }
 
 static int ensure_partials(nw_ctx *h) {
-    const int want = 148 * 4;
+    // layout: [sweep2 partials: n_partials x 16] [mesh partials: ceil(M/256) x 16] [64 doubles of comm staging]
+    const int want = std::max(1, nw_grid(h->P, 256 * 4));
     const size_t need = (size_t)want * 16 + (size_t)nw_grid(h->M, 256) * 16 + 64;
-    if (h->n_partials != want || !h->partials) {
-        NW_CHECK(nw_alloc(h, &h->partials, need));
-        h->n_partials = want;
-    } else {
-        // M may have changed since the last block
-        NW_CHECK(nw_alloc(h, &h->partials, need));
-    }
+    NW_CHECK(nw_alloc(h, &h->partials, need));
+    h->n_partials = want;
     return NW_OK;
 }
 
@@ -160,9 +156,7 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     if (np == 3 && s.last_tests[2] < s.last_tests[1] && s.last_tests[1] < s.last_tests[0] && s.last_tests[0] < 1e-6) s.stop = 2;
     NW_CHECK(upload_state(h, s));
     // S is freshly zeroed on every search() call (mesh_conj_grad.py:207)
-    NW_CUDA(cudaMemsetAsync(h->S0, 0, sizeof(float4) * h->M, h->stream));
-    NW_CUDA(cudaMemsetAsync(h->S1, 0, sizeof(float4) * h->M, h->stream));
-    NW_CUDA(cudaMemsetAsync(h->S2, 0, sizeof(float4) * h->M, h->stream));
+    NW_CUDA(cudaMemsetAsync(h->Sq, 0, sizeof(float4) * 3 * h->M, h->stream));
     NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * h->M, h->stream));
     if (!h->ev_search0) { NW_CUDA(cudaEventCreate(&h->ev_search0)); NW_CUDA(cudaEventCreate(&h->ev_search1)); }
     h->ev_used = 0;

@@ -89,7 +89,7 @@ struct nw_ctx {
     bool seeds_cold = true;                      // no nearest-face seeds yet for this topology
     // ---- solver vectors ----
     unsigned long long *acc = nullptr;           // (M,4) int64 fixed point: AH res xyz, AH 1
-    float4 *S0 = nullptr, *S1 = nullptr, *S2 = nullptr;
+    float4 *Sq = nullptr;                        // search directions, interleaved: S_k of vertex v at Sq[3v + k] (48 B per vertex)
     double *fdef = nullptr;                      // (M,3)
     double *partials = nullptr;                  // per-CTA partial sums
     int n_partials = 0;

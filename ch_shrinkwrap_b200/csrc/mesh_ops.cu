@@ -61,7 +61,7 @@ template <bool WRITE_DIRS>
 __global__ void __launch_bounds__(256) k_mesh_prior(int M, unsigned long long *__restrict__ acc, SolverState *__restrict__ st,
                                                     const float4 *__restrict__ posq, const float4 *__restrict__ nrmq,
                                                     const int *__restrict__ nbrT, const int *__restrict__ valence,
-                                                    float4 *__restrict__ S0, float4 *__restrict__ S1, const float4 *__restrict__ S2,
+                                                    float4 *__restrict__ Sq,
                                                     double *__restrict__ fdef_out, float *__restrict__ pi_out,
                                                     double *__restrict__ partials) {
     if (st->stop) return;
@@ -137,11 +137,11 @@ __global__ void __launch_bounds__(256) k_mesh_prior(int M, unsigned long long *_
             // prefs = f - f_def (float64 in subsearch, float32 in search); S1 = -prefs
             const double px64 = (double)p.x - fx, py64 = (double)p.y - fy, pz64 = (double)p.z - fz;
             const float s1x = -(float)px64, s1y = -(float)py64, s1z = -(float)pz64;
-            S0[v] = make_float4(s0x, s0y, s0z, 0.f);
-            S1[v] = make_float4(s1x, s1y, s1z, 0.f);
+            Sq[3 * (size_t)v] = make_float4(s0x, s0y, s0z, 0.f);
+            Sq[3 * (size_t)v + 1] = make_float4(s1x, s1y, s1z, 0.f);
             if (!(fabsf(s0x) <= FLT_MAX && fabsf(s0y) <= FLT_MAX && fabsf(s0z) <= FLT_MAX &&
                   fabsf(s1x) <= FLT_MAX && fabsf(s1y) <= FLT_MAX && fabsf(s1z) <= FLT_MAX)) st->nan_flag = 1;
-            const float4 s2 = S2[v];
+            const float4 s2 = Sq[3 * (size_t)v + 2];
             const double a0[3] = {s0x, s0y, s0z}, a1[3] = {s1x, s1y, s1z}, a2[3] = {s2.x, s2.y, s2.z};
             const double pr[3] = {px64, py64, pz64};
 #pragma unroll
@@ -241,19 +241,18 @@ __global__ void k_solve(const double *__restrict__ mesh_partials, int n_mesh_blo
 }
 
 __global__ void __launch_bounds__(256) k_update(int M, SolverState *__restrict__ st, float4 *__restrict__ posq,
-                                                const float4 *__restrict__ S0, const float4 *__restrict__ S1,
-                                                float4 *__restrict__ S2, int last_step, int is_final_launch) {
+                                                float4 *__restrict__ Sq, int last_step, int is_final_launch) {
     // runs for the iteration that k_solve just completed, including the one that set `stop`
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (st->nan_flag == 2) return;
     if (st->stop > 1) return;
     if (v < M) {
         const double c0 = st->c[0], c1 = st->c[1], c2 = st->c[2];
-        const float4 p = posq[v], a = S0[v], b = S1[v], d = S2[v];
+        const float4 p = posq[v], a = Sq[3 * (size_t)v], b = Sq[3 * (size_t)v + 1], d = Sq[3 * (size_t)v + 2];
         const double nx = (double)p.x + (((double)a.x * c0 + (double)b.x * c1) + (double)d.x * c2);
         const double ny = (double)p.y + (((double)a.y * c0 + (double)b.y * c1) + (double)d.y * c2);
         const double nz = (double)p.z + (((double)a.z * c0 + (double)b.z * c1) + (double)d.z * c2);
-        if (last_step) S2[v] = make_float4((float)(nx - (double)p.x), (float)(ny - (double)p.y), (float)(nz - (double)p.z), 0.f);
+        if (last_step) Sq[3 * (size_t)v + 2] = make_float4((float)(nx - (double)p.x), (float)(ny - (double)p.y), (float)(nz - (double)p.z), 0.f);
         const float4 q = make_float4((float)nx, (float)ny, (float)nz, 0.f);
         if (!(fabsf(q.x) <= FLT_MAX && fabsf(q.y) <= FLT_MAX && fabsf(q.z) <= FLT_MAX)) st->nan_flag = 1;
         posq[v] = q;
@@ -277,11 +276,10 @@ __global__ void k_norm3(const float *__restrict__ in, int M, float *__restrict__
     float a = in[3 * v], b = in[3 * v + 1], c = in[3 * v + 2];
     out[v] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
 }
-__global__ void k_S_rows(const float4 *__restrict__ S0, const float4 *__restrict__ S1, const float4 *__restrict__ S2, int M,
-                         float *__restrict__ out) {
+__global__ void k_S_rows(const float4 *__restrict__ Sq, int M, float *__restrict__ out) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= M) return;
-    const float4 a = S0[v], b = S1[v], c = S2[v];
+    const float4 a = Sq[3 * (size_t)v], b = Sq[3 * (size_t)v + 1], c = Sq[3 * (size_t)v + 2];
     float *o = out + 9 * (size_t)v;   // rows 3v..3v+2 of the (3M,3) matrix
     o[0] = a.x; o[1] = b.x; o[2] = c.x;
     o[3] = a.y; o[4] = b.y; o[5] = c.y;
@@ -304,10 +302,10 @@ static int mesh_blocks(nw_ctx *h) { return nw_grid(h->M, 256); }
 int nw_launch_mesh_prior(nw_ctx *h, bool write_dirs) {
     const int G = mesh_blocks(h);
     if (write_dirs)
-        k_mesh_prior<true><<<G, 256, 0, h->stream>>>(h->M, h->acc, h->st, h->posq, h->nrmq, h->nbrT, h->valence, h->S0, h->S1, h->S2,
+        k_mesh_prior<true><<<G, 256, 0, h->stream>>>(h->M, h->acc, h->st, h->posq, h->nrmq, h->nbrT, h->valence, h->Sq,
                                                      h->fdef, nullptr, h->partials + (size_t)h->n_partials * 16);
     else
-        k_mesh_prior<false><<<G, 256, 0, h->stream>>>(h->M, h->acc, h->st, h->posq, h->nrmq, h->nbrT, h->valence, h->S0, h->S1, h->S2,
+        k_mesh_prior<false><<<G, 256, 0, h->stream>>>(h->M, h->acc, h->st, h->posq, h->nrmq, h->nbrT, h->valence, h->Sq,
                                                       h->fdef, h->scratchM, nullptr);
     NW_LAUNCH_CHECK();
     return NW_OK;
@@ -316,7 +314,7 @@ int nw_launch_mesh_prior(nw_ctx *h, bool write_dirs) {
 int nw_launch_solve_update(nw_ctx *h, int iter_index, int last_step) {
     k_solve<<<1, 32, 0, h->stream>>>(h->partials + (size_t)h->n_partials * 16, mesh_blocks(h), h->st, h->hist, iter_index);
     NW_LAUNCH_CHECK();
-    k_update<<<mesh_blocks(h), 256, 0, h->stream>>>(h->M, h->st, h->posq, h->S0, h->S1, h->S2, last_step, 0);
+    k_update<<<mesh_blocks(h), 256, 0, h->stream>>>(h->M, h->st, h->posq, h->Sq, last_step, 0);
     NW_LAUNCH_CHECK();
     k_advance<<<1, 1, 0, h->stream>>>(h->st, last_step);
     NW_LAUNCH_CHECK();
@@ -349,7 +347,7 @@ extern "C" int nw_get_S(nw_ctx *h, float *S) {
     NW_CUDA(cudaSetDevice(h->device));
     float *tmp = nullptr;
     NW_CHECK(nw_alloc(h, &tmp, (size_t)9 * h->M));
-    k_S_rows<<<nw_grid(h->M, 256), 256, 0, h->stream>>>(h->S0, h->S1, h->S2, h->M, tmp);
+    k_S_rows<<<nw_grid(h->M, 256), 256, 0, h->stream>>>(h->Sq, h->M, tmp);
     NW_LAUNCH_CHECK();
     NW_CUDA(cudaMemcpyAsync(S, tmp, sizeof(float) * 9 * h->M, cudaMemcpyDeviceToHost, h->stream));
     NW_CUDA(cudaStreamSynchronize(h->stream));

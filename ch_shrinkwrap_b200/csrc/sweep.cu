@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(128) k_seed_leaders(const Sweep1Args a) {
 template <bool F64, int MODE>
 __global__ void __launch_bounds__(128) k_sweep1(const Sweep1Args a) {
     if (MODE == 1 && a.st->stop) return;
+
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool active = i < a.P;
     float x = 0.f, y = 0.f, z = 0.f;
@@ -308,6 +309,10 @@ __global__ void __launch_bounds__(128) k_sweep1(const Sweep1Args a) {
     best.slot = -1;
     best.face = 0x7fffffff;
     find_nearest<F64>(a, i, active, x, y, z, xd, yd, zd, best);
+    if (active && best.slot < 0) {      // non-finite query: nothing compares; flag it (the reference asserts on NaN) and stay in bounds
+        a.st->nan_flag = 1;
+        best.slot = 0;
+    }
     float u0 = 0.f, u1 = 0.f, u2 = 0.f, r_x = 0.f, r_y = 0.f, r_z = 0.f;
     int4 sf = make_int4(0, 0, 0, 0);
     if (active) {
@@ -450,10 +455,12 @@ __global__ void __launch_bounds__(256) k_apply_infl(int64_t P, const int *__rest
 // ---- Gram pass -------------------------------------------------------------------------------------
 #define NW_NSUM 11   // hc00 hc01 hc11 hc02 hc12 hc22 gc0 gc1 gc2 c0 res2
 
+#define NW_S2_PTS 4      // points per thread: their dependent load chains (slot -> face -> S) overlap
+
 __global__ void __launch_bounds__(256) k_sweep2(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
                                                 const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
                                                 const float *__restrict__ rx, const float *__restrict__ ry, const float *__restrict__ rz,
-                                                const float4 *__restrict__ S0, const float4 *__restrict__ S1, const float4 *__restrict__ S2,
+                                                const float4 *__restrict__ Sq,
                                                 const uint8_t *__restrict__ pmask, const SolverState *__restrict__ st,
                                                 double *__restrict__ partials) {
     if (st->stop) return;
@@ -461,35 +468,40 @@ __global__ void __launch_bounds__(256) k_sweep2(int64_t P, const int *__restrict
     double acc[NW_NSUM];
 #pragma unroll
     for (int k = 0; k < NW_NSUM; ++k) acc[k] = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
-        const int4 sf = __ldg(&sfaces[slot[i]]);
-        const float u0 = w0[i], u1 = w1[i], u2 = w2[i];
-        const float r[3] = {rx[i], ry[i], rz[i]};
-        const unsigned m = pmask ? pmask[i] : 7u;
+    const int64_t base = (int64_t)blockIdx.x * (blockDim.x * NW_S2_PTS) + threadIdx.x;
+    int sl[NW_S2_PTS];
+    float u[NW_S2_PTS][3], r[NW_S2_PTS][3];
+    unsigned m[NW_S2_PTS];
+    int4 sf[NW_S2_PTS];
+#pragma unroll
+    for (int j = 0; j < NW_S2_PTS; ++j) {
+        const int64_t i = base + (int64_t)j * blockDim.x;
+        const bool ok = i < P;
+        sl[j] = ok ? slot[i] : -1;
+        u[j][0] = ok ? w0[i] : 0.f; u[j][1] = ok ? w1[i] : 0.f; u[j][2] = ok ? w2[i] : 0.f;
+        r[j][0] = ok ? rx[i] : 0.f; r[j][1] = ok ? ry[i] : 0.f; r[j][2] = ok ? rz[i] : 0.f;
+        m[j] = ok ? (pmask ? pmask[i] : 7u) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < NW_S2_PTS; ++j) sf[j] = sl[j] >= 0 ? __ldg(&sfaces[sl[j]]) : make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < NW_S2_PTS; ++j) {
+        if (sl[j] < 0) continue;
+        const float4 *pa = Sq + 3 * (size_t)sf[j].x, *pb = Sq + 3 * (size_t)sf[j].y, *pc = Sq + 3 * (size_t)sf[j].z;
         float as[3][3];
-        {
-            const float4 a = __ldg(&S0[sf.x]), b = __ldg(&S0[sf.y]), c = __ldg(&S0[sf.z]);
-            as[0][0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, u0), __fmul_rn(b.x, u1)), __fmul_rn(c.x, u2));
-            as[0][1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, u0), __fmul_rn(b.y, u1)), __fmul_rn(c.y, u2));
-            as[0][2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u0), __fmul_rn(b.z, u1)), __fmul_rn(c.z, u2));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k == 2 && !three) { as[2][0] = as[2][1] = as[2][2] = 0.f; break; }
+            const float4 a = __ldg(pa + k), b = __ldg(pb + k), c = __ldg(pc + k);
+            as[k][0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, u[j][0]), __fmul_rn(b.x, u[j][1])), __fmul_rn(c.x, u[j][2]));
+            as[k][1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, u[j][0]), __fmul_rn(b.y, u[j][1])), __fmul_rn(c.y, u[j][2]));
+            as[k][2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u[j][0]), __fmul_rn(b.z, u[j][1])), __fmul_rn(c.z, u[j][2]));
         }
-        {
-            const float4 a = __ldg(&S1[sf.x]), b = __ldg(&S1[sf.y]), c = __ldg(&S1[sf.z]);
-            as[1][0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, u0), __fmul_rn(b.x, u1)), __fmul_rn(c.x, u2));
-            as[1][1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, u0), __fmul_rn(b.y, u1)), __fmul_rn(c.y, u2));
-            as[1][2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u0), __fmul_rn(b.z, u1)), __fmul_rn(c.z, u2));
-        }
-        if (three) {
-            const float4 a = __ldg(&S2[sf.x]), b = __ldg(&S2[sf.y]), c = __ldg(&S2[sf.z]);
-            as[2][0] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, u0), __fmul_rn(b.x, u1)), __fmul_rn(c.x, u2));
-            as[2][1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, u0), __fmul_rn(b.y, u1)), __fmul_rn(c.y, u2));
-            as[2][2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u0), __fmul_rn(b.z, u1)), __fmul_rn(c.z, u2));
-        } else as[2][0] = as[2][1] = as[2][2] = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const double rr = (double)r[c];
+            const double rr = (double)r[j][c];
             acc[10] += rr * rr;
-            if (m & (1u << c)) {     // res[mask], AS[mask]  (mesh_conj_grad.py:274, conj_grad.py:198)
+            if (m[j] & (1u << c)) {     // res[mask], AS[mask]  (mesh_conj_grad.py:274, conj_grad.py:198)
                 const double a0 = as[0][c], a1 = as[1][c], a2 = as[2][c];
                 acc[0] += a0 * a0; acc[1] += a0 * a1; acc[2] += a1 * a1;
                 acc[3] += a0 * a2; acc[4] += a1 * a2; acc[5] += a2 * a2;
@@ -514,17 +526,29 @@ __global__ void __launch_bounds__(256) k_sweep2(int64_t P, const int *__restrict
     }
 }
 
-// fold the per-CTA partials in fixed order into the solver state
-__global__ void k_fold_partials(const double *__restrict__ partials, int n_blocks, SolverState *st) {
+// fold the per-CTA partials in a fixed order into the solver state: one CTA, thread t sums partials t, t+256, ...
+// of each quantity, then a fixed shared-memory tree -- deterministic for a given P.
+__global__ void __launch_bounds__(256) k_fold_partials(const double *__restrict__ partials, int n_blocks, SolverState *st) {
     if (st->stop) return;
-    const int k = threadIdx.x;
-    if (k >= NW_NSUM) return;
-    double v = 0.0;
-    for (int b = 0; b < n_blocks; ++b) v += partials[(size_t)b * NW_NSUM + k];
-    if (k < 6) st->hc[k] = v;
-    else if (k < 9) st->gc[k - 6] = v;
-    else if (k == 9) st->c0 = v;
-    else st->res2 = v;
+    __shared__ double sh[256];
+    for (int k = 0; k < NW_NSUM; ++k) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < n_blocks; b += 256) v += partials[(size_t)b * NW_NSUM + k];
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 128; o; o >>= 1) {
+            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const double t = sh[0];
+            if (k < 6) st->hc[k] = t;
+            else if (k < 9) st->gc[k - 6] = t;
+            else if (k == 9) st->c0 = t;
+            else st->res2 = t;
+        }
+        __syncthreads();
+    }
 }
 
 // ---- host<->device order conversion -------------------------------------------------------------
@@ -631,10 +655,10 @@ int nw_launch_sweep1(nw_ctx *h, bool scatter) {
 int nw_launch_sweep2(nw_ctx *h) {
     const int B = 256;
     const int G = h->n_partials;
-    k_sweep2<<<G, B, 0, h->stream>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->S0, h->S1, h->S2,
+    k_sweep2<<<G, B, 0, h->stream>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->Sq,
                                       h->has_mask ? h->pmask : nullptr, h->st, h->partials);
     NW_LAUNCH_CHECK();
-    k_fold_partials<<<1, 32, 0, h->stream>>>(h->partials, G, h->st);
+    k_fold_partials<<<1, 256, 0, h->stream>>>(h->partials, G, h->st);
     NW_LAUNCH_CHECK();
     return NW_OK;
 }

@@ -262,7 +262,7 @@ extern "C" int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, co
     NW_CHECK(nw_alloc(h, &h->nbrT, (size_t)NW_NEIGHBORSIZE * M)); NW_CHECK(nw_alloc(h, &h->valence, (size_t)M));
     NW_CHECK(nw_alloc(h, &h->valid, (size_t)M));
     NW_CHECK(nw_alloc(h, &h->acc, (size_t)4 * M));
-    NW_CHECK(nw_alloc(h, &h->S0, (size_t)M)); NW_CHECK(nw_alloc(h, &h->S1, (size_t)M)); NW_CHECK(nw_alloc(h, &h->S2, (size_t)M));
+    NW_CHECK(nw_alloc(h, &h->Sq, (size_t)3 * M));
     NW_CHECK(nw_alloc(h, &h->fdef, (size_t)3 * M));
     NW_CHECK(nw_alloc(h, &h->scratchM, (size_t)3 * M));
     NW_CHECK(nw_alloc(h, &h->sfaces, (size_t)F)); NW_CHECK(nw_alloc(h, &h->cent, (size_t)F));
@@ -282,9 +282,7 @@ extern "C" int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, co
     if (valid) NW_CUDA(cudaMemcpyAsync(h->valid, valid, M, cudaMemcpyHostToDevice, s));
     else NW_CUDA(cudaMemsetAsync(h->valid, 1, M, s));
     NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * M, s));
-    NW_CUDA(cudaMemsetAsync(h->S0, 0, sizeof(float4) * M, s));
-    NW_CUDA(cudaMemsetAsync(h->S1, 0, sizeof(float4) * M, s));
-    NW_CUDA(cudaMemsetAsync(h->S2, 0, sizeof(float4) * M, s));
+    NW_CUDA(cudaMemsetAsync(h->Sq, 0, sizeof(float4) * 3 * M, s));
     NW_CUDA(cudaStreamSynchronize(s));
     nw_free(&d_nbr);
     // nearest-face slots refer to the previous block's sort order
