@@ -50,7 +50,8 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free(&h->sfaces); nw_free(&h->cent); nw_free(&h->boxes);
     nw_free(&h->acc); nw_free(&h->Sq); nw_free(&h->fdef);
     nw_free(&h->partials); nw_free(&h->st); nw_free(&h->hist);
-    nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP); nw_free(&h->curvK);
+    nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP);
+    nw_free((char **)&h->cvV); nw_free((char **)&h->cvF); nw_free((char **)&h->cvH); nw_free(&h->cvOut); nw_free(&h->cvJ); nw_free(&h->cvOff);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev_search0) { cudaEventDestroy(h->ev_search0); cudaEventDestroy(h->ev_search1); }
     if (h->stream) cudaStreamDestroy(h->stream);

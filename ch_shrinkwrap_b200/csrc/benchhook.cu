@@ -10,8 +10,24 @@ int nw_launch_influence(nw_ctx *h);
 extern "C" int nw_bench_kernel(nw_ctx *h, const char *name, int reps, float *ms_per_launch) {
     if (!h) return NW_ERR_ARG;
     NW_ARG(name && reps > 0 && ms_per_launch, "nw_bench_kernel: bad arguments");
-    NW_ARG(h->M > 0 && h->weights_valid, "nw_bench_kernel: run nw_search or nw_compute_weights first");
     NW_CUDA(cudaSetDevice(h->device));
+    if (std::string(name) == "curvature") {
+        cudaEvent_t c0, c1;
+        NW_CUDA(cudaEventCreate(&c0)); NW_CUDA(cudaEventCreate(&c1));
+        int rc = nw_curvature_relaunch(h);
+        if (rc == NW_OK) {
+            cudaEventRecord(c0, h->stream);
+            for (int r = 0; r < reps && rc == NW_OK; ++r) rc = nw_curvature_relaunch(h);
+            cudaEventRecord(c1, h->stream);
+            cudaEventSynchronize(c1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c0, c1);
+            *ms_per_launch = ms / reps;
+        }
+        cudaEventDestroy(c0); cudaEventDestroy(c1);
+        return rc;
+    }
+    NW_ARG(h->M > 0 && h->weights_valid, "nw_bench_kernel: run nw_search or nw_compute_weights first");
     SolverState s;
     NW_CUDA(cudaMemcpy(&s, h->st, sizeof(s), cudaMemcpyDeviceToHost));
     s.stop = 0; s.nan_flag = 0;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "../../include/nanowrap.h"
 
@@ -53,6 +54,7 @@ struct nw_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
+    std::unordered_map<void *, size_t> caps;     // capacity (bytes) of the buffer each pointer variable currently owns
 
     // ---- points (Morton-sorted SoA) ----
     int64_t P = 0;
@@ -101,9 +103,15 @@ struct nw_ctx {
     float *scratchP = nullptr;                   // 3P floats
     int64_t scratchP_elems = 0;
 
-    // ---- curvature ----
+    // ---- curvature (device copies are kept after a call so the kernel can be re-timed) ----
     float *curvK = nullptr;
     int curvM = 0;
+    void *cvV = nullptr, *cvF = nullptr, *cvH = nullptr;
+    float *cvOut = nullptr;
+    double *cvJ = nullptr;
+    int *cvOff = nullptr;
+    float cv_dN = 0.1f, cv_kc = 1.f, cv_kg = 0.f, cv_c0 = 0.f;
+    unsigned long long cv_seed = 0;
 
     // ---- measurement: CUDA events on the handle's stream ----
     int profile = 0;                             // 1: per-stage events inside nw_search
@@ -143,11 +151,21 @@ struct nw_ctx {
         }                                                                                  \
     } while (0)
 
+// Grow-only allocation: a buffer is reused when it is already large enough (cudaFree synchronises the device and
+// re-mapping hundreds of MB per remesh block costs far more than the block's kernels).
 template <typename T>
 static inline int nw_alloc(nw_ctx *h, T **p, size_t n) {
-    if (*p) { cudaFree(*p); *p = nullptr; }
+    const size_t bytes = n * sizeof(T);
+    if (*p) {
+        auto it = h->caps.find((void *)p);
+        if (it != h->caps.end() && it->second >= bytes && bytes > 0) return NW_OK;
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    h->caps.erase((void *)p);
     if (n == 0) return NW_OK;
-    NW_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+    NW_CUDA(cudaMalloc((void **)p, bytes));
+    h->caps[(void *)p] = bytes;
     return NW_OK;
 }
 template <typename T>
@@ -197,3 +215,4 @@ int nw_launch_solve_update(nw_ctx *h);
 int nw_allreduce_acc(nw_ctx *h);
 int nw_allreduce_scalars(nw_ctx *h);
 int nw_set_acc_shifts(nw_ctx *h);
+int nw_curvature_relaunch(nw_ctx *h);

@@ -270,6 +270,28 @@ static int exclusive_scan(nw_ctx *h, const int *in, int *out, int n) {
     return NW_OK;
 }
 
+static void curv_outputs(nw_ctx *h, CurvOut &co, size_t *offs) {
+    const size_t M = (size_t)h->curvM;
+    size_t o_ = 0;
+    for (int k = 0; k < 12; ++k) { offs[k] = o_; o_ += (k < 9 ? 1 : 3) * M; }
+    float *out = h->cvOut;
+    co.k0 = out + offs[0]; co.k1 = out + offs[1]; co.H = out + offs[2]; co.K = out + offs[3]; co.dH = out + offs[4];
+    co.dK = out + offs[5]; co.E = out + offs[6]; co.pE = out + offs[7]; co.dEnb = out + offs[8];
+    co.e0 = out + offs[9]; co.e1 = out + offs[10]; co.dEdN = out + offs[11];
+}
+
+int nw_curvature_relaunch(nw_ctx *h) {
+    NW_ARG(h->cvV && h->curvM > 0, "curvature: call nw_curvature_grad first");
+    CurvOut co;
+    size_t offs[12];
+    curv_outputs(h, co, offs);
+    k_curvature<<<nw_grid(h->curvM, 128), 128, 0, h->stream>>>((const VertRec *)h->cvV, (const FaceRec *)h->cvF, (const HeRec *)h->cvH,
+                                                                h->curvM, h->cv_dN, h->cv_kc, h->cv_kg, h->cv_c0, h->cvJ, h->cvOff,
+                                                                h->cv_seed, co);
+    NW_LAUNCH_CHECK();
+    return NW_OK;
+}
+
 extern "C" int nw_curvature_grad(nw_ctx *h, const void *vertices, const void *faces, const void *halfedges, int n_vertices,
                                  int n_faces, int n_halfedges, float dN, float skip_prob, float *k_0, float *k_1, float *e_0,
                                  float *e_1, float *H, float *K, float *dH, float *dK, float *E, float *pE, float *dE_neighbors,
@@ -281,55 +303,46 @@ extern "C" int nw_curvature_grad(nw_ctx *h, const void *vertices, const void *fa
     NW_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const int M = n_vertices;
-    VertRec *dV = nullptr; FaceRec *dF = nullptr; HeRec *dH_ = nullptr;
-    float *out = nullptr; double *dJ = nullptr; int *flag = nullptr, *off = nullptr;
-    int rc = NW_OK;
-    auto cleanup = [&]() { nw_free(&dV); nw_free(&dF); nw_free(&dH_); nw_free(&out); nw_free(&dJ); nw_free(&flag); nw_free(&off); };
-#define NWX(x) do { rc = (x); if (rc != NW_OK) { cleanup(); return rc; } } while (0)
-#define NWC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); return NW_ERR_CUDA; } } while (0)
-    NWX(nw_alloc(h, &dV, (size_t)M)); NWX(nw_alloc(h, &dF, (size_t)n_faces)); NWX(nw_alloc(h, &dH_, (size_t)n_halfedges));
-    NWX(nw_alloc(h, &out, (size_t)18 * M));
-    NWC(cudaMemcpyAsync(dV, vertices, sizeof(VertRec) * M, cudaMemcpyHostToDevice, s));
-    NWC(cudaMemcpyAsync(dF, faces, sizeof(FaceRec) * n_faces, cudaMemcpyHostToDevice, s));
-    NWC(cudaMemcpyAsync(dH_, halfedges, sizeof(HeRec) * n_halfedges, cudaMemcpyHostToDevice, s));
+    int *flag = nullptr;
+    NW_CHECK(nw_alloc(h, (VertRec **)&h->cvV, (size_t)M)); NW_CHECK(nw_alloc(h, (FaceRec **)&h->cvF, (size_t)n_faces));
+    NW_CHECK(nw_alloc(h, (HeRec **)&h->cvH, (size_t)n_halfedges)); NW_CHECK(nw_alloc(h, &h->cvOut, (size_t)18 * M));
+    nw_free(&h->cvJ); nw_free(&h->cvOff);
+    h->curvM = M; h->cv_dN = dN; h->cv_kc = kc; h->cv_kg = kg; h->cv_c0 = c0; h->cv_seed = (unsigned long long)jitter_seed;
+    NW_CUDA(cudaMemcpyAsync(h->cvV, vertices, sizeof(VertRec) * M, cudaMemcpyHostToDevice, s));
+    NW_CUDA(cudaMemcpyAsync(h->cvF, faces, sizeof(FaceRec) * n_faces, cudaMemcpyHostToDevice, s));
+    NW_CUDA(cudaMemcpyAsync(h->cvH, halfedges, sizeof(HeRec) * n_halfedges, cudaMemcpyHostToDevice, s));
+    CurvOut co;
+    size_t offs[12];
+    curv_outputs(h, co, offs);
     // k0,k1,e0,e1 rows of deleted vertices are left untouched by the reference: seed them with the caller's values
     float *host_out[12] = {k_0, k_1, H, K, dH, dK, E, pE, dE_neighbors, e_0, e_1, dEdN};
-    size_t offs[12]; size_t o_ = 0;
-    for (int k = 0; k < 12; ++k) { offs[k] = o_; o_ += (k < 9 ? 1 : 3) * (size_t)M; }
-    NWC(cudaMemcpyAsync(out + offs[0], k_0, sizeof(float) * M, cudaMemcpyHostToDevice, s));
-    NWC(cudaMemcpyAsync(out + offs[1], k_1, sizeof(float) * M, cudaMemcpyHostToDevice, s));
-    NWC(cudaMemcpyAsync(out + offs[9], e_0, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
-    NWC(cudaMemcpyAsync(out + offs[10], e_1, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+    NW_CUDA(cudaMemcpyAsync(co.k0, k_0, sizeof(float) * M, cudaMemcpyHostToDevice, s));
+    NW_CUDA(cudaMemcpyAsync(co.k1, k_1, sizeof(float) * M, cudaMemcpyHostToDevice, s));
+    NW_CUDA(cudaMemcpyAsync(co.e0, e_0, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+    NW_CUDA(cudaMemcpyAsync(co.e1, e_1, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
     if (jitter_u) {
-        NWX(nw_alloc(h, &flag, (size_t)M)); NWX(nw_alloc(h, &off, (size_t)M));
-        k_valid_flags<<<nw_grid(M, 256), 256, 0, s>>>(dV, M, flag);
+        NW_CHECK(nw_alloc(h, &flag, (size_t)M)); NW_CHECK(nw_alloc(h, &h->cvOff, (size_t)M));
+        k_valid_flags<<<nw_grid(M, 256), 256, 0, s>>>((const VertRec *)h->cvV, M, flag);
         h->launches++;
-        NWX(exclusive_scan(h, flag, off, M));
+        int rc = exclusive_scan(h, flag, h->cvOff, M);
         int last_off = 0, last_flag = 0;
-        NWC(cudaMemcpyAsync(&last_off, off + M - 1, sizeof(int), cudaMemcpyDeviceToHost, s));
-        NWC(cudaMemcpyAsync(&last_flag, flag + M - 1, sizeof(int), cudaMemcpyDeviceToHost, s));
-        NWC(cudaStreamSynchronize(s));
+        if (rc == NW_OK) {
+            cudaMemcpyAsync(&last_off, h->cvOff + M - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
+            cudaMemcpyAsync(&last_flag, flag + M - 1, sizeof(int), cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+        }
+        nw_free(&flag);
+        NW_CHECK(rc);
         const size_t nj = 3 * (size_t)(last_off + last_flag);
-        NWX(nw_alloc(h, &dJ, nj + 1));
-        NWC(cudaMemcpyAsync(dJ, jitter_u, sizeof(double) * nj, cudaMemcpyHostToDevice, s));
+        NW_CHECK(nw_alloc(h, &h->cvJ, nj + 1));
+        NW_CUDA(cudaMemcpyAsync(h->cvJ, jitter_u, sizeof(double) * nj, cudaMemcpyHostToDevice, s));
     }
-    CurvOut co;
-    co.k0 = out + offs[0]; co.k1 = out + offs[1]; co.H = out + offs[2]; co.K = out + offs[3]; co.dH = out + offs[4];
-    co.dK = out + offs[5]; co.E = out + offs[6]; co.pE = out + offs[7]; co.dEnb = out + offs[8];
-    co.e0 = out + offs[9]; co.e1 = out + offs[10]; co.dEdN = out + offs[11];
-    k_curvature<<<nw_grid(M, 128), 128, 0, s>>>(dV, dF, dH_, M, dN, kc, kg, c0, dJ, off, (unsigned long long)jitter_seed, co);
-    h->launches++;
-    NWC(cudaGetLastError());
+    NW_CHECK(nw_curvature_relaunch(h));
     for (int k = 0; k < 12; ++k)
-        NWC(cudaMemcpyAsync(host_out[k], out + offs[k], sizeof(float) * (k < 9 ? 1 : 3) * M, cudaMemcpyDeviceToHost, s));
-    // keep K on the device for the neck criterion
-    if (h->curvM != M || !h->curvK) { NWX(nw_alloc(h, &h->curvK, (size_t)M)); h->curvM = M; }
-    NWC(cudaMemcpyAsync(h->curvK, co.K, sizeof(float) * M, cudaMemcpyDeviceToDevice, s));
-    NWC(cudaStreamSynchronize(s));
-    cleanup();
+        NW_CUDA(cudaMemcpyAsync(host_out[k], h->cvOut + offs[k], sizeof(float) * (k < 9 ? 1 : 3) * M, cudaMemcpyDeviceToHost, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+    h->curvK = co.K;       // stays on the device for the neck criterion
     return NW_OK;
-#undef NWX
-#undef NWC
 }
 
 extern "C" int nw_neck_candidates(nw_ctx *h, float low, float high, int32_t *idx, int *n) {

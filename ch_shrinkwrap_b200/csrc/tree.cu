@@ -30,15 +30,18 @@ __global__ void k_unpack_vec3(const float4 *__restrict__ src, int M, float *__re
     if (i < M) { float4 v = src[i]; dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z; }
 }
 
-// (M,20) row-major -> k-major + valence (entries are -1 terminated, mesh_conj_grad.py:50-54)
-__global__ void k_transpose_nbr(const int *__restrict__ nbr, int M, int *__restrict__ nbrT, int *__restrict__ valence) {
+// (M,20) row-major -> k-major + valence (entries are -1 terminated, mesh_conj_grad.py:50-54).  With he_vertex the
+// table holds half-edge indices and is mapped to neighbour vertices here (halfedges['vertex'][neighbors], :50).
+__global__ void k_transpose_nbr(const int *__restrict__ nbr, const int *__restrict__ he_vertex, int n_he, int M,
+                                int *__restrict__ nbrT, int *__restrict__ valence) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= M) return;
     int n = 0;
     bool open = true;
     for (int k = 0; k < NW_NEIGHBORSIZE; ++k) {
         int t = nbr[(size_t)v * NW_NEIGHBORSIZE + k];
-        if (t < 0) open = false;
+        if (t >= 0 && he_vertex) t = (t < n_he) ? he_vertex[t] : -1;
+        if (t < 0 || t >= M) open = false;
         if (open) ++n;
         nbrT[(size_t)k * M + v] = open ? t : -1;
     }
@@ -247,8 +250,23 @@ inline float ordered_to_float(int v) {
 
 }  // namespace
 
+static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces, const int32_t *nbr,
+                             const int32_t *he_vertex, int n_he, const uint8_t *valid, int M, int F);
+
 extern "C" int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces,
                                const int32_t *nbr, const uint8_t *valid, int M, int F) {
+    return set_topology_impl(h, pos, nrm, faces, nbr, nullptr, 0, valid, M, F);
+}
+
+extern "C" int nw_set_topology_halfedge(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces,
+                                        const int32_t *nbr_halfedge, const int32_t *he_vertex, int n_halfedges,
+                                        const uint8_t *valid, int M, int F) {
+    if (h && !(he_vertex && n_halfedges > 0)) { h->err = "nw_set_topology_halfedge: missing half-edge table"; return NW_ERR_ARG; }
+    return set_topology_impl(h, pos, nrm, faces, nbr_halfedge, he_vertex, n_halfedges, valid, M, F);
+}
+
+static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces, const int32_t *nbr,
+                             const int32_t *he_vertex, int n_he, const uint8_t *valid, int M, int F) {
     if (!h) return NW_ERR_ARG;
     NW_ARG(M > 0 && F > 0, "nw_set_topology: empty mesh");
     NW_ARG(pos && nrm && faces && nbr, "nw_set_topology: NULL array");
@@ -268,8 +286,12 @@ extern "C" int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, co
     NW_CHECK(nw_alloc(h, &h->sfaces, (size_t)F)); NW_CHECK(nw_alloc(h, &h->cent, (size_t)F));
 
     // staging: positions / normals through scratchM, neighbour table through a temporary
-    int *d_nbr = nullptr;
+    int *d_nbr = nullptr, *d_hev = nullptr;
     NW_CHECK(nw_alloc(h, &d_nbr, (size_t)NW_NEIGHBORSIZE * M));
+    if (he_vertex) {
+        NW_CHECK(nw_alloc(h, &d_hev, (size_t)n_he));
+        NW_CUDA(cudaMemcpyAsync(d_hev, he_vertex, sizeof(int) * n_he, cudaMemcpyHostToDevice, s));
+    }
     NW_CUDA(cudaMemcpyAsync(h->scratchM, pos, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
     k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->posq);
     NW_CUDA(cudaStreamSynchronize(s));
@@ -277,14 +299,14 @@ extern "C" int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, co
     k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->nrmq);
     NW_CUDA(cudaMemcpyAsync(h->faces, faces, sizeof(int) * 3 * F, cudaMemcpyHostToDevice, s));
     NW_CUDA(cudaMemcpyAsync(d_nbr, nbr, sizeof(int) * NW_NEIGHBORSIZE * M, cudaMemcpyHostToDevice, s));
-    k_transpose_nbr<<<nw_grid(M, B), B, 0, s>>>(d_nbr, M, h->nbrT, h->valence);
+    k_transpose_nbr<<<nw_grid(M, B), B, 0, s>>>(d_nbr, d_hev, n_he, M, h->nbrT, h->valence);
     h->launches += 3;
     if (valid) NW_CUDA(cudaMemcpyAsync(h->valid, valid, M, cudaMemcpyHostToDevice, s));
     else NW_CUDA(cudaMemsetAsync(h->valid, 1, M, s));
     NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * M, s));
     NW_CUDA(cudaMemsetAsync(h->Sq, 0, sizeof(float4) * 3 * M, s));
     NW_CUDA(cudaStreamSynchronize(s));
-    nw_free(&d_nbr);
+    nw_free(&d_nbr); nw_free(&d_hev);
     // nearest-face slots refer to the previous block's sort order
     if (h->slot && h->P) NW_CUDA(cudaMemsetAsync(h->slot, 0xff, sizeof(int) * h->P, s));
     h->seeds_cold = true;

@@ -93,12 +93,9 @@ class ShrinkwrapMeshConjGrad(object):
         self._mesh_vertex_mask = mesh._vertices['halfedge'] != -1   # :44
         self.vertices = mesh._vertices['position']                  # :46
         self.faces = mesh.faces                                     # :47
-        nb = mesh._vertices['neighbors']
-        n = mesh._halfedges['vertex'][nb]                           # :50
-        n[nb == -1] = -1
-        self.vertex_neighbors = n
+        self._vertex_neighbors = None                              # :50-54, built lazily (the device does its own lookup)
         self.M = self.vertices.shape[0]
-        self.N = n.shape[1]
+        self.N = mesh._vertices['neighbors'].shape[1]
         self.dims = 3
         self.shape = self.vertices.shape
         self.search_k = min(search_k, points.shape[0])
@@ -118,6 +115,16 @@ class ShrinkwrapMeshConjGrad(object):
         return self._points
 
     @property
+    def vertex_neighbors(self):
+        """(M,20) neighbour vertex ids, -1 padded (mesh_conj_grad.py:50-54)."""
+        if self._vertex_neighbors is None:
+            nb = self.mesh._vertices['neighbors']
+            n = self.mesh._halfedges['vertex'][nb]
+            n[nb == -1] = -1
+            self._vertex_neighbors = n
+        return self._vertex_neighbors
+
+    @property
     def _h(self):
         return self._session.handle
 
@@ -126,9 +133,11 @@ class ShrinkwrapMeshConjGrad(object):
         pos = _lib.as_f32(mesh._vertices['position'])
         nrm = _lib.as_f32(mesh.vertex_normals)
         faces = np.ascontiguousarray(self.faces, dtype=np.int32)
-        nbr = np.ascontiguousarray(self.vertex_neighbors, dtype=np.int32)
+        nbr_he = np.ascontiguousarray(mesh._vertices['neighbors'], dtype=np.int32)
+        he_vertex = np.ascontiguousarray(mesh._halfedges['vertex'], dtype=np.int32)
         valid = np.ascontiguousarray(self._mesh_vertex_mask, dtype=np.uint8)
-        self._h.call('nw_set_topology', _lib.fptr(pos), _lib.fptr(nrm), _lib.iptr(faces), _lib.iptr(nbr),
+        self._h.call('nw_set_topology_halfedge', _lib.fptr(pos), _lib.fptr(nrm), _lib.iptr(faces), _lib.iptr(nbr_he),
+                     _lib.iptr(he_vertex), int(he_vertex.shape[0]),
                      valid.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), int(pos.shape[0]), int(faces.shape[0]))
         self._topology_uploaded = True
 

@@ -66,6 +66,12 @@ int nw_set_points(nw_ctx *h, const void *pts, int pts_is_f64, int64_t P, const f
  *  valid     (M) uint8 or NULL: mesh._vertices['halfedge'] != -1 (:44); NULL = all valid */
 int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces,
                     const int32_t *nbr, const uint8_t *valid, int M, int F);
+/* Same, but the neighbour table holds HALF-EDGE indices exactly as mesh._vertices['neighbors'] stores them and
+ * he_vertex = mesh._halfedges['vertex'] (n_halfedges int32); the library performs the lookup of
+ * mesh_conj_grad.py:50-52 on the device instead of a 20M-element numpy gather per block on the host. */
+int nw_set_topology_halfedge(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces,
+                             const int32_t *nbr_halfedge, const int32_t *he_vertex, int n_halfedges,
+                             const uint8_t *valid, int M, int F);
 int nw_set_positions(nw_ctx *h, const float *pos);           /* overwrite f (3M) */
 int nw_get_positions(nw_ctx *h, float *pos);                 /* read f (3M)      */
 

@@ -1,0 +1,14 @@
+import sys, os, time, ctypes, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from ch_shrinkwrap_b200 import mesh_conj_grad as mcg, _lib
+t=time.perf_counter(); mesh, pts, sig, cfg = bench.build_workload('c3', 1234); print('build_workload %.2f'%(time.perf_counter()-t))
+s_inv=(1.0/sig.ravel()).astype(np.float32)
+t=time.perf_counter(); sess = mcg._session_for(mesh); print('create handle %.3f'%(time.perf_counter()-t))
+for blk in range(3):
+    t0=time.perf_counter(); cg=mcg.ShrinkwrapMeshConjGrad(mesh, pts); t1=time.perf_counter()
+    cg._sigma_inv=s_inv
+    cg._session.set_points(pts, s_inv, None); t2=time.perf_counter()
+    cg._upload_topology(); t3=time.perf_counter()
+    cg.search(pts, lams=[5.0], num_iters=5, sigma_inv=s_inv); t4=time.perf_counter()
+    print('block %d: ctor %.3f set_points %.3f topo %.3f search %.3f'%(blk, t1-t0, t2-t1, t3-t2, t4-t3))
