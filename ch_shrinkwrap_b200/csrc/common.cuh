@@ -83,6 +83,7 @@ struct nw_ctx {
     int *nbrT = nullptr;                         // neighbour table, k-major: nbrT[k*M + v]
     int *valence = nullptr;
     uint8_t *valid = nullptr;
+    int *stage_nbr = nullptr, *stage_hev = nullptr;   // upload staging (reused across blocks)
     // ---- Morton AABB pyramid over face centroids ----
     int4 *sfaces = nullptr;                      // per sorted slot: corner ids + face id
     float4 *cent = nullptr;                      // per sorted slot: centroid xyz + face id bits

@@ -48,6 +48,28 @@ __global__ void k_transpose_nbr(const int *__restrict__ nbr, const int *__restri
     valence[v] = n;
 }
 
+// vertex_t records (membrane_mesh_utils.h:57-65, 120 B) -> position / normal float4, valid flag, neighbour table
+__global__ void k_unpack_vertex_records(const int *__restrict__ rec, int M, const int *__restrict__ he_vertex, int n_he,
+                                        float4 *__restrict__ posq, float4 *__restrict__ nrmq, uint8_t *__restrict__ valid,
+                                        int *__restrict__ nbrT, int *__restrict__ valence) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= M) return;
+    const int *r = rec + (size_t)v * 30;            // 30 four-byte fields
+    posq[v] = make_float4(__int_as_float(r[0]), __int_as_float(r[1]), __int_as_float(r[2]), 0.f);
+    nrmq[v] = make_float4(__int_as_float(r[3]), __int_as_float(r[4]), __int_as_float(r[5]), 0.f);
+    valid[v] = r[6] != -1;                          // halfedge != -1 (mesh_conj_grad.py:44)
+    int n = 0;
+    bool open = true;
+    for (int k = 0; k < NW_NEIGHBORSIZE; ++k) {
+        int t = r[8 + k];
+        if (t >= 0) t = (t < n_he) ? he_vertex[t] : -1;
+        if (t < 0 || t >= M) open = false;
+        if (open) ++n;
+        nbrT[(size_t)k * M + v] = open ? t : -1;
+    }
+    valence[v] = n;
+}
+
 __global__ void k_face_bbox(const int *__restrict__ faces, const float4 *__restrict__ pos, int F, int *__restrict__ out6) {
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
@@ -265,11 +287,19 @@ extern "C" int nw_set_topology_halfedge(nw_ctx *h, const float *pos, const float
     return set_topology_impl(h, pos, nrm, faces, nbr_halfedge, he_vertex, n_halfedges, valid, M, F);
 }
 
+extern "C" int nw_set_topology_records(nw_ctx *h, const void *vertex_records, const int32_t *faces, const int32_t *he_vertex,
+                                       int n_halfedges, int M, int F) {
+    if (h && !(vertex_records && he_vertex && n_halfedges > 0)) { h->err = "nw_set_topology_records: NULL array"; return NW_ERR_ARG; }
+    return set_topology_impl(h, (const float *)vertex_records, nullptr, faces, nullptr, he_vertex, n_halfedges, nullptr, M, F);
+}
+
+// nrm == NULL && nbr == NULL: `pos` points at M raw vertex_t records
 static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces, const int32_t *nbr,
                              const int32_t *he_vertex, int n_he, const uint8_t *valid, int M, int F) {
     if (!h) return NW_ERR_ARG;
     NW_ARG(M > 0 && F > 0, "nw_set_topology: empty mesh");
-    NW_ARG(pos && nrm && faces && nbr, "nw_set_topology: NULL array");
+    const bool records = (nrm == nullptr && nbr == nullptr);
+    NW_ARG(pos && faces && (records || (nrm && nbr)), "nw_set_topology: NULL array");
     NW_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const int B = 256;
@@ -285,28 +315,33 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     NW_CHECK(nw_alloc(h, &h->scratchM, (size_t)3 * M));
     NW_CHECK(nw_alloc(h, &h->sfaces, (size_t)F)); NW_CHECK(nw_alloc(h, &h->cent, (size_t)F));
 
-    // staging: positions / normals through scratchM, neighbour table through a temporary
-    int *d_nbr = nullptr, *d_hev = nullptr;
-    NW_CHECK(nw_alloc(h, &d_nbr, (size_t)NW_NEIGHBORSIZE * M));
+    // staging buffers are members so that they are reused from block to block (grow-only)
     if (he_vertex) {
-        NW_CHECK(nw_alloc(h, &d_hev, (size_t)n_he));
-        NW_CUDA(cudaMemcpyAsync(d_hev, he_vertex, sizeof(int) * n_he, cudaMemcpyHostToDevice, s));
+        NW_CHECK(nw_alloc(h, &h->stage_hev, (size_t)n_he));
+        NW_CUDA(cudaMemcpyAsync(h->stage_hev, he_vertex, sizeof(int) * n_he, cudaMemcpyHostToDevice, s));
     }
-    NW_CUDA(cudaMemcpyAsync(h->scratchM, pos, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
-    k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->posq);
-    NW_CUDA(cudaStreamSynchronize(s));
-    NW_CUDA(cudaMemcpyAsync(h->scratchM, nrm, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
-    k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->nrmq);
     NW_CUDA(cudaMemcpyAsync(h->faces, faces, sizeof(int) * 3 * F, cudaMemcpyHostToDevice, s));
-    NW_CUDA(cudaMemcpyAsync(d_nbr, nbr, sizeof(int) * NW_NEIGHBORSIZE * M, cudaMemcpyHostToDevice, s));
-    k_transpose_nbr<<<nw_grid(M, B), B, 0, s>>>(d_nbr, d_hev, n_he, M, h->nbrT, h->valence);
-    h->launches += 3;
-    if (valid) NW_CUDA(cudaMemcpyAsync(h->valid, valid, M, cudaMemcpyHostToDevice, s));
-    else NW_CUDA(cudaMemsetAsync(h->valid, 1, M, s));
+    if (records) {
+        NW_CHECK(nw_alloc(h, &h->stage_nbr, (size_t)30 * M));
+        NW_CUDA(cudaMemcpyAsync(h->stage_nbr, pos, (size_t)120 * M, cudaMemcpyHostToDevice, s));
+        k_unpack_vertex_records<<<nw_grid(M, B), B, 0, s>>>(h->stage_nbr, M, h->stage_hev, n_he, h->posq, h->nrmq, h->valid, h->nbrT, h->valence);
+        h->launches += 1;
+    } else {
+        NW_CHECK(nw_alloc(h, &h->stage_nbr, (size_t)NW_NEIGHBORSIZE * M));
+        NW_CUDA(cudaMemcpyAsync(h->scratchM, pos, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+        k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->posq);
+        NW_CUDA(cudaStreamSynchronize(s));
+        NW_CUDA(cudaMemcpyAsync(h->scratchM, nrm, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+        k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->nrmq);
+        NW_CUDA(cudaMemcpyAsync(h->stage_nbr, nbr, sizeof(int) * NW_NEIGHBORSIZE * M, cudaMemcpyHostToDevice, s));
+        k_transpose_nbr<<<nw_grid(M, B), B, 0, s>>>(h->stage_nbr, he_vertex ? h->stage_hev : nullptr, n_he, M, h->nbrT, h->valence);
+        h->launches += 3;
+        if (valid) NW_CUDA(cudaMemcpyAsync(h->valid, valid, M, cudaMemcpyHostToDevice, s));
+        else NW_CUDA(cudaMemsetAsync(h->valid, 1, M, s));
+    }
     NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * M, s));
     NW_CUDA(cudaMemsetAsync(h->Sq, 0, sizeof(float4) * 3 * M, s));
     NW_CUDA(cudaStreamSynchronize(s));
-    nw_free(&d_nbr); nw_free(&d_hev);
     // nearest-face slots refer to the previous block's sort order
     if (h->slot && h->P) NW_CUDA(cudaMemsetAsync(h->slot, 0xff, sizeof(int) * h->P, s));
     h->seeds_cold = true;

@@ -104,6 +104,7 @@ class ShrinkwrapMeshConjGrad(object):
         self.cpred, self.wpreds = None, None
         self._session = _session_for(mesh, device, comm)
         self._topology_uploaded = False
+        self._positions_fresh = False
         self._sigma_inv, self._weights = 1.0, None
         self.f = None
         self.fs = None
@@ -130,16 +131,25 @@ class ShrinkwrapMeshConjGrad(object):
 
     def _upload_topology(self):
         mesh = self.mesh
-        pos = _lib.as_f32(mesh._vertices['position'])
-        nrm = _lib.as_f32(mesh.vertex_normals)
         faces = np.ascontiguousarray(self.faces, dtype=np.int32)
-        nbr_he = np.ascontiguousarray(mesh._vertices['neighbors'], dtype=np.int32)
         he_vertex = np.ascontiguousarray(mesh._halfedges['vertex'], dtype=np.int32)
-        valid = np.ascontiguousarray(self._mesh_vertex_mask, dtype=np.uint8)
-        self._h.call('nw_set_topology_halfedge', _lib.fptr(pos), _lib.fptr(nrm), _lib.iptr(faces), _lib.iptr(nbr_he),
-                     _lib.iptr(he_vertex), int(he_vertex.shape[0]),
-                     valid.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), int(pos.shape[0]), int(faces.shape[0]))
+        verts = mesh._vertices
+        nrm = mesh.vertex_normals
+        if (verts.dtype.itemsize == 120 and verts.flags.c_contiguous and isinstance(nrm, np.ndarray)
+                and np.shares_memory(nrm, verts) and nrm.shape == (len(verts), 3)):
+            # fast path: the records go up as they lie in memory (position, normal, halfedge, neighbors all inside)
+            self._h.call('nw_set_topology_records', ctypes.c_void_p(verts.ctypes.data), _lib.iptr(faces), _lib.iptr(he_vertex),
+                         int(he_vertex.shape[0]), int(len(verts)), int(faces.shape[0]))
+        else:
+            pos = _lib.as_f32(verts['position'])
+            nrm = _lib.as_f32(nrm)
+            nbr_he = np.ascontiguousarray(verts['neighbors'], dtype=np.int32)
+            valid = np.ascontiguousarray(self._mesh_vertex_mask, dtype=np.uint8)
+            self._h.call('nw_set_topology_halfedge', _lib.fptr(pos), _lib.fptr(nrm), _lib.iptr(faces), _lib.iptr(nbr_he),
+                         _lib.iptr(he_vertex), int(he_vertex.shape[0]),
+                         valid.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), int(pos.shape[0]), int(faces.shape[0]))
         self._topology_uploaded = True
+        self._positions_fresh = True
 
     def _ensure_ready(self):
         self._session.set_points(self._points, self._sigma_inv, self._weights)
@@ -161,11 +171,13 @@ class ShrinkwrapMeshConjGrad(object):
                 self._points = data
         self._sigma_inv, self._weights = sigma_inv, weights
         self._mask_src = (sigma_inv if weights is None else weights, data)   # mask is built lazily (3P bools)
+        self._positions_fresh = False
         self._ensure_ready()
-        # positions may have been edited on the host since the upload (remesh happens between blocks,
-        # which builds a new object, so this only matters for repeated search() calls)
-        posn = _lib.as_f32(self.mesh._vertices['position'])
-        self._h.call('nw_set_positions', _lib.fptr(posn))
+        if not self._positions_fresh:
+            # positions may have been edited on the host since the upload (remesh happens between blocks, which builds
+            # a new object, so this only matters for repeated search() calls on one object)
+            posn = _lib.as_f32(self.mesh._vertices['position'])
+            self._h.call('nw_set_positions', _lib.fptr(posn))
         n = int(num_iters)
         out = np.empty((self.M, 3), np.float32)
         hist = [np.zeros(max(n, 1), np.float64) for _ in range(5)]
@@ -184,7 +196,10 @@ class ShrinkwrapMeshConjGrad(object):
         self.fs = out
         self.f = out.ravel()
         valid = self._mesh_vertex_mask
-        self.mesh._vertices['position'][valid] = out[valid]             # :289
+        if valid.all():
+            self.mesh._vertices['position'][:] = out                    # :289 (all rows valid: plain strided copy)
+        else:
+            self.mesh._vertices['position'][valid] = out[valid]
         self.mesh._initialize_curvature_vectors()                        # :290
         return self.fs
 

@@ -72,6 +72,11 @@ int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, const int32_t
 int nw_set_topology_halfedge(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces,
                              const int32_t *nbr_halfedge, const int32_t *he_vertex, int n_halfedges,
                              const uint8_t *valid, int M, int F);
+/* Same from the raw records: vertex_records = mesh._vertices as it lies in memory (M x vertex_t, 120 B each,
+ * membrane_mesh_utils.h:57-65: position, normal, halfedge, valence, neighbors[20], component, locally_manifold).
+ * One contiguous upload, no host-side packing; position / normal / valid / neighbours are unpacked on the device. */
+int nw_set_topology_records(nw_ctx *h, const void *vertex_records, const int32_t *faces, const int32_t *he_vertex,
+                            int n_halfedges, int M, int F);
 int nw_set_positions(nw_ctx *h, const float *pos);           /* overwrite f (3M) */
 int nw_get_positions(nw_ctx *h, float *pos);                 /* read f (3M)      */
 
