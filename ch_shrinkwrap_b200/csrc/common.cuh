@@ -90,6 +90,10 @@ struct nw_ctx {
     Box *boxes = nullptr;
     TreeLevels tl;
     bool seeds_cold = true;                      // no nearest-face seeds yet for this topology
+    float *fx = nullptr, *fy = nullptr, *fz = nullptr;   // foot points on the previous block's surface (seeds after a remesh)
+    bool feet_valid = false;
+    unsigned *fkeys = nullptr;                   // sorted Hilbert keys of the face centroids at upload time
+    float key_lo[3] = {0, 0, 0}, key_inv = 0.f;  // quantisation used for those keys
     // ---- solver vectors ----
     unsigned long long *acc = nullptr;           // (M,4) int64 fixed point: AH res xyz, AH 1
     float4 *Sq = nullptr;                        // search directions, interleaved: S_k of vertex v at Sq[3v + k] (48 B per vertex)
@@ -210,6 +214,7 @@ int nw_tree_build(nw_ctx *h);                 // after topology upload: Morton s
 int nw_tree_refit(nw_ctx *h);                 // every iteration: centroids + boxes at the current f
 int nw_launch_sweep1(nw_ctx *h, bool scatter);
 int nw_launch_seed_leaders(nw_ctx *h);
+int nw_save_feet(nw_ctx *h);
 int nw_launch_sweep2(nw_ctx *h);
 int nw_launch_mesh_prior(nw_ctx *h, bool write_dirs);
 int nw_launch_solve_update(nw_ctx *h);

@@ -149,6 +149,7 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
     h->P = P;
     h->weights_valid = false;
     h->seeds_cold = true;
+    h->feet_valid = false;
     NWX(nw_alloc(h, &d_pts, (size_t)3 * P));
     NWC(cudaMemcpyAsync(d_pts, pts_host, sizeof(T) * 3 * P, cudaMemcpyHostToDevice, s));
     NWX(nw_alloc(h, &d_bbox, 6));

@@ -89,25 +89,39 @@ __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp,
     return __fmul_rd(__fadd_rd(__fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1)), __fmul_rd(g2, g2)), 0.99999f);
 }
 
-#define NW_STACK 96
+// greedy-descent score: the bound, with the squared distance to the box centre as a tie-breaker (several overlapping
+// boxes can contain the query and all have bound 0)
+template <typename Q>
+__device__ __forceinline__ float node_score(const Q &q, const Box *__restrict__ bp, float eps) {
+    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
+    const float x = q.fx(), y = q.fy(), z = q.fz();
+    const float t2x = a.y * b.y - a.z * b.x, t2y = a.z * a.w - a.x * b.y, t2z = a.x * b.x - a.y * a.w;
+    const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
+    const float p1 = fmaf(a.w, x, fmaf(b.x, y, b.y * z));
+    const float p2 = fmaf(t2x, x, fmaf(t2y, y, t2z * z));
+    const float g0 = fmaxf(fmaxf(b.z - pn, pn - b.w), 0.f), g1 = fmaxf(fmaxf(c.x - p1, p1 - c.y), 0.f),
+                g2 = fmaxf(fmaxf(c.z - p2, p2 - c.w), 0.f);
+    const float c0 = pn - 0.5f * (b.z + b.w), c1 = p1 - 0.5f * (c.x + c.y), c2 = p2 - 0.5f * (c.z + c.w);
+    return (g0 * g0 + g1 * g1 + g2 * g2) + 1e-4f * (c0 * c0 + c1 * c1 + c2 * c2);
+}
 
+// Stackless search of the implicit pyramid.  All state is scalar and held BY VALUE so that it stays in registers
+// (a per-thread stack array, or references to the caller's query, made the compiler spill the whole object to local
+// memory and reload it inside every node test).
 template <typename Q>
 struct Traversal {
-    const Q &q;
-    Nearest &best;
+    Q q;
+    Nearest best;
     const float4 *__restrict__ cent;
     const Box *__restrict__ boxes;
-    const TreeLevels &tl;
+    const TreeLevels &tl;          // lives in the kernel's __grid_constant__ parameter space (LDC with a dynamic index)
     int F;
     float eps;
-    float slb[NW_STACK];
-    int snode[NW_STACK];
-    int sp;
     unsigned n_tests = 0, n_leaves = 0, n_exact = 0;
     unsigned budget = 0xffffffffu;   // seeds only: stop refining after this many node tests (the result is then approximate)
 
-    __device__ __forceinline__ Traversal(const Q &q_, Nearest &b_, const float4 *c_, const Box *bx_, const TreeLevels &tl_, int F_, float eps_)
-        : q(q_), best(b_), cent(c_), boxes(bx_), tl(tl_), F(F_), eps(eps_), sp(0) {}
+    __device__ __forceinline__ Traversal(const Q &q_, const Nearest &b_, const float4 *c_, const Box *bx_, const TreeLevels &tl_, int F_, float eps_)
+        : q(q_), best(b_), cent(c_), boxes(bx_), tl(tl_), F(F_), eps(eps_) {}
 
     __device__ __forceinline__ void leaf(int idx) {
         const int base = idx * NW_LEAF;
@@ -118,55 +132,13 @@ struct Traversal {
             if (q.lb_box(c, c) <= best.ub) { ++n_exact; best.offer(q.d2(c), base + k, __float_as_int(c.w)); }
         }
     }
-    // test the children [c0, c0+n) of level cl, push the survivors nearest-last; `skip` = child not to visit
-    __device__ __forceinline__ void expand(int cl, int c0, int n, int skip) {
-        float l[NW_FAN];
-        int id[NW_FAN];
-#pragma unroll
-        for (int k = 0; k < NW_FAN; ++k) {
-            l[k] = (k < n && c0 + k != skip) ? node_lb(q, &boxes[tl.offset[cl] + c0 + k], eps) : FLT_MAX;
-            n_tests += (k < n && c0 + k != skip);
-            id[k] = (cl << 26) | (c0 + k);
-        }
-#define NW_CSWAP(a, b) if (l[a] < l[b]) { float tf = l[a]; l[a] = l[b]; l[b] = tf; int ti = id[a]; id[a] = id[b]; id[b] = ti; }
-#if NW_FAN == 4
-        NW_CSWAP(0, 1) NW_CSWAP(2, 3) NW_CSWAP(0, 2) NW_CSWAP(1, 3) NW_CSWAP(1, 2)
-#elif NW_FAN == 2
-        NW_CSWAP(0, 1)
-#else
-#error "NW_FAN must be 2 or 4"
-#endif
-#undef NW_CSWAP
-#pragma unroll
-        for (int k = 0; k < NW_FAN; ++k)
-            if (l[k] <= best.ub && l[k] != FLT_MAX && sp < NW_STACK) { slb[sp] = l[k]; snode[sp++] = id[k]; }
-    }
-    __device__ __forceinline__ void run() {
-        while (sp > 0) {
-            if (n_tests > budget) { sp = 0; break; }
-            --sp;
-            const float lb = slb[sp];
-            const int node = snode[sp];
-            if (lb > best.ub) continue;
-            const int level = node >> 26, idx = node & 0x3ffffff;
-            if (level == 0) leaf(idx);
-            else expand(level - 1, idx * NW_FAN, min(NW_FAN, tl.count[level - 1] - idx * NW_FAN), -1);
-        }
-    }
-    // cold query: from the top level down
-    __device__ __forceinline__ void top_down() {
-        const int top = tl.n_levels - 1;
-        expand(top, 0, tl.count[top], -1);
-        run();
-    }
-    // Stackless depth-first search of the subtree rooted at (L, I).  The hierarchy is implicit (children of node i
-    // are 4i..4i+3), so "next node" is index arithmetic and no per-thread stack (local memory) is needed.  Children
-    // are visited in index order: with a seed the bound is already (nearly) exact, so nearest-first ordering would
-    // buy nothing.
+    // Depth-first search of the subtree rooted at (L, I).  The hierarchy is implicit (children of node i are
+    // 4i..4i+3), so "next node" is index arithmetic.  Children are visited in index order: with a seed the bound is
+    // already (nearly) exact, so nearest-first ordering would buy nothing.
     __device__ __forceinline__ void dfs_subtree(int L, int I) {
         int level = L, idx = I;
         while (true) {
-            ++n_tests;
+            if (++n_tests > budget) return;
             if (node_lb(q, &boxes[tl.offset[level] + idx], eps) <= best.ub) {
                 if (level == 0) leaf(idx);
                 else { --level; idx *= NW_FAN; continue; }
@@ -190,6 +162,22 @@ struct Traversal {
                 if (c0 + k != node) dfs_subtree(level, c0 + k);
             node /= NW_FAN;
         }
+    }
+    // cold query: greedy descent (always into the child with the smallest bound) to get a first candidate, then the
+    // exact search from the leaf it reached
+    __device__ __forceinline__ void top_down() {
+        const int top = tl.n_levels - 1;
+        int node = 0, c0 = 0, n = tl.count[top];
+        for (int level = top; level >= 0; --level) {
+            float bl = FLT_MAX * 2.0f;
+            for (int k = 0; k < n; ++k) {
+                const float l = node_score(q, &boxes[tl.offset[level] + c0 + k], eps);
+                ++n_tests;
+                if (l < bl) { bl = l; node = c0 + k; }
+            }
+            if (level > 0) { c0 = node * NW_FAN; n = min(NW_FAN, tl.count[level - 1] - c0); }
+        }
+        from_seed(node * NW_LEAF);
     }
 };
 
@@ -249,16 +237,17 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
         if (warm) donor = __ffs(warm) - 1;
         else {
             donor = __ffs(cold) - 1;
-            if ((threadIdx.x & 31) == donor) { tr.top_down(); seed = best.slot; }
+            if ((threadIdx.x & 31) == donor) { tr.top_down(); seed = tr.best.slot; }
         }
         const int s0 = __shfl_sync(0xffffffffu, seed, donor);
         if (seed < 0) seed = s0;
     }
-    if (active && best.slot < 0) {
+    if (active && tr.best.slot < 0) {
         const float4 c = a.cent[seed];
-        best.offer(q.d2(c), seed, __float_as_int(c.w));
+        tr.best.offer(tr.q.d2(c), seed, __float_as_int(c.w));
         tr.from_seed(seed);
     }
+    best = tr.best;
     // traversal statistics (one atomic per warp and counter)
     const unsigned t = __reduce_add_sync(0xffffffffu, tr.n_tests), l = __reduce_add_sync(0xffffffffu, tr.n_leaves),
                    e = __reduce_add_sync(0xffffffffu, tr.n_exact), m = __reduce_max_sync(0xffffffffu, tr.n_tests);
@@ -272,7 +261,7 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
 // face from a root search that stops refining after a fixed number of node tests (a seed only has to be close, the
 // exact search happens in k_sweep1; bounding the effort removes the long tail of near-equidistant queries).
 template <bool F64>
-__global__ void __launch_bounds__(128) k_seed_leaders(const Sweep1Args a) {
+__global__ void __launch_bounds__(128) k_seed_leaders(const __grid_constant__ Sweep1Args a) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t i = t * 32;
     if (i >= a.P || a.slot[i] >= 0) return;
@@ -286,12 +275,72 @@ __global__ void __launch_bounds__(128) k_seed_leaders(const Sweep1Args a) {
     Traversal<decltype(q)> tr(q, best, a.cent, a.boxes, a.tl, a.F, eps);
     tr.budget = 512;
     tr.top_down();
-    a.slot[i] = best.slot;     // >= 0: the first descent always reaches a leaf before the budget can run out
+    a.slot[i] = tr.best.slot;     // >= 0: the first descent always reaches a leaf before the budget can run out
+}
+
+// Foot points A f of the previous block (the point on the OLD surface each localisation was attached to).  After a
+// remesh the new surface is close to the old one, and a query that lies ON the surface is cheap (its search ball is
+// tiny), so the face nearest to the old foot point is an excellent, individually computed seed for the real query.
+__global__ void __launch_bounds__(256) k_save_feet(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
+                                                   const float4 *__restrict__ posq, const float *__restrict__ w0,
+                                                   const float *__restrict__ w1, const float *__restrict__ w2,
+                                                   float *__restrict__ fx, float *__restrict__ fy, float *__restrict__ fz) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int sl = slot[i];
+    if (sl < 0) { fx[i] = fy[i] = fz[i] = __int_as_float(0x7fc00000); return; }
+    const int4 sf = sfaces[sl];
+    const float4 a = posq[sf.x], b = posq[sf.y], c = posq[sf.z];
+    const float u0 = w0[i], u1 = w1[i], u2 = w2[i];
+    fx[i] = a.x * u0 + b.x * u1 + c.x * u2; fy[i] = a.y * u0 + b.y * u1 + c.y * u2; fz[i] = a.z * u0 + b.z * u1 + c.z * u2;
+}
+
+__device__ __forceinline__ unsigned spread10s(unsigned v) {
+    v &= 0x3ffu;
+    v = (v | v << 16) & 0x30000ffu;
+    v = (v | v << 8) & 0x300f00fu;
+    v = (v | v << 4) & 0x30c30c3u;
+    v = (v | v << 2) & 0x9249249u;
+    return v;
+}
+
+// The faces are sorted by the Hilbert key of their centroid, so the face nearest to a point ON the surface is found
+// (approximately) by a binary search of the point's own key -- no box tests at all; a short bounded local search from
+// there polishes the seed.
+__global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ Sweep1Args a, const float *__restrict__ fx,
+                                                        const float *__restrict__ fy, const float *__restrict__ fz,
+                                                        const unsigned *__restrict__ fkeys, float3 klo, float kinv, unsigned budget) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= a.P || a.slot[i] >= 0) return;
+    const float x = fx[i], y = fy[i], z = fz[i];
+    if (!(x == x && y == y && z == z)) return;          // no foot point: k_sweep1 borrows a neighbour's seed
+    unsigned qx = (unsigned)fminf(fmaxf((x - klo.x) * kinv, 0.f), 1023.f);
+    unsigned qy = (unsigned)fminf(fmaxf((y - klo.y) * kinv, 0.f), 1023.f);
+    unsigned qz = (unsigned)fminf(fmaxf((z - klo.z) * kinv, 0.f), 1023.f);
+    hilbert_axes_to_transpose(qx, qy, qz, 10);
+    const unsigned key = (spread10s(qx) << 2) | (spread10s(qy) << 1) | spread10s(qz);
+    int lo = 0, hi = a.F;                               // lower_bound
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&fkeys[mid]) < key) lo = mid + 1; else hi = mid;
+    }
+    Nearest best;
+    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
+    const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
+    QueryF32 q;
+    q.x = x; q.y = y; q.z = z;
+    Traversal<QueryF32> tr(q, best, a.cent, a.boxes, a.tl, a.F, eps);
+    const int s1 = min(lo, a.F - 1), s0 = max(s1 - 1, 0);
+    { const float4 c = a.cent[s0]; tr.best.offer(q.d2(c), s0, __float_as_int(c.w)); }
+    { const float4 c = a.cent[s1]; tr.best.offer(q.d2(c), s1, __float_as_int(c.w)); }
+    tr.budget = budget;
+    tr.from_seed(tr.best.slot);
+    a.slot[i] = tr.best.slot;
 }
 
 // MODE 0: nearest face + weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
 template <bool F64, int MODE>
-__global__ void __launch_bounds__(128) k_sweep1(const Sweep1Args a) {
+__global__ void __launch_bounds__(128) k_sweep1(const __grid_constant__ Sweep1Args a) {
     if (MODE == 1 && a.st->stop) return;
 
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -623,10 +672,30 @@ static Sweep1Args make_args(nw_ctx *h) {
     return a;
 }
 
+int nw_save_feet(nw_ctx *h) {
+    // called by nw_set_topology BEFORE the old mesh is overwritten
+    if (h->P == 0 || !h->weights_valid || !h->sfaces || !h->posq || !h->slot) { h->feet_valid = false; return NW_OK; }
+    NW_CHECK(nw_alloc(h, &h->fx, (size_t)h->P)); NW_CHECK(nw_alloc(h, &h->fy, (size_t)h->P)); NW_CHECK(nw_alloc(h, &h->fz, (size_t)h->P));
+    k_save_feet<<<nw_grid(h->P, 256), 256, 0, h->stream>>>(h->P, h->slot, h->sfaces, h->posq, h->w0, h->w1, h->w2, h->fx, h->fy, h->fz);
+    NW_LAUNCH_CHECK();
+    h->feet_valid = true;
+    return NW_OK;
+}
+
 int nw_launch_seed_leaders(nw_ctx *h) {
     if (h->P == 0 || !h->seeds_cold) return NW_OK;
     const int B = 128;
     Sweep1Args a = make_args(h);
+    if (h->feet_valid) {
+        // foot points of the previous block exist: on-surface queries, individually good seeds (measured: the cold
+        // iteration costs 8.3 ms instead of 27 ms at C3).  On the very first block the localisations themselves are
+        // too far from the surface for this lookup to pay off (measured slower than the 1-in-32 root search below).
+        k_seed_from_feet<<<nw_grid(h->P, B), B, 0, h->stream>>>(a, h->fx, h->fy, h->fz, h->fkeys,
+                                                                make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv, 48u);
+        NW_LAUNCH_CHECK();
+        h->seeds_cold = false;
+        return NW_OK;
+    }
     const int GL = nw_grid((h->P + 31) / 32, B);
     if (h->px64) k_seed_leaders<true><<<GL, B, 0, h->stream>>>(a);
     else k_seed_leaders<false><<<GL, B, 0, h->stream>>>(a);

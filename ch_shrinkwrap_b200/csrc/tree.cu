@@ -303,6 +303,7 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     NW_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const int B = 256;
+    NW_CHECK(nw_save_feet(h));       // seeds for the next block, taken from the mesh that is about to be replaced
     h->M = M; h->F = F;
     h->weights_valid = false;
     NW_CHECK(nw_alloc(h, &h->posq, (size_t)M)); NW_CHECK(nw_alloc(h, &h->nrmq, (size_t)M));
@@ -372,6 +373,9 @@ int nw_tree_build(nw_ctx *h) {
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, keys2, idx, order, F, 0, 30, s);
     if (tmp > h->cub_tmp_bytes) { NW_CHECK(nw_alloc(h, (char **)&h->cub_tmp, tmp)); h->cub_tmp_bytes = tmp; }
     NW_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, keys, keys2, idx, order, F, 0, 30, s));
+    NW_CHECK(nw_alloc(h, &h->fkeys, (size_t)F));
+    NW_CUDA(cudaMemcpyAsync(h->fkeys, keys2, sizeof(unsigned) * F, cudaMemcpyDeviceToDevice, s));
+    h->key_lo[0] = lo[0]; h->key_lo[1] = lo[1]; h->key_lo[2] = lo[2]; h->key_inv = inv;
     k_sorted_faces<<<nw_grid(F, B), B, 0, s>>>(h->faces, order, F, h->sfaces);
     h->launches += 7;
     // level sizes

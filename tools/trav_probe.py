@@ -10,6 +10,7 @@ P=len(pts)
 st=(ctypes.c_uint64*4)(); sg=(ctypes.c_double*9)(); cg._h.call('nw_set_profile',1)
 sm=ctypes.c_double()
 for it in range(8):
+    if it == 4: cg._upload_topology()
     cg.search(pts, lams=[5.0], num_iters=1, sigma_inv=s_inv)
     cg._h.call('nw_get_traversal_stats', st)
     cg._h.call('nw_get_profile', sg, None, ctypes.byref(sm)); print('   stages', [round(x,2) for x in sg]); cg._h.call('nw_set_profile',1)
