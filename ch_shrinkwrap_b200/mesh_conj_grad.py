@@ -26,6 +26,12 @@ class _Session:
             rank, nranks, uid = comm
             self.handle.call('nw_comm_init', int(rank), int(nranks), uid)
 
+    def __deepcopy__(self, memo):
+        return None            # device state is not copyable; a copied mesh opens its own session on first use
+
+    def __reduce__(self):
+        return (type(None), ())
+
     def set_points(self, points, sigma_inv, weights):
         key = (id(points), points.shape, points.dtype.str, points.__array_interface__['data'][0],
                None if np.isscalar(sigma_inv) else (id(sigma_inv), sigma_inv.__array_interface__['data'][0]),

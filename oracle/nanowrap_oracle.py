@@ -233,6 +233,28 @@ class OracleConjGrad:
         return np.real(self.fs)
 
 
+class OracleConjGrad64(OracleConjGrad):
+    """Same algorithm with the subspace matrices accumulated in float64.  The reference forms ``Hc = AS^T AS`` with a
+    float32 sgemm and keeps ``H`` in float32 (conj_grad.py:194,202,208-215), so whenever the search
+    directions are nearly dependent (cond(H) up to 1e8 once the last step is added) its own step carries visible
+    float32 noise.  This variant separates that noise from implementation error in the parity tests."""
+
+    def subsearch(self, f0, res, fdefs, lams, S):
+        n_search = S.shape[1]
+        prefs = f0 - fdefs[0]
+        AS = np.zeros((np.size(res), n_search), 'f')
+        for k in range(n_search):
+            AS[:, k] = self.Afunc(S[:, k])[self.mask]
+        AS = AS.astype(np.float64)
+        S64 = S.astype(np.float64)
+        l2 = float(lams[0]) ** 2
+        H = AS.T @ AS + l2 * (S64.T @ S64)
+        G = AS.T @ np.asarray(res, np.float64) - l2 * (S64.T @ prefs)
+        c = np.linalg.solve(H, G)
+        self.c, self.cond = c, float(np.linalg.cond(H))
+        return f0 + np.dot(S, c), 0.0, [0.0]
+
+
 # ---- secondary 1-ring regularisers (conj_grad_utils.c:249-710) -----------------------
 def _ring_call(name, f, nbrs, ref, out):
     f = np.ascontiguousarray(f, dtype=np.float32)
