@@ -33,6 +33,8 @@ WORKLOADS = {
     'c1': dict(points=10_000, geo=8, curvature_weight=20.0, block=10, desc='config0: ~10k localisations, 642-vertex mesh'),
     'c2': dict(points=1_000_000, geo=71, curvature_weight=10.0, block=5, desc='config1: 1M localisations, 50 412-vertex mesh'),
     'c3': dict(points=10_000_000, geo=224, curvature_weight=10.0, block=5, desc='config2: 10M localisations, 501 762-vertex two-lobed mesh'),
+    'c4': dict(points=12_500_000, geo=316, curvature_weight=10.0, block=5, desc='config3: 100M localisations over 8 GPUs (12.5M per GPU), 998 562-vertex replicated mesh'),
+    'c5': dict(points=2_000_000, geo=632, curvature_weight=50.0, block=5, desc='config4: curvature stress, 3 994 242-vertex mesh, sparse 2M-localisation cloud'),
 }
 REFERENCE_SAMPLE = 'c2'   # bounded CPU sample: same shape, same 20 localisations per vertex, 1/10 of c3
 STAGES = ['refit', 'shift', 'sweep1', 'allreduce_acc', 'mesh_prior', 'sweep2', 'allreduce_scalars', 'solve_update', 'seed_leaders']
@@ -44,6 +46,7 @@ def build_workload(name, seed):
     cfg = WORKLOADS[name]
     shape = synth.two_lobed()
     v, f = minimesh.geodesic_sphere(cfg['geo'])
+    v, f = minimesh.spatially_sorted(v, f)       # arbitrary generator order -> spatially coherent vertex / face order
     r = synth.radial_surface(shape, v, n_bisect=32)
     pts, sig = synth.mesh_surface_cloud(v * r[:, None], f, cfg['points'], seed=seed)
     mesh = MembraneMesh(v * (1.2 * r)[:, None], f, kc=1.0, step_size=cfg['curvature_weight'],

@@ -76,7 +76,9 @@ static int ensure_partials(nw_ctx *h) {
     return NW_OK;
 }
 
-static int upload_state(nw_ctx *h, const SolverState &s) {
+static int upload_state(nw_ctx *h, const SolverState &s0) {
+    SolverState s = s0;
+    for (int a = 0; a < 3; ++a) { s.bbox[a] = 0x7fffffff; s.bbox[3 + a] = (int)0x80000000; }
     NW_CUDA(cudaMemcpyAsync(h->st, &s, sizeof(SolverState), cudaMemcpyHostToDevice, h->stream));
     return NW_OK;
 }

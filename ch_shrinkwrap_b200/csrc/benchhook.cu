@@ -31,6 +31,7 @@ extern "C" int nw_bench_kernel(nw_ctx *h, const char *name, int reps, float *ms_
     SolverState s;
     NW_CUDA(cudaMemcpy(&s, h->st, sizeof(s), cudaMemcpyDeviceToHost));
     s.stop = 0; s.nan_flag = 0;
+    for (int a = 0; a < 3; ++a) { s.bbox[a] = 0x7fffffff; s.bbox[3 + a] = (int)0x80000000; }
     if (s.n_search < 2) s.n_search = 2;
     NW_CUDA(cudaMemcpy(h->st, &s, sizeof(s), cudaMemcpyHostToDevice));
     NW_CHECK(nw_set_acc_shifts(h));

@@ -44,6 +44,7 @@ struct SolverState {
     int n_search;                 // 2 on the first iteration of a call, 3 afterwards (last_step)
     int acc_shift;                // fixed-point fraction bits of the adjoint accumulators
     int infl_shift;               // ditto for the AH*1 accumulator
+    int bbox[6];                  // ordered-int bounding box of the vertices (k_shift_partial -> k_shift_final)
     float coord_l1;               // bound on |x|+|y|+|z| over vertices and points (rounding slack of the box tests)
     float lam;
     unsigned long long trav[4];   // traversal statistics: node tests, leaf visits, exact fp64 evaluations, max node tests of one point

@@ -15,17 +15,19 @@ namespace {
 
 __device__ __forceinline__ double pow2d(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }
 
-// single CTA: bbox of the vertices, combined with the (static) bbox of the points
-__global__ void k_shift(const float4 *__restrict__ pos, int M, float plo_x, float plo_y, float plo_z,
-                        float phi_x, float phi_y, float phi_z, double wn_max, double p_global, SolverState *st) {
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// bounding box of the vertices: block reduction + ordered-int atomics into st->bbox (reset by k_shift_final)
+__global__ void __launch_bounds__(256) k_shift_partial(const float4 *__restrict__ pos, int M, SolverState *st) {
     if (st->stop) return;
-    float lo[3] = {plo_x, plo_y, plo_z}, hi[3] = {phi_x, phi_y, phi_z};
-    for (int i = threadIdx.x; i < M; i += blockDim.x) {
-        float4 v = pos[i];
-        float c[3] = {v.x, v.y, v.z};
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        const float4 v = pos[i];
+        const float c[3] = {v.x, v.y, v.z};
         for (int a = 0; a < 3; ++a) if (c[a] == c[a]) { lo[a] = fminf(lo[a], c[a]); hi[a] = fmaxf(hi[a], c[a]); }
     }
-    __shared__ float slo[3][32], shi[3][32];
+    __shared__ float slo[3][8], shi[3][8];
     for (int a = 0; a < 3; ++a)
         for (int o = 16; o; o >>= 1) {
             lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
@@ -34,31 +36,41 @@ __global__ void k_shift(const float4 *__restrict__ pos, int M, float plo_x, floa
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) for (int a = 0; a < 3; ++a) { slo[a][wid] = lo[a]; shi[a][wid] = hi[a]; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double ext = 0.0;
-        float l1 = 0.f;
-        for (int a = 0; a < 3; ++a) {
-            float l = slo[a][0], u = shi[a][0];
-            for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { l = fminf(l, slo[a][k]); u = fmaxf(u, shi[a][k]); }
-            ext = fmax(ext, (double)u - (double)l);
-            l1 += fmaxf(fabsf(l), fabsf(u));
-        }
-        st->coord_l1 = l1;
-        // |w_j res_c| <= Wn_max * extent ; a vertex sums at most P_global of them
-        double bound = fmax(wn_max * ext, 1e-30) * fmax(p_global, 1.0);
-        int e;
-        frexp(bound, &e);
-        int sh = 61 - e;
-        st->acc_shift = max(-60, min(60, sh));
-        frexp(fmax(p_global, 1.0), &e);
-        st->infl_shift = 61 - e;
+    if (threadIdx.x < 3) {
+        const int a = threadIdx.x;
+        float l = slo[a][0], u = shi[a][0];
+        for (int k = 1; k < 8; ++k) { l = fminf(l, slo[a][k]); u = fmaxf(u, shi[a][k]); }
+        if (l <= u) { atomicMin(&st->bbox[a], f2ord(l)); atomicMax(&st->bbox[3 + a], f2ord(u)); }
     }
+}
+
+// combine with the (static) bbox of the points -> fixed-point scales and the coordinate bound of the box tests
+__global__ void k_shift_final(float plo_x, float plo_y, float plo_z, float phi_x, float phi_y, float phi_z, double wn_max,
+                              double p_global, SolverState *st) {
+    if (st->stop || threadIdx.x != 0) return;
+    const float plo[3] = {plo_x, plo_y, plo_z}, phi[3] = {phi_x, phi_y, phi_z};
+    double ext = 0.0;
+    float l1 = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        const float l = fminf(plo[a], ord2f(st->bbox[a])), u = fmaxf(phi[a], ord2f(st->bbox[3 + a]));
+        ext = fmax(ext, (double)u - (double)l);
+        l1 += fmaxf(fabsf(l), fabsf(u));
+        st->bbox[a] = 0x7fffffff; st->bbox[3 + a] = (int)0x80000000;      // ready for the next iteration
+    }
+    st->coord_l1 = l1;
+    // |w_j res_c| <= Wn_max * extent ; a vertex sums at most P_global of them
+    double bound = fmax(wn_max * ext, 1e-30) * fmax(p_global, 1.0);
+    int e;
+    frexp(bound, &e);
+    st->acc_shift = max(-60, min(60, 61 - e));
+    frexp(fmax(p_global, 1.0), &e);
+    st->infl_shift = 61 - e;
 }
 
 #define NW_MSUM 9   // hw00 hw01 hw11 hw02 hw12 hw22 gw0 gw1 gw2
 
 template <bool WRITE_DIRS>
-__global__ void __launch_bounds__(256) k_mesh_prior(int M, unsigned long long *__restrict__ acc, SolverState *__restrict__ st,
+__global__ void __launch_bounds__(256, 3) k_mesh_prior(int M, unsigned long long *__restrict__ acc, SolverState *__restrict__ st,
                                                     const float4 *__restrict__ posq, const float4 *__restrict__ nrmq,
                                                     const int *__restrict__ nbrT, const int *__restrict__ valence,
                                                     float4 *__restrict__ Sq,
@@ -174,12 +186,19 @@ __global__ void k_solve(const double *__restrict__ mesh_partials, int n_mesh_blo
                         int iter_index) {
     if (st->stop) return;
     __shared__ double red[NW_MSUM];
-    if (threadIdx.x < NW_MSUM) {
+    __shared__ double sh[256];
+    for (int k = 0; k < NW_MSUM; ++k) {         // fixed order: thread t sums partials t, t+256, ...; then a fixed tree
         double v = 0.0;
-        for (int b = 0; b < n_mesh_blocks; ++b) v += mesh_partials[(size_t)b * NW_MSUM + threadIdx.x];
-        red[threadIdx.x] = v;
+        for (int b = threadIdx.x; b < n_mesh_blocks; b += 256) v += mesh_partials[(size_t)b * NW_MSUM + k];
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 128; o; o >>= 1) {
+            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) red[k] = sh[0];
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x != 0) return;
     for (int k = 0; k < 6; ++k) st->hw[k] = red[k];
     for (int k = 0; k < 3; ++k) st->gw[k] = red[6 + k];
@@ -291,8 +310,10 @@ __global__ void k_S_rows(const float4 *__restrict__ Sq, int M, float *__restrict
 int nw_apply_AH_device(nw_ctx *h, const float *rx, const float *ry, const float *rz, double bound, float *out3M);
 
 int nw_set_acc_shifts(nw_ctx *h) {
-    k_shift<<<1, 1024, 0, h->stream>>>(h->posq, h->M, h->bbox_pts[0], h->bbox_pts[1], h->bbox_pts[2], h->bbox_pts[3],
-                                        h->bbox_pts[4], h->bbox_pts[5], h->wn_max, (double)std::max<int64_t>(h->P_global, 1), h->st);
+    k_shift_partial<<<std::min(nw_grid(h->M, 256), 148 * 4), 256, 0, h->stream>>>(h->posq, h->M, h->st);
+    NW_LAUNCH_CHECK();
+    k_shift_final<<<1, 32, 0, h->stream>>>(h->bbox_pts[0], h->bbox_pts[1], h->bbox_pts[2], h->bbox_pts[3], h->bbox_pts[4],
+                                            h->bbox_pts[5], h->wn_max, (double)std::max<int64_t>(h->P_global, 1), h->st);
     NW_LAUNCH_CHECK();
     return NW_OK;
 }
@@ -303,7 +324,7 @@ int nw_launch_mesh_prior(nw_ctx *h, bool write_dirs) {
     const int G = mesh_blocks(h);
     if (write_dirs)
         k_mesh_prior<true><<<G, 256, 0, h->stream>>>(h->M, h->acc, h->st, h->posq, h->nrmq, h->nbrT, h->valence, h->Sq,
-                                                     h->fdef, nullptr, h->partials + (size_t)h->n_partials * 16);
+                                                     nullptr, nullptr, h->partials + (size_t)h->n_partials * 16);
     else
         k_mesh_prior<false><<<G, 256, 0, h->stream>>>(h->M, h->acc, h->st, h->posq, h->nrmq, h->nbrT, h->valence, h->Sq,
                                                       h->fdef, h->scratchM, nullptr);
@@ -312,7 +333,7 @@ int nw_launch_mesh_prior(nw_ctx *h, bool write_dirs) {
 }
 
 int nw_launch_solve_update(nw_ctx *h, int iter_index, int last_step) {
-    k_solve<<<1, 32, 0, h->stream>>>(h->partials + (size_t)h->n_partials * 16, mesh_blocks(h), h->st, h->hist, iter_index);
+    k_solve<<<1, 256, 0, h->stream>>>(h->partials + (size_t)h->n_partials * 16, mesh_blocks(h), h->st, h->hist, iter_index);
     NW_LAUNCH_CHECK();
     k_update<<<mesh_blocks(h), 256, 0, h->stream>>>(h->M, h->st, h->posq, h->Sq, last_step, 0);
     NW_LAUNCH_CHECK();

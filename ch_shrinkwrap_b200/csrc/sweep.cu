@@ -10,6 +10,7 @@
 // Determinism: the adjoint accumulates in 64-bit fixed point (integer atomics are order-independent,
 // float atomics are not); the Gram sums use a fixed thread->point assignment and a fixed two-stage tree.
 #include <cfloat>
+#include <cstring>
 #include <type_traits>
 #include "common.cuh"
 
@@ -760,7 +761,12 @@ extern "C" int nw_compute_weights(nw_ctx *h) {
     if (!h) return NW_ERR_ARG;
     NW_ARG(h->M > 0 && (h->px || h->P == 0), "nw_compute_weights: points and topology must be set first");
     NW_CUDA(cudaSetDevice(h->device));
-    NW_CUDA(cudaMemsetAsync(h->st, 0, sizeof(SolverState), h->stream));
+    {
+        SolverState z;
+        memset(&z, 0, sizeof(z));
+        for (int a = 0; a < 3; ++a) { z.bbox[a] = 0x7fffffff; z.bbox[3 + a] = (int)0x80000000; }
+        NW_CUDA(cudaMemcpyAsync(h->st, &z, sizeof(SolverState), cudaMemcpyHostToDevice, h->stream));
+    }
     NW_CHECK(nw_tree_refit(h));
     NW_CHECK(nw_set_acc_shifts(h));             // also refreshes the coordinate bound used by the box tests
     NW_CHECK(nw_launch_sweep1(h, false));

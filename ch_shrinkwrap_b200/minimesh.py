@@ -243,6 +243,27 @@ def geodesic_sphere(n):
     return verts, faces
 
 
+def spatially_sorted(vertices, faces, bits=10):
+    """Renumber vertices (and sort faces) along a Morton curve.  The order of a mesh's vertex array is arbitrary; a
+    spatially coherent one (what marching-cubes / remeshing codes produce) keeps 1-ring gathers cache-local."""
+    v = np.asarray(vertices, dtype=np.float64)
+    lo, hi = v.min(0), v.max(0)
+    q = np.clip(((v - lo) / max(float((hi - lo).max()), 1e-30) * (2 ** bits - 1)).astype(np.uint64), 0, 2 ** bits - 1)
+
+    def spread(x):
+        r = np.zeros_like(x)
+        for b in range(bits):
+            r |= ((x >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b)
+        return r
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1)) | (spread(q[:, 2]) << np.uint64(2))
+    order = np.argsort(key, kind='stable')
+    rank = np.empty(len(v), np.int64)
+    rank[order] = np.arange(len(v))
+    f = rank[np.asarray(faces)]
+    f = f[np.argsort(f.min(1), kind='stable')]
+    return v[order], f.astype(np.int32)
+
+
 def icosphere(level):
     """Icosahedron subdivided ``level`` times (10*4^level + 2 vertices)."""
     return geodesic_sphere(2 ** level)
