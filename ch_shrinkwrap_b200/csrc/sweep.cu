@@ -159,8 +159,11 @@ struct Traversal {
         for (int level = 0; level <= top; ++level) {
             const int c0 = (level < top) ? (node / NW_FAN) * NW_FAN : 0;
             const int n = min(NW_FAN, tl.count[level] - c0);
-            for (int k = 0; k < n; ++k)
-                if (c0 + k != node) dfs_subtree(level, c0 + k);
+            // the NW_FAN-1 OTHER children, rotated so that every lane has work in every round
+            for (int j = 1; j < NW_FAN; ++j) {
+                const int cand = c0 + ((node - c0 + j) % NW_FAN);
+                if (cand < c0 + n) dfs_subtree(level, cand);
+            }
             node /= NW_FAN;
         }
     }
