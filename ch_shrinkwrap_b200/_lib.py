@@ -51,6 +51,7 @@ SIGNATURES = {
     'nw_set_profile': (c_int, [c_void_p, c_int]),
     'nw_get_profile': (c_int, [c_void_p, _d, POINTER(c_int64), _d]),
     'nw_get_traversal_stats': (c_int, [c_void_p, POINTER(c_uint64)]),
+    'nw_debug_tree': (c_int, [c_void_p, c_int, _f, POINTER(c_int), POINTER(c_int)]),
     'nw_launch_count': (c_int64, [c_void_p]),
 }
 

@@ -2,6 +2,7 @@
 // one stream without host round trips; the stop rule, NaN guard and histories live on the device and
 // are read back once at the end (the reference's loop is mesh_conj_grad.py:218-290).
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include "common.cuh"
 
@@ -47,7 +48,7 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free(&h->w0); nw_free(&h->w1); nw_free(&h->w2);
     nw_free(&h->rx); nw_free(&h->ry); nw_free(&h->rz);
     nw_free(&h->posq); nw_free(&h->nrmq); nw_free(&h->faces); nw_free(&h->nbrT); nw_free(&h->valence); nw_free(&h->valid); nw_free(&h->stage_nbr); nw_free(&h->stage_hev);
-    nw_free(&h->sfaces); nw_free(&h->cent); nw_free(&h->boxes);
+    nw_free(&h->sfaces); nw_free(&h->cent); nw_free(&h->boxes); nw_free(&h->shell_mom);
     nw_free(&h->acc); nw_free(&h->Sq); nw_free(&h->fdef);
     nw_free(&h->partials); nw_free(&h->st); nw_free(&h->hist);
     nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP);
@@ -126,7 +127,20 @@ extern "C" int nw_get_traversal_stats(nw_ctx *h, uint64_t out[4]) {
     if (!h || !out) return NW_ERR_ARG;
     SolverState r;
     NW_CUDA(cudaMemcpy(&r, h->st, sizeof(SolverState), cudaMemcpyDeviceToHost));
+#ifdef NW_LEVEL_STATS
+    for (int l = 0; l < 12; ++l) fprintf(stderr, "level %2d tests %12llu pass %12llu\n", l, r.lvl_tests[l], r.lvl_pass[l]);
+#endif
     for (int k = 0; k < 4; ++k) out[k] = r.trav[k];
+    return NW_OK;
+}
+// diagnosis: copy the boxes of one tree level (16 floats each) and the level sizes
+extern "C" int nw_debug_tree(nw_ctx *h, int level, float *boxes16, int *counts, int *n_levels) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(h->boxes && h->tl.n_levels > 0, "nw_debug_tree: no tree");
+    if (n_levels) *n_levels = h->tl.n_levels;
+    if (counts) for (int l = 0; l < h->tl.n_levels; ++l) counts[l] = h->tl.count[l];
+    if (boxes16 && level >= 0 && level < h->tl.n_levels)
+        NW_CUDA(cudaMemcpy(boxes16, h->boxes + h->tl.offset[level], sizeof(Box) * h->tl.count[level], cudaMemcpyDeviceToHost));
     return NW_OK;
 }
 extern "C" int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms) {

@@ -17,13 +17,27 @@
 #define NW_MAX_ITERS 4096
 #define NW_N_STAGES 9    // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders
 
-// Node bound = ORIENTED box: a surface patch is thin along its normal and tilted against the coordinate axes, so an
-// axis-aligned box is mostly empty space.  Axes: n (patch normal), t1 (stored), t2 = n x t1; one interval per axis.
+// Node bound = ORIENTED box INTERSECTED with a SPHERICAL SHELL.
+//  * oriented box: a surface patch is thin along its normal and tilted against the coordinate axes, so an axis-aligned
+//    box is mostly empty space.  Axes n (patch normal), t1 = tangent_of(n), t2 = n x t1; one interval per axis.
+//  * spherical shell: a large patch of a curved surface is thick along its mean normal (sagitta L^2/8R) but still thin
+//    around a sphere fitted to it; {x : r_lo <= |x - o| <= r_hi} removes that thickness from the upper tree levels.
+// Both only ever prune: the answer never depends on how tight they are.
 struct Box {
-    float4 a;   // n.x n.y n.z | t1.x
-    float4 b;   // t1.y t1.z | n-interval min, max
-    float4 c;   // t1-interval min, max | t2-interval min, max
-};              // 48 B
+    float4 a;   // n.x n.y n.z | n-interval min
+    float4 b;   // n-interval max | t1-interval min, max | t2-interval min
+    float4 c;   // t2-interval max | shell centre o.x o.y o.z
+    float4 d;   // shell r_lo, r_hi | 1 if the node has a fitted shell | unused
+};              // 64 B
+
+// orthonormal completion of a unit vector (Duff et al. 2017, branchless): returns t1; t2 = n x t1 everywhere.
+// Used identically when boxes are built and when they are tested.
+__host__ __device__ __forceinline__ float3 nw_tangent_of(const float nx, const float ny, const float nz) {
+    const float sg = copysignf(1.0f, nz);
+    const float a = -1.0f / (sg + nz);
+    const float b = nx * ny * a;
+    return make_float3(1.0f + sg * nx * nx * a, sg * b, -sg * nx);
+}
 struct TreeLevels {
     int n_levels;                 // level 0 = leaves
     int count[NW_MAX_LEVELS];
@@ -47,6 +61,9 @@ struct SolverState {
     int bbox[6];                  // ordered-int bounding box of the vertices (k_shift_partial -> k_shift_final)
     float coord_l1;               // bound on |x|+|y|+|z| over vertices and points (rounding slack of the box tests)
     float lam;
+#ifdef NW_LEVEL_STATS
+    unsigned long long lvl_tests[32], lvl_pass[32];   // diagnosis builds only: node tests / passes per tree level
+#endif
     unsigned long long trav[4];   // traversal statistics: node tests, leaf visits, exact fp64 evaluations, max node tests of one point
 };
 
@@ -89,6 +106,7 @@ struct nw_ctx {
     int4 *sfaces = nullptr;                      // per sorted slot: corner ids + face id
     float4 *cent = nullptr;                      // per sorted slot: centroid xyz + face id bits
     Box *boxes = nullptr;
+    float *shell_mom = nullptr;                  // 5 regression moments per node (sphere fit at upload time)
     TreeLevels tl;
     bool seeds_cold = true;                      // no nearest-face seeds yet for this topology
     float *fx = nullptr, *fy = nullptr, *fz = nullptr;   // foot points on the previous block's surface (seeds after a remesh)

@@ -71,23 +71,30 @@ struct Nearest {
     }
 };
 
-// Conservative lower bound of the squared distance from the query to anything inside a node's oriented box:
-// sum over the three axes of (interval gap - eps)^2.  Projections are float32 dot products, so every gap is shrunk
-// by an absolute slack eps (>= 4x the worst-case rounding error of both projections, DESIGN.md "exactness") and the
-// sum by a relative 1e-5 (axes are orthonormal only to float32 accuracy).  A node is skipped only if this bound
-// exceeds the best exact fp64 distance, so skipping can never change the answer.
+// Conservative lower bound of the squared distance from the query to anything inside a node:
+//   max( sum over the three box axes of (interval gap - eps)^2 ,  (shell gap - eps_s)^2 ).
+// Projections / radii are float32, so every gap is shrunk by an absolute slack (>= 4x the worst-case rounding error of
+// both the query's and the members' evaluation, DESIGN.md "exactness") and the squares by a relative 1e-5 (axes are
+// orthonormal only to float32 accuracy).  A node is skipped only if this bound exceeds the best exact fp64 distance,
+// so skipping can never change the answer.
 template <typename Q>
 __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps) {
-    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
+    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c), d = __ldg(&bp->d);
     const float x = q.fx(), y = q.fy(), z = q.fz();
-    const float t2x = a.y * b.y - a.z * b.x, t2y = a.z * a.w - a.x * b.y, t2z = a.x * b.x - a.y * a.w;
+    const float3 t1 = nw_tangent_of(a.x, a.y, a.z);
+    const float t2x = a.y * t1.z - a.z * t1.y, t2y = a.z * t1.x - a.x * t1.z, t2z = a.x * t1.y - a.y * t1.x;
     const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
-    const float p1 = fmaf(a.w, x, fmaf(b.x, y, b.y * z));
+    const float p1 = fmaf(t1.x, x, fmaf(t1.y, y, t1.z * z));
     const float p2 = fmaf(t2x, x, fmaf(t2y, y, t2z * z));
-    const float g0 = fmaxf(fmaxf(fmaxf(b.z - pn, pn - b.w), 0.f) - eps, 0.f);
-    const float g1 = fmaxf(fmaxf(fmaxf(c.x - p1, p1 - c.y), 0.f) - eps, 0.f);
-    const float g2 = fmaxf(fmaxf(fmaxf(c.z - p2, p2 - c.w), 0.f) - eps, 0.f);
-    return __fmul_rd(__fadd_rd(__fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1)), __fmul_rd(g2, g2)), 0.99999f);
+    const float g0 = fmaxf(fmaxf(fmaxf(a.w - pn, pn - b.x), 0.f) - eps, 0.f);
+    const float g1 = fmaxf(fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f) - eps, 0.f);
+    const float g2 = fmaxf(fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f) - eps, 0.f);
+    float lb = __fadd_rd(__fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1)), __fmul_rd(g2, g2));
+    const float dx = x - c.y, dy = y - c.z, dz = z - c.w;
+    const float r = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    const float gs = fmaxf(fmaxf(d.x - r, r - d.y), 0.f) - fmaf(r, 4e-6f, eps);
+    if (gs > 0.f) lb = fmaxf(lb, __fmul_rd(gs, gs));
+    return __fmul_rd(lb, 0.99999f);
 }
 
 // greedy-descent score: the bound, with the squared distance to the box centre as a tie-breaker (several overlapping
@@ -96,13 +103,14 @@ template <typename Q>
 __device__ __forceinline__ float node_score(const Q &q, const Box *__restrict__ bp, float eps) {
     const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
     const float x = q.fx(), y = q.fy(), z = q.fz();
-    const float t2x = a.y * b.y - a.z * b.x, t2y = a.z * a.w - a.x * b.y, t2z = a.x * b.x - a.y * a.w;
+    const float3 t1 = nw_tangent_of(a.x, a.y, a.z);
+    const float t2x = a.y * t1.z - a.z * t1.y, t2y = a.z * t1.x - a.x * t1.z, t2z = a.x * t1.y - a.y * t1.x;
     const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
-    const float p1 = fmaf(a.w, x, fmaf(b.x, y, b.y * z));
+    const float p1 = fmaf(t1.x, x, fmaf(t1.y, y, t1.z * z));
     const float p2 = fmaf(t2x, x, fmaf(t2y, y, t2z * z));
-    const float g0 = fmaxf(fmaxf(b.z - pn, pn - b.w), 0.f), g1 = fmaxf(fmaxf(c.x - p1, p1 - c.y), 0.f),
-                g2 = fmaxf(fmaxf(c.z - p2, p2 - c.w), 0.f);
-    const float c0 = pn - 0.5f * (b.z + b.w), c1 = p1 - 0.5f * (c.x + c.y), c2 = p2 - 0.5f * (c.z + c.w);
+    const float g0 = fmaxf(fmaxf(a.w - pn, pn - b.x), 0.f), g1 = fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f),
+                g2 = fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f);
+    const float c0 = pn - 0.5f * (a.w + b.x), c1 = p1 - 0.5f * (b.y + b.z), c2 = p2 - 0.5f * (b.w + c.x);
     return (g0 * g0 + g1 * g1 + g2 * g2) + 1e-4f * (c0 * c0 + c1 * c1 + c2 * c2);
 }
 
@@ -119,6 +127,9 @@ struct Traversal {
     int F;
     float eps;
     unsigned n_tests = 0, n_leaves = 0, n_exact = 0;
+#ifdef NW_LEVEL_STATS
+    SolverState *dbg = nullptr;
+#endif
     unsigned budget = 0xffffffffu;   // seeds only: stop refining after this many node tests (the result is then approximate)
 
     __device__ __forceinline__ Traversal(const Q &q_, const Nearest &b_, const float4 *c_, const Box *bx_, const TreeLevels &tl_, int F_, float eps_)
@@ -140,7 +151,13 @@ struct Traversal {
         int level = L, idx = I;
         while (true) {
             if (++n_tests > budget) return;
+#ifdef NW_LEVEL_STATS
+            const bool pass_ = node_lb(q, &boxes[tl.offset[level] + idx], eps) <= best.ub;
+            if (dbg) { atomicAdd(&dbg->lvl_tests[level], 1ull); if (pass_) atomicAdd(&dbg->lvl_pass[level], 1ull); }
+            if (pass_) {
+#else
             if (node_lb(q, &boxes[tl.offset[level] + idx], eps) <= best.ub) {
+#endif
                 if (level == 0) leaf(idx);
                 else { --level; idx *= NW_FAN; continue; }
             }
@@ -229,6 +246,9 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
     if constexpr (F64) q.set(xd, yd, zd);
     else { q.x = x; q.y = y; q.z = z; }
     Traversal<decltype(q)> tr(q, best, a.cent, a.boxes, a.tl, a.F, eps);
+#ifdef NW_LEVEL_STATS
+    tr.dbg = a.st;
+#endif
     int seed = active ? a.slot[i] : 0;
     // Cold start (first iteration after a topology upload): lanes without a seed borrow one from a lane that has it
     // (k_seed_leaders searched lane 0's point from the root) -- Hilbert-sorted neighbours share (nearly) the same

@@ -123,27 +123,23 @@ __global__ void k_sorted_faces(const int *__restrict__ faces, const int *__restr
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-// orthonormal completion of a unit vector (Duff et al. 2017, branchless): returns t1; t2 = n x t1 everywhere
-__device__ __forceinline__ float3 tangent_of(const float3 n) {
-    const float sg = copysignf(1.0f, n.z);
-    const float a = -1.0f / (sg + n.z);
-    const float b = n.x * n.y * a;
-    return make_float3(1.0f + sg * n.x * n.x * a, sg * b, -sg * n.x);
-}
 __device__ __forceinline__ float3 unit_or_z(float3 n) {
     const float nn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
     if (nn > 1e-20f && nn <= FLT_MAX) return make_float3(n.x / nn, n.y / nn, n.z / nn);
     return make_float3(0.f, 0.f, 1.f);
 }
-__device__ __forceinline__ void project3(const float3 n, const float3 t1, const float4 c, float &pn, float &p1, float &p2) {
+__device__ __forceinline__ void project3(const float3 n, const float4 c, float &pn, float &p1, float &p2) {
+    const float3 t1 = nw_tangent_of(n.x, n.y, n.z);
     const float3 t2 = make_float3(n.y * t1.z - n.z * t1.y, n.z * t1.x - n.x * t1.z, n.x * t1.y - n.y * t1.x);
     pn = fmaf(n.x, c.x, fmaf(n.y, c.y, n.z * c.z));
     p1 = fmaf(t1.x, c.x, fmaf(t1.y, c.y, t1.z * c.z));
     p2 = fmaf(t2.x, c.x, fmaf(t2.y, c.y, t2.z * c.z));
 }
+#define NW_EMPTY_LO __int_as_float(f2ord(FLT_MAX))      // ordered-int encodings of an empty interval
+#define NW_EMPTY_HI __int_as_float(f2ord(-FLT_MAX))
 
 // centroids at the current f (sorted order) + leaf boxes: 8 lanes cooperate on one leaf.
-// Leaf normal = normalised sum of the member faces' area-weighted normals.
+// Leaf normal = normalised sum of the member faces' area-weighted normals.  Leaves carry no shell.
 __global__ void k_refit_leaves(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F,
                                float4 *__restrict__ cent, Box *__restrict__ leaf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,9 +160,8 @@ __global__ void k_refit_leaves(const int4 *__restrict__ sfaces, const float4 *__
         fn.x += __shfl_xor_sync(0xffffffffu, fn.x, o); fn.y += __shfl_xor_sync(0xffffffffu, fn.y, o); fn.z += __shfl_xor_sync(0xffffffffu, fn.z, o);
     }
     const float3 n = unit_or_z(fn);
-    const float3 t1 = tangent_of(n);
     float p[3];
-    project3(n, t1, c, p[0], p[1], p[2]);
+    project3(n, c, p[0], p[1], p[2]);
     float mn[3], mx[3];
     for (int k = 0; k < 3; ++k) {
         const bool ok = live && (p[k] == p[k]);
@@ -178,16 +173,18 @@ __global__ void k_refit_leaves(const int4 *__restrict__ sfaces, const float4 *__
     }
     if ((threadIdx.x & (NW_LEAF - 1)) == 0 && live) {
         Box b;
-        b.a = make_float4(n.x, n.y, n.z, t1.x);
-        b.b = make_float4(t1.y, t1.z, mn[0], mx[0]);
-        b.c = make_float4(mn[1], mx[1], mn[2], mx[2]);
+        b.a = make_float4(n.x, n.y, n.z, mn[0]);
+        b.b = make_float4(mx[0], mn[1], mx[1], mn[2]);
+        b.c = make_float4(mx[2], 0.f, 0.f, 0.f);
+        b.d = make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f);          // shell disabled: [0, inf)
         leaf[i / NW_LEAF] = b;
     }
 }
 
 // one interior level: node i covers children [4i, 4i+4); normal = normalised sum of child normals.  Intervals start
-// empty (ordered-int encoding) and are filled by k_box_extents.
-__global__ void k_refit_level(const Box *__restrict__ child, int n_child, Box *__restrict__ parent, int n_parent) {
+// empty (ordered-int encoding) and are filled by k_box_extents.  The shell centre (fitted once per topology upload by
+// k_shell_fit) is preserved.
+__global__ void k_refit_level(const Box *__restrict__ child, int n_child, Box *__restrict__ parent, int n_parent, int init) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_parent) return;
     float3 n = make_float3(0.f, 0.f, 0.f);
@@ -197,24 +194,24 @@ __global__ void k_refit_level(const Box *__restrict__ child, int n_child, Box *_
     }
     const float nn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
     n = (nn > 1e-3f) ? unit_or_z(n) : make_float3(0.f, 0.f, 1.f);
-    const float3 t1 = tangent_of(n);
-    const float e0 = __int_as_float(f2ord(FLT_MAX)), e1 = __int_as_float(f2ord(-FLT_MAX));
-    Box b;
-    b.a = make_float4(n.x, n.y, n.z, t1.x);
-    b.b = make_float4(t1.y, t1.z, e0, e1);
-    b.c = make_float4(e0, e1, e0, e1);
-    parent[i] = b;
+    Box *b = &parent[i];
+    const float4 oc = init ? make_float4(0.f, 0.f, 0.f, 0.f) : b->c;
+    const bool shell = !init && b->d.z > 0.5f;
+    b->a = make_float4(n.x, n.y, n.z, NW_EMPTY_LO);
+    b->b = make_float4(NW_EMPTY_HI, NW_EMPTY_LO, NW_EMPTY_HI, NW_EMPTY_LO);
+    b->c = make_float4(NW_EMPTY_HI, oc.y, oc.z, oc.w);
+    b->d = shell ? make_float4(NW_EMPTY_LO, NW_EMPTY_HI, 1.f, 0.f) : make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f);
 }
 
-// box extents of interior levels: every centroid projects onto its ancestors' axes.  A level-l node covers
+// box (and shell) extents of interior levels: every centroid projects onto its ancestors' axes.  A level-l node covers
 // NW_LEAF * NW_FAN^l consecutive slots: below 32 the reduction is a sub-warp shuffle, from 32 a warp shuffle (one
-// atomic pair per warp and axis), from 256 (one CTA inside one node) it goes through shared memory (one pair per CTA).
+// atomic pair per warp and quantity), from 256 (one CTA inside one node) it goes through shared memory.
 __global__ void __launch_bounds__(256) k_box_extents(const float4 *__restrict__ cent, int F, Box *__restrict__ boxes, TreeLevels tl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < F;
     const float4 c = live ? cent[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __shared__ float smn[3][8], smx[3][8];
+    __shared__ float smn[4][8], smx[4][8];
     int node = i / NW_LEAF;
     int span = NW_LEAF;
     for (int l = 1; l < tl.n_levels; ++l) {
@@ -222,12 +219,17 @@ __global__ void __launch_bounds__(256) k_box_extents(const float4 *__restrict__ 
         span = min(span * NW_FAN, 1 << 20);
         const int nd = min(node, tl.count[l] - 1);          // lanes past F still take part in the shuffles
         Box *b = &boxes[tl.offset[l] + nd];
-        const float4 ba = b->a, bb = b->b;
-        float p[3];
-        project3(make_float3(ba.x, ba.y, ba.z), make_float3(ba.w, bb.x, bb.y), c, p[0], p[1], p[2]);
-        float mn[3], mx[3];
+        const float4 ba = b->a, bc = b->c;
+        const bool shell = b->d.z > 0.5f;
+        float p[4];
+        project3(make_float3(ba.x, ba.y, ba.z), c, p[0], p[1], p[2]);
+        {
+            const float dx = c.x - bc.y, dy = c.y - bc.z, dz = c.z - bc.w;
+            p[3] = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        }
+        float mn[4], mx[4];
         const int width = min(span, 32);
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 4; ++k) {
             const bool ok = live && (p[k] == p[k]);
             mn[k] = ok ? p[k] : FLT_MAX; mx[k] = ok ? p[k] : -FLT_MAX;
             for (int o = width / 2; o; o >>= 1) {
@@ -235,16 +237,17 @@ __global__ void __launch_bounds__(256) k_box_extents(const float4 *__restrict__ 
                 mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
             }
         }
-        int *dmin[3] = {(int *)&b->b.z, (int *)&b->c.x, (int *)&b->c.z};
-        int *dmax[3] = {(int *)&b->b.w, (int *)&b->c.y, (int *)&b->c.w};
+        int *dmin[4] = {(int *)&b->a.w, (int *)&b->b.y, (int *)&b->b.w, (int *)&b->d.x};
+        int *dmax[4] = {(int *)&b->b.x, (int *)&b->b.z, (int *)&b->c.x, (int *)&b->d.y};
+        const int nq = shell ? 4 : 3;
         if (span < 256) {
             if ((lane & (width - 1)) == 0)
-                for (int k = 0; k < 3; ++k) if (mn[k] <= mx[k]) { atomicMin(dmin[k], f2ord(mn[k])); atomicMax(dmax[k], f2ord(mx[k])); }
+                for (int k = 0; k < nq; ++k) if (mn[k] <= mx[k]) { atomicMin(dmin[k], f2ord(mn[k])); atomicMax(dmax[k], f2ord(mx[k])); }
         } else {
             __syncthreads();
-            if (lane == 0) for (int k = 0; k < 3; ++k) { smn[k][wid] = mn[k]; smx[k][wid] = mx[k]; }
+            if (lane == 0) for (int k = 0; k < 4; ++k) { smn[k][wid] = mn[k]; smx[k][wid] = mx[k]; }
             __syncthreads();
-            if (threadIdx.x < 3) {
+            if (threadIdx.x < nq) {
                 const int k = threadIdx.x;
                 float a = smn[k][0], z = smx[k][0];
                 for (int w = 1; w < 8; ++w) { a = fminf(a, smn[k][w]); z = fmaxf(z, smx[k][w]); }
@@ -258,9 +261,65 @@ __global__ void k_box_decode(Box *__restrict__ boxes, int first, int count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     Box *b = &boxes[first + i];
-    b->b.z = ord2f(__float_as_int(b->b.z)); b->b.w = ord2f(__float_as_int(b->b.w));
-    b->c.x = ord2f(__float_as_int(b->c.x)); b->c.y = ord2f(__float_as_int(b->c.y));
-    b->c.z = ord2f(__float_as_int(b->c.z)); b->c.w = ord2f(__float_as_int(b->c.w));
+    b->a.w = ord2f(__float_as_int(b->a.w)); b->b.x = ord2f(__float_as_int(b->b.x));
+    b->b.y = ord2f(__float_as_int(b->b.y)); b->b.z = ord2f(__float_as_int(b->b.z));
+    b->b.w = ord2f(__float_as_int(b->b.w)); b->c.x = ord2f(__float_as_int(b->c.x));
+    if (b->d.z > 0.5f) { b->d.x = ord2f(__float_as_int(b->d.x)); b->d.y = ord2f(__float_as_int(b->d.y)); }
+}
+
+// ---- spherical-shell fit, once per topology upload ---------------------------------------------------------------------
+// In a node's frame (origin = box centre) a spherical cap is z = z0 + s r^2 with s = -1/(2 rho): regress z on r^2.
+// Moments per node: N, sum z, sum r^2, sum z r^2, sum r^4.  (float atomics are fine here: the fit only decides how
+// tight a pruning bound is, never a result.)
+__global__ void __launch_bounds__(256) k_shell_moments(const float4 *__restrict__ cent, int F, const Box *__restrict__ boxes, TreeLevels tl,
+                                                       float *__restrict__ mom) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < F;
+    const float4 c = live ? cent[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int lane = threadIdx.x & 31;
+    int node = i / NW_LEAF;
+    for (int l = 1; l < tl.n_levels; ++l) {
+        node /= NW_FAN;
+        const int nd = min(node, tl.count[l] - 1);
+        const Box *b = &boxes[tl.offset[l] + nd];
+        const float4 ba = b->a, bb = b->b, bc = b->c;
+        float pn, p1, p2;
+        project3(make_float3(ba.x, ba.y, ba.z), c, pn, p1, p2);
+        const float z = pn - 0.5f * (ba.w + bb.x), u = p1 - 0.5f * (bb.y + bb.z), v = p2 - 0.5f * (bb.w + bc.x);
+        const float r2 = u * u + v * v;
+        float m[5] = {live ? 1.f : 0.f, live ? z : 0.f, live ? r2 : 0.f, live ? z * r2 : 0.f, live ? r2 * r2 : 0.f};
+        for (int k = 0; k < 5; ++k)
+            for (int o = 16; o; o >>= 1) m[k] += __shfl_xor_sync(0xffffffffu, m[k], o);   // a warp (32 slots) lies in one node for l >= 1
+        if (lane == 0 && node < tl.count[l])
+            for (int k = 0; k < 5; ++k) atomicAdd(&mom[5 * (size_t)(tl.offset[l] + nd) + k], m[k]);
+    }
+}
+
+__global__ void k_shell_fit(Box *__restrict__ boxes, const float *__restrict__ mom, int first, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Box *b = &boxes[first + i];
+    const float *m = mom + 5 * (size_t)(first + i);
+    const double N = m[0], Sz = m[1], Sr = m[2], Szr = m[3], Srr = m[4];
+    const double den = N * Srr - Sr * Sr;
+    bool ok = N >= 32.0 && den > 1e-12 * fmax(N * Srr, 1e-300);
+    double slope = 0.0, z0 = 0.0, rho = 0.0;
+    if (ok) {
+        slope = (N * Szr - Sz * Sr) / den;
+        z0 = (Sz - slope * Sr) / N;
+        ok = fabs(slope) > 2.5e-5;                   // |rho| = 1/(2|slope|) <= 2e4: beyond that the cap is a plane for our purposes
+        if (ok) rho = -1.0 / (2.0 * slope);
+    }
+    if (!ok || !(fabs(rho) <= 2e4)) { b->d = make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f); return; }
+    const float4 ba = b->a, bb = b->b, bc = b->c;
+    const float3 n = make_float3(ba.x, ba.y, ba.z);
+    const float3 t1 = nw_tangent_of(n.x, n.y, n.z);
+    const float3 t2 = make_float3(n.y * t1.z - n.z * t1.y, n.z * t1.x - n.x * t1.z, n.x * t1.y - n.y * t1.x);
+    const double cn = 0.5 * ((double)ba.w + bb.x) + z0 - rho, c1 = 0.5 * ((double)bb.y + bb.z), c2 = 0.5 * ((double)bb.w + bc.x);
+    b->c.y = (float)(cn * n.x + c1 * t1.x + c2 * t2.x);
+    b->c.z = (float)(cn * n.y + c1 * t1.y + c2 * t2.y);
+    b->c.w = (float)(cn * n.z + c1 * t1.z + c2 * t2.z);
+    b->d = make_float4(0.f, FLT_MAX * 2.0f, 1.f, 0.f);      // enabled; the radius interval is measured by the next refit
 }
 
 inline float ordered_to_float(int v) {
@@ -349,6 +408,8 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     return nw_tree_build(h);
 }
 
+static int tree_fit_shells(nw_ctx *h);
+
 int nw_tree_build(nw_ctx *h) {
     cudaStream_t s = h->stream;
     const int B = 256, F = h->F;
@@ -392,10 +453,10 @@ int nw_tree_build(nw_ctx *h) {
     NW_CHECK(nw_alloc(h, &h->boxes, (size_t)off));
     NW_CUDA(cudaStreamSynchronize(s));
     nw_free(&d_bbox); nw_free(&idx); nw_free(&order); nw_free(&keys); nw_free(&keys2);
-    return nw_tree_refit(h);
+    return tree_fit_shells(h);
 }
 
-int nw_tree_refit(nw_ctx *h) {
+static int tree_refit_impl(nw_ctx *h, int init) {
     cudaStream_t s = h->stream;
     const int B = 256;
     const TreeLevels &tl = h->tl;
@@ -403,7 +464,7 @@ int nw_tree_refit(nw_ctx *h) {
     NW_LAUNCH_CHECK();
     for (int l = 1; l < tl.n_levels; ++l) {
         k_refit_level<<<nw_grid(tl.count[l], B), B, 0, s>>>(h->boxes + tl.offset[l - 1], tl.count[l - 1],
-                                                             h->boxes + tl.offset[l], tl.count[l]);
+                                                             h->boxes + tl.offset[l], tl.count[l], init);
         NW_LAUNCH_CHECK();
     }
     if (tl.n_levels > 1) {
@@ -414,6 +475,29 @@ int nw_tree_refit(nw_ctx *h) {
         NW_LAUNCH_CHECK();
     }
     return NW_OK;
+}
+
+int nw_tree_refit(nw_ctx *h) { return tree_refit_impl(h, 0); }
+
+// once per topology upload: boxes without shells, then the sphere fits, then the first regular refit measures the shells
+static int tree_fit_shells(nw_ctx *h) {
+    cudaStream_t s = h->stream;
+    const int B = 256;
+    const TreeLevels &tl = h->tl;
+    NW_CHECK(tree_refit_impl(h, 1));
+    if (tl.n_levels > 1) {
+        const int total = tl.offset[tl.n_levels - 1] + tl.count[tl.n_levels - 1];
+        float *mom = nullptr;
+        NW_CHECK(nw_alloc(h, &h->shell_mom, (size_t)5 * total));
+        mom = h->shell_mom;
+        NW_CUDA(cudaMemsetAsync(mom, 0, sizeof(float) * 5 * total, s));
+        k_shell_moments<<<nw_grid(h->F, B), B, 0, s>>>(h->cent, h->F, h->boxes, tl, mom);
+        NW_LAUNCH_CHECK();
+        const int first = tl.offset[1], count = total - first;
+        k_shell_fit<<<nw_grid(count, B), B, 0, s>>>(h->boxes, mom, first, count);
+        NW_LAUNCH_CHECK();
+    }
+    return tree_refit_impl(h, 0);
 }
 
 extern "C" int nw_set_positions(nw_ctx *h, const float *pos) {

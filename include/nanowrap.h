@@ -149,6 +149,8 @@ int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double 
 /* nearest-face traversal statistics accumulated since the last nw_search / nw_ncc / nw_bench_kernel state reset:
  * node bound tests, leaf visits, exact fp64 distance evaluations, largest node-test count of a single point */
 int nw_get_traversal_stats(nw_ctx *h, uint64_t out[4]);
+/* diagnosis: boxes of one level of the centroid pyramid (16 floats per node, layout of csrc/common.cuh: Box) */
+int nw_debug_tree(nw_ctx *h, int level, float *boxes16, int *counts, int *n_levels);
 /* kernels launched by this handle since creation (for bench.py's gpu_launches) */
 int64_t nw_launch_count(nw_ctx *h);
 

@@ -1,0 +1,18 @@
+import sys, os, ctypes, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from ch_shrinkwrap_b200.mesh_conj_grad import ShrinkwrapMeshConjGrad
+mesh, pts, sig, cfg = bench.build_workload('c3', 1234)
+s_inv=(1.0/sig.ravel()).astype(np.float32)
+cg=ShrinkwrapMeshConjGrad(mesh, pts); mesh.cg=cg
+cg.search(pts, lams=[5.0], num_iters=6, sigma_inv=s_inv)
+counts=(ctypes.c_int*32)(); nl=ctypes.c_int()
+cg._h.call('nw_debug_tree', -1, None, counts, ctypes.byref(nl))
+print('levels', nl.value, list(counts)[:nl.value])
+for lvl in range(nl.value-1, max(nl.value-5,0), -1):
+    n=counts[lvl]; b=np.zeros((n,16),np.float32)
+    cg._h.call('nw_debug_tree', lvl, b.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), None, None)
+    print('level', lvl)
+    for k in range(min(n,8)):
+        r=b[k]
+        print('  n=(%.2f %.2f %.2f) ext n[%.0f,%.0f] t1[%.0f,%.0f] t2[%.0f,%.0f] o=(%.0f %.0f %.0f) r[%.1f,%.1f] shell=%d'%(r[0],r[1],r[2],r[3],r[4],r[5],r[6],r[7],r[8],r[9],r[10],r[11],r[12],min(r[13],1e9),r[14]))
