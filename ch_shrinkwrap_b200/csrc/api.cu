@@ -48,7 +48,7 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free(&h->w0); nw_free(&h->w1); nw_free(&h->w2);
     nw_free(&h->rx); nw_free(&h->ry); nw_free(&h->rz);
     nw_free(&h->posq); nw_free(&h->nrmq); nw_free(&h->faces); nw_free(&h->nbrT); nw_free(&h->valence); nw_free(&h->valid); nw_free(&h->stage_nbr); nw_free(&h->stage_hev);
-    nw_free(&h->sfaces); nw_free(&h->cent); nw_free(&h->boxes); nw_free(&h->shell_mom);
+    nw_free(&h->sfaces); nw_free(&h->cent); nw_free(&h->boxes); nw_free(&h->par); nw_free(&h->cbegin); nw_free(&h->leaf_of_slot); nw_free(&h->node_f);
     nw_free(&h->acc); nw_free(&h->Sq); nw_free(&h->fdef);
     nw_free(&h->partials); nw_free(&h->st); nw_free(&h->hist);
     nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP);
@@ -140,7 +140,7 @@ extern "C" int nw_debug_tree(nw_ctx *h, int level, float *boxes16, int *counts, 
     if (n_levels) *n_levels = h->tl.n_levels;
     if (counts) for (int l = 0; l < h->tl.n_levels; ++l) counts[l] = h->tl.count[l];
     if (boxes16 && level >= 0 && level < h->tl.n_levels)
-        NW_CUDA(cudaMemcpy(boxes16, h->boxes + h->tl.offset[level], sizeof(Box) * h->tl.count[level], cudaMemcpyDeviceToHost));
+        NW_CUDA(cudaMemcpy(boxes16, h->boxes + h->tl.off[level], sizeof(Box) * h->tl.count[level], cudaMemcpyDeviceToHost));
     return NW_OK;
 }
 extern "C" int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms) {

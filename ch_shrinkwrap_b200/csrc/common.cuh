@@ -13,7 +13,7 @@
 #ifndef NW_FAN
 #define NW_FAN 4         // children per interior node
 #endif
-#define NW_MAX_LEVELS 28
+#define NW_MAX_LEVELS 12
 #define NW_MAX_ITERS 4096
 #define NW_N_STAGES 9    // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders
 
@@ -39,9 +39,10 @@ __host__ __device__ __forceinline__ float3 nw_tangent_of(const float nx, const f
     return make_float3(1.0f + sg * nx * nx * a, sg * b, -sg * nx);
 }
 struct TreeLevels {
-    int n_levels;                 // level 0 = leaves
-    int count[NW_MAX_LEVELS];
-    int offset[NW_MAX_LEVELS];    // into the single boxes[] buffer
+    int n_levels;                 // level 0 = root, n_levels-1 = leaf level
+    int count[NW_MAX_LEVELS];     // nodes per level
+    int off[NW_MAX_LEVELS];       // node offset of the level in boxes[] / par[]
+    int cb_off[NW_MAX_LEVELS];    // offset of the level in cbegin[] (count+1 entries: first child; leaf level: first slot)
 };
 
 // Scalars produced and consumed on the device inside one search() call.
@@ -106,7 +107,8 @@ struct nw_ctx {
     int4 *sfaces = nullptr;                      // per sorted slot: corner ids + face id
     float4 *cent = nullptr;                      // per sorted slot: centroid xyz + face id bits
     Box *boxes = nullptr;
-    float *shell_mom = nullptr;                  // 5 regression moments per node (sphere fit at upload time)
+    int *par = nullptr, *cbegin = nullptr, *leaf_of_slot = nullptr;   // octree tables (see tree.cu)
+    float *node_f = nullptr;                     // 5 floats per node: normal sums, then sphere-fit moments (upload time)
     TreeLevels tl;
     bool seeds_cold = true;                      // no nearest-face seeds yet for this topology
     float *fx = nullptr, *fy = nullptr, *fz = nullptr;   // foot points on the previous block's surface (seeds after a remesh)

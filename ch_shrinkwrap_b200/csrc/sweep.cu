@@ -114,17 +114,23 @@ __device__ __forceinline__ float node_score(const Q &q, const Box *__restrict__ 
     return (g0 * g0 + g1 * g1 + g2 * g2) + 1e-4f * (c0 * c0 + c1 * c1 + c2 * c2);
 }
 
-// Stackless search of the implicit pyramid.  All state is scalar and held BY VALUE so that it stays in registers
-// (a per-thread stack array, or references to the caller's query, made the compiler spill the whole object to local
-// memory and reload it inside every node test).
+// Stackless search of the octree of occupied Hilbert cells (tree.cu).  All state is scalar and held BY VALUE so that it
+// stays in registers (a per-thread stack array, or references to the caller's query, made the compiler spill the whole
+// object to local memory and reload it inside every node test).
+struct TreeView {
+    const float4 *__restrict__ cent;
+    const Box *__restrict__ boxes;
+    const int *__restrict__ par;        // parent index | (last child of its parent) << 31
+    const int *__restrict__ cbegin;     // first child (leaf level: first slot), count+1 entries per level
+    const int *__restrict__ leaf_of_slot;
+};
+
 template <typename Q>
 struct Traversal {
     Q q;
     Nearest best;
-    const float4 *__restrict__ cent;
-    const Box *__restrict__ boxes;
+    TreeView tv;
     const TreeLevels &tl;          // lives in the kernel's __grid_constant__ parameter space (LDC with a dynamic index)
-    int F;
     float eps;
     unsigned n_tests = 0, n_leaves = 0, n_exact = 0;
 #ifdef NW_LEVEL_STATS
@@ -132,73 +138,73 @@ struct Traversal {
 #endif
     unsigned budget = 0xffffffffu;   // seeds only: stop refining after this many node tests (the result is then approximate)
 
-    __device__ __forceinline__ Traversal(const Q &q_, const Nearest &b_, const float4 *c_, const Box *bx_, const TreeLevels &tl_, int F_, float eps_)
-        : q(q_), best(b_), cent(c_), boxes(bx_), tl(tl_), F(F_), eps(eps_) {}
+    __device__ __forceinline__ Traversal(const Q &q_, const Nearest &b_, const TreeView &tv_, const TreeLevels &tl_, float eps_)
+        : q(q_), best(b_), tv(tv_), tl(tl_), eps(eps_) {}
 
     __device__ __forceinline__ void leaf(int idx) {
-        const int base = idx * NW_LEAF;
-        const int n = min(NW_LEAF, F - base);
+        const int *cb = tv.cbegin + tl.cb_off[tl.n_levels - 1] + idx;
+        const int s0 = __ldg(cb), s1 = __ldg(cb + 1);
         ++n_leaves;
-        for (int k = 0; k < n; ++k) {
-            const float4 c = __ldg(&cent[base + k]);
-            if (q.lb_box(c, c) <= best.ub) { ++n_exact; best.offer(q.d2(c), base + k, __float_as_int(c.w)); }
+        for (int s = s0; s < s1; ++s) {
+            const float4 c = __ldg(&tv.cent[s]);
+            if (q.lb_box(c, c) <= best.ub) { ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
         }
     }
-    // Depth-first search of the subtree rooted at (L, I).  The hierarchy is implicit (children of node i are
-    // 4i..4i+3), so "next node" is index arithmetic.  Children are visited in index order: with a seed the bound is
-    // already (nearly) exact, so nearest-first ordering would buy nothing.
+    // Depth-first search of the subtree rooted at node I of level L.  Children and next siblings come from two small
+    // integer tables, so no per-thread stack is needed.  Children are visited in index (= Hilbert) order: with a seed
+    // the bound is already (nearly) exact, so nearest-first ordering would buy nothing.
     __device__ __forceinline__ void dfs_subtree(int L, int I) {
+        const int leafL = tl.n_levels - 1;
         int level = L, idx = I;
         while (true) {
             if (++n_tests > budget) return;
 #ifdef NW_LEVEL_STATS
-            const bool pass_ = node_lb(q, &boxes[tl.offset[level] + idx], eps) <= best.ub;
+            const bool pass_ = node_lb(q, &tv.boxes[tl.off[level] + idx], eps) <= best.ub;
             if (dbg) { atomicAdd(&dbg->lvl_tests[level], 1ull); if (pass_) atomicAdd(&dbg->lvl_pass[level], 1ull); }
             if (pass_) {
 #else
-            if (node_lb(q, &boxes[tl.offset[level] + idx], eps) <= best.ub) {
+            if (node_lb(q, &tv.boxes[tl.off[level] + idx], eps) <= best.ub) {
 #endif
-                if (level == 0) leaf(idx);
-                else { --level; idx *= NW_FAN; continue; }
+                if (level == leafL) leaf(idx);
+                else { idx = __ldg(&tv.cbegin[tl.cb_off[level] + idx]); ++level; continue; }
             }
             while (true) {
                 if (level == L) return;
-                if ((idx % NW_FAN) != NW_FAN - 1 && idx + 1 < tl.count[level]) { ++idx; break; }
-                ++level; idx /= NW_FAN;
+                const int pv = __ldg(&tv.par[tl.off[level] + idx]);
+                if (pv >= 0) { ++idx; break; }            // not the last child: next sibling
+                --level; idx = pv & 0x7fffffff;
             }
         }
     }
-    // warm query: start at the seed's leaf and climb; at every level only the sibling subtrees are searched
-    __device__ __forceinline__ void from_seed(int seed_slot) {
-        int node = seed_slot / NW_LEAF;
+    // climb from a leaf: at every level only the sibling subtrees are searched
+    __device__ __forceinline__ void from_leaf(int node) {
         leaf(node);
-        const int top = tl.n_levels - 1;
-        for (int level = 0; level <= top; ++level) {
-            const int c0 = (level < top) ? (node / NW_FAN) * NW_FAN : 0;
-            const int n = min(NW_FAN, tl.count[level] - c0);
-            // the NW_FAN-1 OTHER children, rotated so that every lane has work in every round
-            for (int j = 1; j < NW_FAN; ++j) {
-                const int cand = c0 + ((node - c0 + j) % NW_FAN);
-                if (cand < c0 + n) dfs_subtree(level, cand);
-            }
-            node /= NW_FAN;
+        for (int level = tl.n_levels - 1; level >= 1; --level) {
+            const int p = __ldg(&tv.par[tl.off[level] + node]) & 0x7fffffff;
+            const int *cb = tv.cbegin + tl.cb_off[level - 1] + p;
+            const int c0 = __ldg(cb), c1 = __ldg(cb + 1);
+            for (int sib = c0; sib < c1; ++sib)
+                if (sib != node) dfs_subtree(level, sib);
+            node = p;
         }
     }
+    // warm query: start at the seed's leaf
+    __device__ __forceinline__ void from_seed(int seed_slot) { from_leaf(__ldg(&tv.leaf_of_slot[seed_slot])); }
     // cold query: greedy descent (always into the child with the smallest bound) to get a first candidate, then the
     // exact search from the leaf it reached
     __device__ __forceinline__ void top_down() {
-        const int top = tl.n_levels - 1;
-        int node = 0, c0 = 0, n = tl.count[top];
-        for (int level = top; level >= 0; --level) {
+        int node = 0;
+        for (int level = 0; level < tl.n_levels - 1; ++level) {
+            const int *cb = tv.cbegin + tl.cb_off[level] + node;
+            const int c0 = __ldg(cb), c1 = __ldg(cb + 1);
             float bl = FLT_MAX * 2.0f;
-            for (int k = 0; k < n; ++k) {
-                const float l = node_score(q, &boxes[tl.offset[level] + c0 + k], eps);
+            for (int ch = c0; ch < c1; ++ch) {
+                const float l = node_score(q, &tv.boxes[tl.off[level + 1] + ch], eps);
                 ++n_tests;
-                if (l < bl) { bl = l; node = c0 + k; }
+                if (l < bl) { bl = l; node = ch; }
             }
-            if (level > 0) { c0 = node * NW_FAN; n = min(NW_FAN, tl.count[level - 1] - c0); }
         }
-        from_seed(node * NW_LEAF);
+        from_leaf(node);
     }
 };
 
@@ -229,9 +235,9 @@ struct Sweep1Args {
     float sinv_scalar, wmean;
     int *slot;
     float *w0, *w1, *w2, *rx, *ry, *rz;
-    const float4 *cent, *posq;
+    const float4 *posq;
     const int4 *sfaces;
-    const Box *boxes;
+    TreeView tv;
     TreeLevels tl;
     int F;
     unsigned long long *acc;
@@ -245,7 +251,7 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
     if constexpr (F64) q.set(xd, yd, zd);
     else { q.x = x; q.y = y; q.z = z; }
-    Traversal<decltype(q)> tr(q, best, a.cent, a.boxes, a.tl, a.F, eps);
+    Traversal<decltype(q)> tr(q, best, a.tv, a.tl, eps);
 #ifdef NW_LEVEL_STATS
     tr.dbg = a.st;
 #endif
@@ -267,7 +273,7 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
         if (seed < 0) seed = s0;
     }
     if (active && tr.best.slot < 0) {
-        const float4 c = a.cent[seed];
+        const float4 c = a.tv.cent[seed];
         tr.best.offer(tr.q.d2(c), seed, __float_as_int(c.w));
         tr.from_seed(seed);
     }
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(128) k_seed_leaders(const __grid_constant__ Sw
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
     if constexpr (F64) q.set(a.px64[i], a.py64[i], a.pz64[i]);
     else { q.x = x; q.y = y; q.z = z; }
-    Traversal<decltype(q)> tr(q, best, a.cent, a.boxes, a.tl, a.F, eps);
+    Traversal<decltype(q)> tr(q, best, a.tv, a.tl, eps);
     tr.budget = 512;
     tr.top_down();
     a.slot[i] = tr.best.slot;     // >= 0: the first descent always reaches a leaf before the budget can run out
@@ -353,10 +359,10 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
     QueryF32 q;
     q.x = x; q.y = y; q.z = z;
-    Traversal<QueryF32> tr(q, best, a.cent, a.boxes, a.tl, a.F, eps);
+    Traversal<QueryF32> tr(q, best, a.tv, a.tl, eps);
     const int s1 = min(lo, a.F - 1), s0 = max(s1 - 1, 0);
-    { const float4 c = a.cent[s0]; tr.best.offer(q.d2(c), s0, __float_as_int(c.w)); }
-    { const float4 c = a.cent[s1]; tr.best.offer(q.d2(c), s1, __float_as_int(c.w)); }
+    { const float4 c = a.tv.cent[s0]; tr.best.offer(q.d2(c), s0, __float_as_int(c.w)); }
+    { const float4 c = a.tv.cent[s1]; tr.best.offer(q.d2(c), s1, __float_as_int(c.w)); }
     tr.budget = budget;
     tr.from_seed(tr.best.slot);
     a.slot[i] = tr.best.slot;
@@ -691,7 +697,8 @@ static Sweep1Args make_args(nw_ctx *h) {
     a.sinv_scalar = h->sinv_scalar; a.wmean = h->wmean;
     a.slot = h->slot;
     a.w0 = h->w0; a.w1 = h->w1; a.w2 = h->w2; a.rx = h->rx; a.ry = h->ry; a.rz = h->rz;
-    a.cent = h->cent; a.posq = h->posq; a.sfaces = h->sfaces; a.boxes = h->boxes; a.tl = h->tl; a.F = h->F;
+    a.posq = h->posq; a.sfaces = h->sfaces; a.tl = h->tl; a.F = h->F;
+    a.tv.cent = h->cent; a.tv.boxes = h->boxes; a.tv.par = h->par; a.tv.cbegin = h->cbegin; a.tv.leaf_of_slot = h->leaf_of_slot;
     a.acc = h->acc; a.st = h->st;
     return a;
 }

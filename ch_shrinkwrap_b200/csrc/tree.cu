@@ -122,6 +122,8 @@ __global__ void k_sorted_faces(const int *__restrict__ faces, const int *__restr
 
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ unsigned f2u(float f) { return (unsigned)f2ord(f) ^ 0x80000000u; }      // order-preserving float -> unsigned
+__device__ __forceinline__ int u2ord(unsigned u) { return (int)(u ^ 0x80000000u); }
 
 __device__ __forceinline__ float3 unit_or_z(float3 n) {
     const float nn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
@@ -138,125 +140,171 @@ __device__ __forceinline__ void project3(const float3 n, const float4 c, float &
 #define NW_EMPTY_LO __int_as_float(f2ord(FLT_MAX))      // ordered-int encodings of an empty interval
 #define NW_EMPTY_HI __int_as_float(f2ord(-FLT_MAX))
 
-// centroids at the current f (sorted order) + leaf boxes: 8 lanes cooperate on one leaf.
-// Leaf normal = normalised sum of the member faces' area-weighted normals.  Leaves carry no shell.
-__global__ void k_refit_leaves(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F,
-                               float4 *__restrict__ cent, Box *__restrict__ leaf) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+// ======================================================================================================================
+// The hierarchy is the OCTREE OF OCCUPIED HILBERT CELLS: a level-k node is the set of centroids that share the first 3k
+// bits of their (sorted) Hilbert key, i.e. one cube of the 2^k grid -- always a compact piece of surface.  (Cutting the
+// sorted order into fixed-size chunks instead mixes pieces that are consecutive on the curve but far apart in space:
+// measured boxes of 1/120 of the surface spanned half the object.)  Because the keys are sorted every node is a
+// contiguous range of slots, its children are a contiguous range of nodes one level down, and traversal needs two small
+// integer tables per level: `par` (parent index, top bit = "last child of its parent") and `cbegin` (first child; at the
+// leaf level: first slot).
+// ======================================================================================================================
+
+// histogram of the level at which consecutive keys first differ (-> number of nodes of every level)
+__global__ void k_level_histogram(const unsigned *__restrict__ keys, int F, int *__restrict__ hist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F || i == 0) return;
+    const unsigned x = keys[i] ^ keys[i - 1];
+    if (!x) return;
+    const int hb = 31 - __clz(x);                 // highest differing bit, 0..29
+    const int lvl = (29 - hb) / 3 + 1;            // first level whose prefix differs, 1..10
+    atomicAdd(&hist[lvl], 1);
+}
+
+__global__ void k_level_flags(const unsigned *__restrict__ keys, int F, int shift, int *__restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F) return;
+    flag[i] = (i == 0) ? 1 : (shift >= 32 ? 0 : ((keys[i] >> shift) != (keys[i - 1] >> shift)));
+}
+
+// id = inclusive scan of the flags (1-based node id per slot).  Writes, for the nodes of this level: first slot, parent,
+// and for the parent level the first-child table.
+__global__ void k_level_tables(const int *__restrict__ flag, const int *__restrict__ id, const int *__restrict__ id_parent,
+                               int F, int *__restrict__ start, int *__restrict__ par, int *__restrict__ cbegin_parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F || !flag[i]) return;
+    const int j = id[i] - 1;
+    start[j] = i;
+    if (id_parent) {
+        const int pj = id_parent[i] - 1;
+        par[j] = pj;
+        if (i == 0 || id_parent[i - 1] != id_parent[i]) cbegin_parent[pj] = j;     // first child of pj
+    } else par[j] = 0;
+}
+// top bit of par = this node is the last child of its parent
+__global__ void k_mark_last_child(int *__restrict__ par, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int p = par[j] & 0x7fffffff;
+    const bool last = (j == n - 1) || ((par[j + 1] & 0x7fffffff) != p);
+    par[j] = p | (last ? 0x80000000 : 0);
+}
+__global__ void k_copy_minus1(const int *__restrict__ id, int F, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F) out[i] = id[i] - 1;
+}
+
+// centroids at the current f, in sorted order
+__global__ void k_refit_centroids(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F, float4 *__restrict__ cent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F) return;
+    const int4 sf = sfaces[i];
+    const float3 cc = centroid_f32(pos[sf.x], pos[sf.y], pos[sf.z]);
+    cent[i] = make_float4(cc.x, cc.y, cc.z, __int_as_float(sf.w));
+}
+
+// warp-level "sum over lanes with the same key" for floats (build time only): every lane returns its group's sum
+__device__ __forceinline__ float group_sumf(unsigned grp, float v) {
+    float s = 0.f;
+    for (int src = 0; src < 32; ++src) {          // uniform trip count: every lane takes part in every shuffle
+        const float t = __shfl_sync(0xffffffffu, v, src);
+        if ((grp >> src) & 1u) s += t;
+    }
+    return s;
+}
+
+// build pass A: area-weighted face normals summed into every ancestor -> node frames
+__global__ void __launch_bounds__(256) k_node_normals(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F,
+                                                      const int *__restrict__ leaf_of_slot, const int *__restrict__ par,
+                                                      TreeLevels tl, float *__restrict__ nsum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < F;
     float3 fn = make_float3(0.f, 0.f, 0.f);
-    bool live = i < F;
+    int node = 0;
     if (live) {
-        int4 sf = sfaces[i];
+        const int4 sf = sfaces[i];
         const float4 a = pos[sf.x], b = pos[sf.y], d = pos[sf.z];
-        const float3 cc = centroid_f32(a, b, d);
-        c = make_float4(cc.x, cc.y, cc.z, __int_as_float(sf.w));
-        cent[i] = c;
         const float ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, vx = d.x - a.x, vy = d.y - a.y, vz = d.z - a.z;
         fn = make_float3(uy * vz - uz * vy, uz * vx - ux * vz, ux * vy - uy * vx);
         if (!(fabsf(fn.x) <= FLT_MAX && fabsf(fn.y) <= FLT_MAX && fabsf(fn.z) <= FLT_MAX)) fn = make_float3(0.f, 0.f, 0.f);
+        node = leaf_of_slot[i];
     }
-    for (int o = NW_LEAF / 2; o; o >>= 1) {
-        fn.x += __shfl_xor_sync(0xffffffffu, fn.x, o); fn.y += __shfl_xor_sync(0xffffffffu, fn.y, o); fn.z += __shfl_xor_sync(0xffffffffu, fn.z, o);
-    }
-    const float3 n = unit_or_z(fn);
-    float p[3];
-    project3(n, c, p[0], p[1], p[2]);
-    float mn[3], mx[3];
-    for (int k = 0; k < 3; ++k) {
-        const bool ok = live && (p[k] == p[k]);
-        mn[k] = ok ? p[k] : FLT_MAX; mx[k] = ok ? p[k] : -FLT_MAX;
-        for (int o = NW_LEAF / 2; o; o >>= 1) {
-            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    for (int l = tl.n_levels - 1; l >= 1; --l) {
+        const int key = live ? node : -1 - (int)(threadIdx.x & 31);
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const float sx = group_sumf(grp, fn.x), sy = group_sumf(grp, fn.y), sz = group_sumf(grp, fn.z);
+        if (live && (threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1)) {
+            float *d = nsum + 3 * (size_t)(tl.off[l] + node);
+            atomicAdd(d, sx); atomicAdd(d + 1, sy); atomicAdd(d + 2, sz);
         }
-    }
-    if ((threadIdx.x & (NW_LEAF - 1)) == 0 && live) {
-        Box b;
-        b.a = make_float4(n.x, n.y, n.z, mn[0]);
-        b.b = make_float4(mx[0], mn[1], mx[1], mn[2]);
-        b.c = make_float4(mx[2], 0.f, 0.f, 0.f);
-        b.d = make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f);          // shell disabled: [0, inf)
-        leaf[i / NW_LEAF] = b;
+        if (live) node = par[tl.off[l] + node] & 0x7fffffff;
     }
 }
 
-// one interior level: node i covers children [4i, 4i+4); normal = normalised sum of child normals.  Intervals start
-// empty (ordered-int encoding) and are filled by k_box_extents.  The shell centre (fitted once per topology upload by
-// k_shell_fit) is preserved.
-__global__ void k_refit_level(const Box *__restrict__ child, int n_child, Box *__restrict__ parent, int n_parent, int init) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_parent) return;
-    float3 n = make_float3(0.f, 0.f, 0.f);
-    for (int k = 0; k < NW_FAN; ++k) {
-        int c = NW_FAN * i + k;
-        if (c < n_child) { const float4 a = child[c].a; n.x += a.x; n.y += a.y; n.z += a.z; }
-    }
+// frames from the normal sums; intervals empty; shell disabled
+__global__ void k_node_frames(Box *__restrict__ boxes, const float *__restrict__ nsum, int first, int count) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const float *s = nsum + 3 * (size_t)(first + j);
+    float3 n = make_float3(s[0], s[1], s[2]);
     const float nn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
-    n = (nn > 1e-3f) ? unit_or_z(n) : make_float3(0.f, 0.f, 1.f);
-    Box *b = &parent[i];
-    const float4 oc = init ? make_float4(0.f, 0.f, 0.f, 0.f) : b->c;
-    const bool shell = !init && b->d.z > 0.5f;
+    n = (nn > 1e-20f && nn <= FLT_MAX) ? make_float3(n.x / nn, n.y / nn, n.z / nn) : make_float3(0.f, 0.f, 1.f);
+    Box *b = &boxes[first + j];
     b->a = make_float4(n.x, n.y, n.z, NW_EMPTY_LO);
     b->b = make_float4(NW_EMPTY_HI, NW_EMPTY_LO, NW_EMPTY_HI, NW_EMPTY_LO);
-    b->c = make_float4(NW_EMPTY_HI, oc.y, oc.z, oc.w);
-    b->d = shell ? make_float4(NW_EMPTY_LO, NW_EMPTY_HI, 1.f, 0.f) : make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f);
+    b->c = make_float4(NW_EMPTY_HI, 0.f, 0.f, 0.f);
+    b->d = make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f);
 }
 
-// box (and shell) extents of interior levels: every centroid projects onto its ancestors' axes.  A level-l node covers
-// NW_LEAF * NW_FAN^l consecutive slots: below 32 the reduction is a sub-warp shuffle, from 32 a warp shuffle (one
-// atomic pair per warp and quantity), from 256 (one CTA inside one node) it goes through shared memory.
-__global__ void __launch_bounds__(256) k_box_extents(const float4 *__restrict__ cent, int F, Box *__restrict__ boxes, TreeLevels tl) {
+// every iteration: intervals back to "empty" (frames and shell centres are kept for the whole block)
+__global__ void k_reset_extents(Box *__restrict__ boxes, int first, int count) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    Box *b = &boxes[first + j];
+    b->a.w = NW_EMPTY_LO; b->b.x = NW_EMPTY_HI; b->b.y = NW_EMPTY_LO; b->b.z = NW_EMPTY_HI; b->b.w = NW_EMPTY_LO; b->c.x = NW_EMPTY_HI;
+    if (b->d.z > 0.5f) { b->d.x = NW_EMPTY_LO; b->d.y = NW_EMPTY_HI; }
+}
+
+// every iteration: each centroid projects onto the frame (and shell centre) of every ancestor; lanes of a warp that
+// share the node are reduced with REDUX first, then one ordered-int atomic min/max per quantity
+__global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent, int F, const int *__restrict__ leaf_of_slot,
+                                                 const int *__restrict__ par, Box *__restrict__ boxes, TreeLevels tl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < F;
     const float4 c = live ? cent[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __shared__ float smn[4][8], smx[4][8];
-    int node = i / NW_LEAF;
-    int span = NW_LEAF;
-    for (int l = 1; l < tl.n_levels; ++l) {
-        node /= NW_FAN;
-        span = min(span * NW_FAN, 1 << 20);
-        const int nd = min(node, tl.count[l] - 1);          // lanes past F still take part in the shuffles
-        Box *b = &boxes[tl.offset[l] + nd];
-        const float4 ba = b->a, bc = b->c;
-        const bool shell = b->d.z > 0.5f;
-        float p[4];
-        project3(make_float3(ba.x, ba.y, ba.z), c, p[0], p[1], p[2]);
-        {
+    const bool finite = live && (c.x == c.x) && (c.y == c.y) && (c.z == c.z);
+    int node = live ? leaf_of_slot[i] : 0;
+    const unsigned lane = threadIdx.x & 31;
+    for (int l = tl.n_levels - 1; l >= 1; --l) {
+        const int key = live ? node : -1 - (int)lane;
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        Box *b = &boxes[tl.off[l] + node];
+        float p[4] = {0.f, 0.f, 0.f, 0.f};
+        bool shell = false;
+        if (live) {
+            const float4 ba = b->a, bc = b->c;
+            shell = b->d.z > 0.5f;
+            project3(make_float3(ba.x, ba.y, ba.z), c, p[0], p[1], p[2]);
             const float dx = c.x - bc.y, dy = c.y - bc.z, dz = c.z - bc.w;
             p[3] = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
         }
-        float mn[4], mx[4];
-        const int width = min(span, 32);
+        unsigned mn[4], mx[4];
+#pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const bool ok = live && (p[k] == p[k]);
-            mn[k] = ok ? p[k] : FLT_MAX; mx[k] = ok ? p[k] : -FLT_MAX;
-            for (int o = width / 2; o; o >>= 1) {
-                mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-                mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-            }
+            const unsigned lo = finite ? f2u(p[k]) : 0xffffffffu, hi = finite ? f2u(p[k]) : 0u;
+            mn[k] = __reduce_min_sync(grp, lo);
+            mx[k] = __reduce_max_sync(grp, hi);
         }
-        int *dmin[4] = {(int *)&b->a.w, (int *)&b->b.y, (int *)&b->b.w, (int *)&b->d.x};
-        int *dmax[4] = {(int *)&b->b.x, (int *)&b->b.z, (int *)&b->c.x, (int *)&b->d.y};
-        const int nq = shell ? 4 : 3;
-        if (span < 256) {
-            if ((lane & (width - 1)) == 0)
-                for (int k = 0; k < nq; ++k) if (mn[k] <= mx[k]) { atomicMin(dmin[k], f2ord(mn[k])); atomicMax(dmax[k], f2ord(mx[k])); }
-        } else {
-            __syncthreads();
-            if (lane == 0) for (int k = 0; k < 4; ++k) { smn[k][wid] = mn[k]; smx[k][wid] = mx[k]; }
-            __syncthreads();
-            if (threadIdx.x < nq) {
-                const int k = threadIdx.x;
-                float a = smn[k][0], z = smx[k][0];
-                for (int w = 1; w < 8; ++w) { a = fminf(a, smn[k][w]); z = fmaxf(z, smx[k][w]); }
-                if (a <= z) { atomicMin(dmin[k], f2ord(a)); atomicMax(dmax[k], f2ord(z)); }
-            }
+        if (live && lane == (unsigned)(__ffs(grp) - 1) && mn[0] <= mx[0]) {
+            atomicMin((int *)&b->a.w, u2ord(mn[0])); atomicMax((int *)&b->b.x, u2ord(mx[0]));
+            atomicMin((int *)&b->b.y, u2ord(mn[1])); atomicMax((int *)&b->b.z, u2ord(mx[1]));
+            atomicMin((int *)&b->b.w, u2ord(mn[2])); atomicMax((int *)&b->c.x, u2ord(mx[2]));
+            if (shell) { atomicMin((int *)&b->d.x, u2ord(mn[3])); atomicMax((int *)&b->d.y, u2ord(mx[3])); }
         }
+        if (live) node = par[tl.off[l] + node] & 0x7fffffff;
     }
 }
-// ordered-int -> float for the extents written by k_box_extents
+// ordered-int -> float for the extents written by k_extents
 __global__ void k_box_decode(Box *__restrict__ boxes, int first, int count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -271,27 +319,32 @@ __global__ void k_box_decode(Box *__restrict__ boxes, int first, int count) {
 // In a node's frame (origin = box centre) a spherical cap is z = z0 + s r^2 with s = -1/(2 rho): regress z on r^2.
 // Moments per node: N, sum z, sum r^2, sum z r^2, sum r^4.  (float atomics are fine here: the fit only decides how
 // tight a pruning bound is, never a result.)
-__global__ void __launch_bounds__(256) k_shell_moments(const float4 *__restrict__ cent, int F, const Box *__restrict__ boxes, TreeLevels tl,
+__global__ void __launch_bounds__(256) k_shell_moments(const float4 *__restrict__ cent, int F, const int *__restrict__ leaf_of_slot,
+                                                       const int *__restrict__ par, const Box *__restrict__ boxes, TreeLevels tl,
                                                        float *__restrict__ mom) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < F;
     const float4 c = live ? cent[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int lane = threadIdx.x & 31;
-    int node = i / NW_LEAF;
-    for (int l = 1; l < tl.n_levels; ++l) {
-        node /= NW_FAN;
-        const int nd = min(node, tl.count[l] - 1);
-        const Box *b = &boxes[tl.offset[l] + nd];
-        const float4 ba = b->a, bb = b->b, bc = b->c;
-        float pn, p1, p2;
-        project3(make_float3(ba.x, ba.y, ba.z), c, pn, p1, p2);
-        const float z = pn - 0.5f * (ba.w + bb.x), u = p1 - 0.5f * (bb.y + bb.z), v = p2 - 0.5f * (bb.w + bc.x);
-        const float r2 = u * u + v * v;
-        float m[5] = {live ? 1.f : 0.f, live ? z : 0.f, live ? r2 : 0.f, live ? z * r2 : 0.f, live ? r2 * r2 : 0.f};
-        for (int k = 0; k < 5; ++k)
-            for (int o = 16; o; o >>= 1) m[k] += __shfl_xor_sync(0xffffffffu, m[k], o);   // a warp (32 slots) lies in one node for l >= 1
-        if (lane == 0 && node < tl.count[l])
-            for (int k = 0; k < 5; ++k) atomicAdd(&mom[5 * (size_t)(tl.offset[l] + nd) + k], m[k]);
+    int node = live ? leaf_of_slot[i] : 0;
+    const unsigned lane = threadIdx.x & 31;
+    for (int l = tl.n_levels - 1; l >= 1; --l) {
+        const int key = live ? node : -1 - (int)lane;
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (live) {
+            const Box *b = &boxes[tl.off[l] + node];
+            const float4 ba = b->a, bb = b->b, bc = b->c;
+            float pn, p1, p2;
+            project3(make_float3(ba.x, ba.y, ba.z), c, pn, p1, p2);
+            const float z = pn - 0.5f * (ba.w + bb.x), u = p1 - 0.5f * (bb.y + bb.z), v = p2 - 0.5f * (bb.w + bc.x);
+            const float r2 = u * u + v * v;
+            m[0] = 1.f; m[1] = z; m[2] = r2; m[3] = z * r2; m[4] = r2 * r2;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) m[k] = group_sumf(grp, m[k]);
+        if (live && lane == (unsigned)(__ffs(grp) - 1))
+            for (int k = 0; k < 5; ++k) atomicAdd(&mom[5 * (size_t)(tl.off[l] + node) + k], m[k]);
+        if (live) node = par[tl.off[l] + node] & 0x7fffffff;
     }
 }
 
@@ -302,7 +355,7 @@ __global__ void k_shell_fit(Box *__restrict__ boxes, const float *__restrict__ m
     const float *m = mom + 5 * (size_t)(first + i);
     const double N = m[0], Sz = m[1], Sr = m[2], Szr = m[3], Srr = m[4];
     const double den = N * Srr - Sr * Sr;
-    bool ok = N >= 32.0 && den > 1e-12 * fmax(N * Srr, 1e-300);
+    bool ok = N >= 24.0 && den > 1e-12 * fmax(N * Srr, 1e-300);
     double slope = 0.0, z0 = 0.0, rho = 0.0;
     if (ok) {
         slope = (N * Szr - Sz * Sr) / den;
@@ -408,14 +461,41 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     return nw_tree_build(h);
 }
 
-static int tree_fit_shells(nw_ctx *h);
+static int scan_inclusive(nw_ctx *h, const int *in, int *out, int n) {
+    size_t tmp = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tmp, in, out, n, h->stream);
+    if (tmp > h->cub_tmp_bytes) { NW_CHECK(nw_alloc(h, (char **)&h->cub_tmp, tmp)); h->cub_tmp_bytes = tmp; }
+    NW_CUDA(cub::DeviceScan::InclusiveSum(h->cub_tmp, tmp, in, out, n, h->stream));
+    h->launches += 2;
+    return NW_OK;
+}
+
+static int extents_pass(nw_ctx *h) {
+    cudaStream_t s = h->stream;
+    const int B = 256;
+    const TreeLevels &tl = h->tl;
+    const int first = tl.off[1], count = tl.off[tl.n_levels - 1] + tl.count[tl.n_levels - 1] - first;
+    k_reset_extents<<<nw_grid(count, B), B, 0, s>>>(h->boxes, first, count);
+    NW_LAUNCH_CHECK();
+    k_extents<<<nw_grid(h->F, B), B, 0, s>>>(h->cent, h->F, h->leaf_of_slot, h->par, h->boxes, tl);
+    NW_LAUNCH_CHECK();
+    k_box_decode<<<nw_grid(count, B), B, 0, s>>>(h->boxes, first, count);
+    NW_LAUNCH_CHECK();
+    return NW_OK;
+}
+
+int nw_tree_refit(nw_ctx *h) {
+    k_refit_centroids<<<nw_grid(h->F, 256), 256, 0, h->stream>>>(h->sfaces, h->posq, h->F, h->cent);
+    NW_LAUNCH_CHECK();
+    return extents_pass(h);
+}
 
 int nw_tree_build(nw_ctx *h) {
     cudaStream_t s = h->stream;
     const int B = 256, F = h->F;
     int *d_bbox = nullptr, *idx = nullptr, *order = nullptr;
     unsigned *keys = nullptr, *keys2 = nullptr;
-    NW_CHECK(nw_alloc(h, &d_bbox, 6));
+    NW_CHECK(nw_alloc(h, &d_bbox, 16));
     int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
     NW_CUDA(cudaMemcpyAsync(d_bbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
     k_face_bbox<<<std::min(nw_grid(F, B), 148 * 4), B, 0, s>>>(h->faces, h->posq, F, d_bbox);
@@ -426,7 +506,6 @@ int nw_tree_build(nw_ctx *h) {
     for (int a = 0; a < 3; ++a) { lo[a] = ordered_to_float(bb[a]); hi[a] = ordered_to_float(bb[3 + a]); }
     float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     float inv = (ext > 0.f && ext < FLT_MAX) ? 1023.f / ext : 0.f;
-
     NW_CHECK(nw_alloc(h, &keys, (size_t)F)); NW_CHECK(nw_alloc(h, &keys2, (size_t)F));
     NW_CHECK(nw_alloc(h, &idx, (size_t)F)); NW_CHECK(nw_alloc(h, &order, (size_t)F));
     k_face_keys<<<nw_grid(F, B), B, 0, s>>>(h->faces, h->posq, F, make_float3(lo[0], lo[1], lo[2]), inv, keys, idx);
@@ -439,65 +518,70 @@ int nw_tree_build(nw_ctx *h) {
     h->key_lo[0] = lo[0]; h->key_lo[1] = lo[1]; h->key_lo[2] = lo[2]; h->key_inv = inv;
     k_sorted_faces<<<nw_grid(F, B), B, 0, s>>>(h->faces, order, F, h->sfaces);
     h->launches += 7;
-    // level sizes
+
+    // ---- level sizes: nodes of level k = distinct 3k-bit key prefixes; leaf level = deepest with >= 4 centroids per node
+    int *hist = d_bbox;                                   // 16 ints
+    NW_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * 16, s));
+    k_level_histogram<<<nw_grid(F, B), B, 0, s>>>(h->fkeys, F, hist);
+    int hh[16];
+    NW_CUDA(cudaMemcpyAsync(hh, hist, sizeof(hh), cudaMemcpyDeviceToHost, s));
+    NW_CUDA(cudaStreamSynchronize(s));
+    int cnt[11];
+    cnt[0] = 1;
+    for (int k = 1; k <= 10; ++k) cnt[k] = cnt[k - 1] + hh[k];
+    int kL = 1;
+    for (int k = 1; k <= 10; ++k) if ((double)F / cnt[k] >= 4.0) kL = k;
     TreeLevels &tl = h->tl;
-    tl.n_levels = 0;
-    int n = (F + NW_LEAF - 1) / NW_LEAF, off = 0;
-    while (true) {
-        NW_ARG(tl.n_levels < NW_MAX_LEVELS, "nw_tree_build: too many levels");
-        tl.count[tl.n_levels] = n; tl.offset[tl.n_levels] = off; tl.n_levels++;
-        off += n;
-        if (n <= NW_FAN) break;
-        n = (n + NW_FAN - 1) / NW_FAN;
+    tl.n_levels = kL + 1;
+    int off = 0, cb = 0;
+    for (int k = 0; k <= kL; ++k) {
+        tl.count[k] = cnt[k]; tl.off[k] = off; tl.cb_off[k] = cb;
+        off += cnt[k]; cb += cnt[k] + 1;
     }
-    NW_CHECK(nw_alloc(h, &h->boxes, (size_t)off));
+    const int total = off;
+    NW_CHECK(nw_alloc(h, &h->boxes, (size_t)total)); NW_CHECK(nw_alloc(h, &h->par, (size_t)total));
+    NW_CHECK(nw_alloc(h, &h->cbegin, (size_t)cb)); NW_CHECK(nw_alloc(h, &h->leaf_of_slot, (size_t)F));
+    NW_CHECK(nw_alloc(h, &h->node_f, (size_t)5 * total));
+    // ---- per-level tables
+    int *flag = idx, *id_cur = order, *id_prev = (int *)keys, *start = (int *)keys2;     // reuse the sort buffers (F ints each)
+    for (int k = 0; k <= kL; ++k) {
+        k_level_flags<<<nw_grid(F, B), B, 0, s>>>(h->fkeys, F, 30 - 3 * k, flag);
+        NW_LAUNCH_CHECK();
+        NW_CHECK(scan_inclusive(h, flag, id_cur, F));
+        k_level_tables<<<nw_grid(F, B), B, 0, s>>>(flag, id_cur, k ? id_prev : nullptr, F, start, h->par + tl.off[k],
+                                                   k ? h->cbegin + tl.cb_off[k - 1] : nullptr);
+        NW_LAUNCH_CHECK();
+        if (k) NW_CUDA(cudaMemcpyAsync(h->cbegin + tl.cb_off[k - 1] + tl.count[k - 1], &tl.count[k], sizeof(int), cudaMemcpyHostToDevice, s));
+        if (k == kL) {
+            NW_CUDA(cudaMemcpyAsync(h->cbegin + tl.cb_off[k], start, sizeof(int) * tl.count[k], cudaMemcpyDeviceToDevice, s));
+            NW_CUDA(cudaMemcpyAsync(h->cbegin + tl.cb_off[k] + tl.count[k], &h->F, sizeof(int), cudaMemcpyHostToDevice, s));
+            k_copy_minus1<<<nw_grid(F, B), B, 0, s>>>(id_cur, F, h->leaf_of_slot);
+            NW_LAUNCH_CHECK();
+        }
+        k_mark_last_child<<<nw_grid(tl.count[k], B), B, 0, s>>>(h->par + tl.off[k], tl.count[k]);
+        NW_LAUNCH_CHECK();
+        std::swap(id_cur, id_prev);
+    }
     NW_CUDA(cudaStreamSynchronize(s));
     nw_free(&d_bbox); nw_free(&idx); nw_free(&order); nw_free(&keys); nw_free(&keys2);
-    return tree_fit_shells(h);
-}
 
-static int tree_refit_impl(nw_ctx *h, int init) {
-    cudaStream_t s = h->stream;
-    const int B = 256;
-    const TreeLevels &tl = h->tl;
-    k_refit_leaves<<<nw_grid(h->F, B), B, 0, s>>>(h->sfaces, h->posq, h->F, h->cent, h->boxes);
+    // ---- frames (fixed for the block), first extents, sphere fits, extents again (now with the shell radii)
+    k_refit_centroids<<<nw_grid(F, B), B, 0, s>>>(h->sfaces, h->posq, F, h->cent);
     NW_LAUNCH_CHECK();
-    for (int l = 1; l < tl.n_levels; ++l) {
-        k_refit_level<<<nw_grid(tl.count[l], B), B, 0, s>>>(h->boxes + tl.offset[l - 1], tl.count[l - 1],
-                                                             h->boxes + tl.offset[l], tl.count[l], init);
+    NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * 5 * total, s));
+    if (kL >= 1) {
+        k_node_normals<<<nw_grid(F, B), B, 0, s>>>(h->sfaces, h->posq, F, h->leaf_of_slot, h->par, tl, h->node_f);
         NW_LAUNCH_CHECK();
     }
-    if (tl.n_levels > 1) {
-        k_box_extents<<<nw_grid(h->F, B), B, 0, s>>>(h->cent, h->F, h->boxes, tl);
-        NW_LAUNCH_CHECK();
-        const int first = tl.offset[1], count = tl.offset[tl.n_levels - 1] + tl.count[tl.n_levels - 1] - tl.offset[1];
-        k_box_decode<<<nw_grid(count, B), B, 0, s>>>(h->boxes, first, count);
-        NW_LAUNCH_CHECK();
-    }
-    return NW_OK;
-}
-
-int nw_tree_refit(nw_ctx *h) { return tree_refit_impl(h, 0); }
-
-// once per topology upload: boxes without shells, then the sphere fits, then the first regular refit measures the shells
-static int tree_fit_shells(nw_ctx *h) {
-    cudaStream_t s = h->stream;
-    const int B = 256;
-    const TreeLevels &tl = h->tl;
-    NW_CHECK(tree_refit_impl(h, 1));
-    if (tl.n_levels > 1) {
-        const int total = tl.offset[tl.n_levels - 1] + tl.count[tl.n_levels - 1];
-        float *mom = nullptr;
-        NW_CHECK(nw_alloc(h, &h->shell_mom, (size_t)5 * total));
-        mom = h->shell_mom;
-        NW_CUDA(cudaMemsetAsync(mom, 0, sizeof(float) * 5 * total, s));
-        k_shell_moments<<<nw_grid(h->F, B), B, 0, s>>>(h->cent, h->F, h->boxes, tl, mom);
-        NW_LAUNCH_CHECK();
-        const int first = tl.offset[1], count = total - first;
-        k_shell_fit<<<nw_grid(count, B), B, 0, s>>>(h->boxes, mom, first, count);
-        NW_LAUNCH_CHECK();
-    }
-    return tree_refit_impl(h, 0);
+    k_node_frames<<<nw_grid(total, B), B, 0, s>>>(h->boxes, h->node_f, 0, total);
+    NW_LAUNCH_CHECK();
+    NW_CHECK(extents_pass(h));
+    NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * 5 * total, s));
+    k_shell_moments<<<nw_grid(F, B), B, 0, s>>>(h->cent, F, h->leaf_of_slot, h->par, h->boxes, tl, h->node_f);
+    NW_LAUNCH_CHECK();
+    k_shell_fit<<<nw_grid(total - tl.off[1], B), B, 0, s>>>(h->boxes, h->node_f, tl.off[1], total - tl.off[1]);
+    NW_LAUNCH_CHECK();
+    return extents_pass(h);
 }
 
 extern "C" int nw_set_positions(nw_ctx *h, const float *pos) {

@@ -9,7 +9,7 @@ cg.search(pts, lams=[5.0], num_iters=6, sigma_inv=s_inv)
 counts=(ctypes.c_int*32)(); nl=ctypes.c_int()
 cg._h.call('nw_debug_tree', -1, None, counts, ctypes.byref(nl))
 print('levels', nl.value, list(counts)[:nl.value])
-for lvl in range(nl.value-1, max(nl.value-5,0), -1):
+for lvl in range(1, min(nl.value,5)):
     n=counts[lvl]; b=np.zeros((n,16),np.float32)
     cg._h.call('nw_debug_tree', lvl, b.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), None, None)
     print('level', lvl)
