@@ -79,7 +79,7 @@ struct Nearest {
 // so skipping can never change the answer.
 template <typename Q>
 __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps) {
-    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c), d = __ldg(&bp->d);
+    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
     const float x = q.fx(), y = q.fy(), z = q.fz();
     const float3 t1 = nw_tangent_of(a.x, a.y, a.z);
     const float t2x = a.y * t1.z - a.z * t1.y, t2y = a.z * t1.x - a.x * t1.z, t2z = a.x * t1.y - a.y * t1.x;
@@ -90,10 +90,13 @@ __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp,
     const float g1 = fmaxf(fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f) - eps, 0.f);
     const float g2 = fmaxf(fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f) - eps, 0.f);
     float lb = __fadd_rd(__fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1)), __fmul_rd(g2, g2));
+#if NW_SHELL
+    const float4 d = __ldg(&bp->d);
     const float dx = x - c.y, dy = y - c.z, dz = z - c.w;
     const float r = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
     const float gs = fmaxf(fmaxf(d.x - r, r - d.y), 0.f) - fmaf(r, 4e-6f, eps);
     if (gs > 0.f) lb = fmaxf(lb, __fmul_rd(gs, gs));
+#endif
     return __fmul_rd(lb, 0.99999f);
 }
 

@@ -316,9 +316,10 @@ __global__ void k_box_decode(Box *__restrict__ boxes, int first, int count) {
 }
 
 // ---- spherical-shell fit, once per topology upload ---------------------------------------------------------------------
-// In a node's frame (origin = box centre) a spherical cap is z = z0 + s r^2 with s = -1/(2 rho): regress z on r^2.
-// Moments per node: N, sum z, sum r^2, sum z r^2, sum r^4.  (float atomics are fine here: the fit only decides how
-// tight a pruning bound is, never a result.)
+// Algebraic sphere fit in the node's frame (origin = box centre, coordinates u,v,z):  u^2+v^2+z^2 + A u + B v + C z + E = 0
+// is linear in (A,B,C,E); the 14 moments of its normal equations are summed per node.  (Float atomics are fine here: the
+// fit only decides how tight a pruning bound is, never a result.)
+#define NW_NMOM 14
 __global__ void __launch_bounds__(256) k_shell_moments(const float4 *__restrict__ cent, int F, const int *__restrict__ leaf_of_slot,
                                                        const int *__restrict__ par, const Box *__restrict__ boxes, TreeLevels tl,
                                                        float *__restrict__ mom) {
@@ -330,20 +331,23 @@ __global__ void __launch_bounds__(256) k_shell_moments(const float4 *__restrict_
     for (int l = tl.n_levels - 1; l >= 1; --l) {
         const int key = live ? node : -1 - (int)lane;
         const unsigned grp = __match_any_sync(0xffffffffu, key);
-        float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        float m[NW_NMOM];
+#pragma unroll
+        for (int k = 0; k < NW_NMOM; ++k) m[k] = 0.f;
         if (live) {
             const Box *b = &boxes[tl.off[l] + node];
             const float4 ba = b->a, bb = b->b, bc = b->c;
             float pn, p1, p2;
             project3(make_float3(ba.x, ba.y, ba.z), c, pn, p1, p2);
             const float z = pn - 0.5f * (ba.w + bb.x), u = p1 - 0.5f * (bb.y + bb.z), v = p2 - 0.5f * (bb.w + bc.x);
-            const float r2 = u * u + v * v;
-            m[0] = 1.f; m[1] = z; m[2] = r2; m[3] = z * r2; m[4] = r2 * r2;
+            const float w = -(u * u + v * v + z * z);
+            m[0] = 1.f; m[1] = u; m[2] = v; m[3] = z; m[4] = u * u; m[5] = u * v; m[6] = u * z; m[7] = v * v; m[8] = v * z;
+            m[9] = z * z; m[10] = w; m[11] = w * u; m[12] = w * v; m[13] = w * z;
         }
 #pragma unroll
-        for (int k = 0; k < 5; ++k) m[k] = group_sumf(grp, m[k]);
+        for (int k = 0; k < NW_NMOM; ++k) m[k] = group_sumf(grp, m[k]);      // all lanes, always: full-mask shuffles inside
         if (live && lane == (unsigned)(__ffs(grp) - 1))
-            for (int k = 0; k < 5; ++k) atomicAdd(&mom[5 * (size_t)(tl.off[l] + node) + k], m[k]);
+            for (int k = 0; k < NW_NMOM; ++k) atomicAdd(&mom[NW_NMOM * (size_t)(tl.off[l] + node) + k], m[k]);
         if (live) node = par[tl.off[l] + node] & 0x7fffffff;
     }
 }
@@ -352,23 +356,36 @@ __global__ void k_shell_fit(Box *__restrict__ boxes, const float *__restrict__ m
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     Box *b = &boxes[first + i];
-    const float *m = mom + 5 * (size_t)(first + i);
-    const double N = m[0], Sz = m[1], Sr = m[2], Szr = m[3], Srr = m[4];
-    const double den = N * Srr - Sr * Sr;
-    bool ok = N >= 24.0 && den > 1e-12 * fmax(N * Srr, 1e-300);
-    double slope = 0.0, z0 = 0.0, rho = 0.0;
-    if (ok) {
-        slope = (N * Szr - Sz * Sr) / den;
-        z0 = (Sz - slope * Sr) / N;
-        ok = fabs(slope) > 2.5e-5;                   // |rho| = 1/(2|slope|) <= 2e4: beyond that the cap is a plane for our purposes
-        if (ok) rho = -1.0 / (2.0 * slope);
+    const float *m = mom + NW_NMOM * (size_t)(first + i);
+    b->d = make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f);
+    const double N = m[0];
+    if (!(N >= 24.0)) return;
+    // normal equations  M x = r  for x = (A, B, C, E), columns (u, v, z, 1)
+    double M[4][5] = {{m[4], m[5], m[6], m[1], m[11]}, {m[5], m[7], m[8], m[2], m[12]}, {m[6], m[8], m[9], m[3], m[13]}, {m[1], m[2], m[3], N, m[10]}};
+    for (int k = 0; k < 4; ++k) {
+        int piv = k;
+        for (int r = k + 1; r < 4; ++r) if (fabs(M[r][k]) > fabs(M[piv][k])) piv = r;
+        if (!(fabs(M[piv][k]) > 1e-9 * fmax(fabs(M[k][k]) + fabs(M[3][3]), 1e-300))) return;      // (near-)planar or degenerate patch
+        if (piv != k) for (int c = 0; c < 5; ++c) { const double t = M[k][c]; M[k][c] = M[piv][c]; M[piv][c] = t; }
+        for (int r = k + 1; r < 4; ++r) {
+            const double f = M[r][k] / M[k][k];
+            for (int c = k; c < 5; ++c) M[r][c] -= f * M[k][c];
+        }
     }
-    if (!ok || !(fabs(rho) <= 2e4)) { b->d = make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f); return; }
+    double x[4];
+    for (int r = 3; r >= 0; --r) {
+        double t = M[r][4];
+        for (int c = r + 1; c < 4; ++c) t -= M[r][c] * x[c];
+        x[r] = t / M[r][r];
+    }
+    const double cu = -0.5 * x[0], cv = -0.5 * x[1], cz = -0.5 * x[2];
+    const double rho2 = cu * cu + cv * cv + cz * cz - x[3];
+    if (!(rho2 > 0.0) || !(rho2 <= 4e8)) return;                  // radius above 2e4: a plane for our purposes
     const float4 ba = b->a, bb = b->b, bc = b->c;
     const float3 n = make_float3(ba.x, ba.y, ba.z);
     const float3 t1 = nw_tangent_of(n.x, n.y, n.z);
     const float3 t2 = make_float3(n.y * t1.z - n.z * t1.y, n.z * t1.x - n.x * t1.z, n.x * t1.y - n.y * t1.x);
-    const double cn = 0.5 * ((double)ba.w + bb.x) + z0 - rho, c1 = 0.5 * ((double)bb.y + bb.z), c2 = 0.5 * ((double)bb.w + bc.x);
+    const double cn = 0.5 * ((double)ba.w + bb.x) + cz, c1 = 0.5 * ((double)bb.y + bb.z) + cu, c2 = 0.5 * ((double)bb.w + bc.x) + cv;
     b->c.y = (float)(cn * n.x + c1 * t1.x + c2 * t2.x);
     b->c.z = (float)(cn * n.y + c1 * t1.y + c2 * t2.y);
     b->c.w = (float)(cn * n.z + c1 * t1.z + c2 * t2.z);
@@ -541,7 +558,7 @@ int nw_tree_build(nw_ctx *h) {
     const int total = off;
     NW_CHECK(nw_alloc(h, &h->boxes, (size_t)total)); NW_CHECK(nw_alloc(h, &h->par, (size_t)total));
     NW_CHECK(nw_alloc(h, &h->cbegin, (size_t)cb)); NW_CHECK(nw_alloc(h, &h->leaf_of_slot, (size_t)F));
-    NW_CHECK(nw_alloc(h, &h->node_f, (size_t)5 * total));
+    NW_CHECK(nw_alloc(h, &h->node_f, (size_t)NW_NMOM * total));
     // ---- per-level tables
     int *flag = idx, *id_cur = order, *id_prev = (int *)keys, *start = (int *)keys2;     // reuse the sort buffers (F ints each)
     for (int k = 0; k <= kL; ++k) {
@@ -568,19 +585,21 @@ int nw_tree_build(nw_ctx *h) {
     // ---- frames (fixed for the block), first extents, sphere fits, extents again (now with the shell radii)
     k_refit_centroids<<<nw_grid(F, B), B, 0, s>>>(h->sfaces, h->posq, F, h->cent);
     NW_LAUNCH_CHECK();
-    NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * 5 * total, s));
+    NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * NW_NMOM * total, s));
     if (kL >= 1) {
         k_node_normals<<<nw_grid(F, B), B, 0, s>>>(h->sfaces, h->posq, F, h->leaf_of_slot, h->par, tl, h->node_f);
         NW_LAUNCH_CHECK();
     }
     k_node_frames<<<nw_grid(total, B), B, 0, s>>>(h->boxes, h->node_f, 0, total);
     NW_LAUNCH_CHECK();
+#if NW_SHELL
     NW_CHECK(extents_pass(h));
-    NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * 5 * total, s));
+    NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * NW_NMOM * total, s));
     k_shell_moments<<<nw_grid(F, B), B, 0, s>>>(h->cent, F, h->leaf_of_slot, h->par, h->boxes, tl, h->node_f);
     NW_LAUNCH_CHECK();
     k_shell_fit<<<nw_grid(total - tl.off[1], B), B, 0, s>>>(h->boxes, h->node_f, tl.off[1], total - tl.off[1]);
     NW_LAUNCH_CHECK();
+#endif
     return extents_pass(h);
 }
 
