@@ -105,8 +105,8 @@ static int stage_end(nw_ctx *h, int stage) {
 
 // one full iteration, enqueued asynchronously
 static int enqueue_iteration(nw_ctx *h, int it, int last_step) {
+    NW_STAGE(1, nw_set_acc_shifts(h));             // vertex bbox -> fixed-point scales, rounding slack of the box tests
     NW_STAGE(0, nw_tree_refit(h));                 // centroids + boxes at the current f  (:443)
-    NW_STAGE(1, nw_set_acc_shifts(h));
     if (h->seeds_cold) NW_STAGE(8, nw_launch_seed_leaders(h));   // first iteration after a topology upload only
     NW_STAGE(2, nw_launch_sweep1(h, true));        // NN, weights, A f, residual, AH res, AH 1  (:222-253)
     if (h->nranks > 1) NW_STAGE(3, nw_allreduce_acc(h));   // N>1: vertex-gradient allreduce

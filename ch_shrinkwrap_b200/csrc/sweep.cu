@@ -81,14 +81,24 @@ template <typename Q>
 __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps) {
     const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
     const float x = q.fx(), y = q.fy(), z = q.fz();
+#if NW_SHELL
     const float3 t1 = nw_tangent_of(a.x, a.y, a.z);
+#else
+    const float4 d4 = __ldg(&bp->d);                 // without the shell the fourth quarter of the node stores t1
+    const float3 t1 = make_float3(d4.x, d4.y, d4.z);
+#endif
+#if NW_SHELL
     const float t2x = a.y * t1.z - a.z * t1.y, t2y = a.z * t1.x - a.x * t1.z, t2z = a.x * t1.y - a.y * t1.x;
+#else
+    const float t2x = c.y, t2y = c.z, t2z = c.w;     // ... and the shell-centre slot stores t2 = n x t1
+#endif
     const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
     const float p1 = fmaf(t1.x, x, fmaf(t1.y, y, t1.z * z));
     const float p2 = fmaf(t2x, x, fmaf(t2y, y, t2z * z));
-    const float g0 = fmaxf(fmaxf(fmaxf(a.w - pn, pn - b.x), 0.f) - eps, 0.f);
-    const float g1 = fmaxf(fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f) - eps, 0.f);
-    const float g2 = fmaxf(fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f) - eps, 0.f);
+    // the stored intervals are already widened by the rounding slack (k_box_decode)
+    const float g0 = fmaxf(fmaxf(a.w - pn, pn - b.x), 0.f);
+    const float g1 = fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f);
+    const float g2 = fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f);
     float lb = __fadd_rd(__fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1)), __fmul_rd(g2, g2));
 #if NW_SHELL
     const float4 d = __ldg(&bp->d);
@@ -800,8 +810,8 @@ extern "C" int nw_compute_weights(nw_ctx *h) {
         for (int a = 0; a < 3; ++a) { z.bbox[a] = 0x7fffffff; z.bbox[3 + a] = (int)0x80000000; }
         NW_CUDA(cudaMemcpyAsync(h->st, &z, sizeof(SolverState), cudaMemcpyHostToDevice, h->stream));
     }
+    NW_CHECK(nw_set_acc_shifts(h));             // first: it refreshes the coordinate bound the refit folds into the boxes
     NW_CHECK(nw_tree_refit(h));
-    NW_CHECK(nw_set_acc_shifts(h));             // also refreshes the coordinate bound used by the box tests
     NW_CHECK(nw_launch_sweep1(h, false));
     NW_CUDA(cudaStreamSynchronize(h->stream));
     h->weights_valid = true;

@@ -7,6 +7,7 @@
 // children, so the hierarchy is implicit (no child pointers) and a node's children are one 128 B line.
 #include <cub/cub.cuh>
 #include <cfloat>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -253,7 +254,14 @@ __global__ void k_node_frames(Box *__restrict__ boxes, const float *__restrict__
     b->a = make_float4(n.x, n.y, n.z, NW_EMPTY_LO);
     b->b = make_float4(NW_EMPTY_HI, NW_EMPTY_LO, NW_EMPTY_HI, NW_EMPTY_LO);
     b->c = make_float4(NW_EMPTY_HI, 0.f, 0.f, 0.f);
+#if NW_SHELL
     b->d = make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f);
+#else
+    const float3 t1 = nw_tangent_of(n.x, n.y, n.z);
+    b->c.y = n.y * t1.z - n.z * t1.y; b->c.z = n.z * t1.x - n.x * t1.z; b->c.w = n.x * t1.y - n.y * t1.x;   // t2, exactly as project3 forms it
+    b->d = make_float4(t1.x, t1.y, t1.z, 0.f);       // d.z doubles as the "shell enabled" flag elsewhere: |t1.z| <= 1, and those
+                                                     // code paths are compiled out without the shell
+#endif
 }
 
 // every iteration: intervals back to "empty" (frames and shell centres are kept for the whole block)
@@ -262,7 +270,9 @@ __global__ void k_reset_extents(Box *__restrict__ boxes, int first, int count) {
     if (j >= count) return;
     Box *b = &boxes[first + j];
     b->a.w = NW_EMPTY_LO; b->b.x = NW_EMPTY_HI; b->b.y = NW_EMPTY_LO; b->b.z = NW_EMPTY_HI; b->b.w = NW_EMPTY_LO; b->c.x = NW_EMPTY_HI;
+#if NW_SHELL
     if (b->d.z > 0.5f) { b->d.x = NW_EMPTY_LO; b->d.y = NW_EMPTY_HI; }
+#endif
 }
 
 // every iteration: each centroid projects onto the frame (and shell centre) of every ancestor; lanes of a warp that
@@ -283,7 +293,9 @@ __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent
         bool shell = false;
         if (live) {
             const float4 ba = b->a, bc = b->c;
+#if NW_SHELL
             shell = b->d.z > 0.5f;
+#endif
             project3(make_float3(ba.x, ba.y, ba.z), c, p[0], p[1], p[2]);
             const float dx = c.x - bc.y, dy = c.y - bc.z, dz = c.z - bc.w;
             p[3] = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
@@ -304,15 +316,20 @@ __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent
         if (live) node = par[tl.off[l] + node] & 0x7fffffff;
     }
 }
-// ordered-int -> float for the extents written by k_extents
-__global__ void k_box_decode(Box *__restrict__ boxes, int first, int count) {
+// ordered-int -> float for the extents written by k_extents.  The intervals are widened by the rounding slack of the
+// box test (2^-19 x the coordinate bound: >= 4x the worst-case error of the query's and the members' float32
+// projections, see node_lb), so the test itself needs no per-axis subtraction.
+__global__ void k_box_decode(Box *__restrict__ boxes, int first, int count, const SolverState *__restrict__ st) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
+    const float w = st->coord_l1 * 1.9073486328125e-6f;
     Box *b = &boxes[first + i];
-    b->a.w = ord2f(__float_as_int(b->a.w)); b->b.x = ord2f(__float_as_int(b->b.x));
-    b->b.y = ord2f(__float_as_int(b->b.y)); b->b.z = ord2f(__float_as_int(b->b.z));
-    b->b.w = ord2f(__float_as_int(b->b.w)); b->c.x = ord2f(__float_as_int(b->c.x));
+    b->a.w = ord2f(__float_as_int(b->a.w)) - w; b->b.x = ord2f(__float_as_int(b->b.x)) + w;
+    b->b.y = ord2f(__float_as_int(b->b.y)) - w; b->b.z = ord2f(__float_as_int(b->b.z)) + w;
+    b->b.w = ord2f(__float_as_int(b->b.w)) - w; b->c.x = ord2f(__float_as_int(b->c.x)) + w;
+#if NW_SHELL
     if (b->d.z > 0.5f) { b->d.x = ord2f(__float_as_int(b->d.x)); b->d.y = ord2f(__float_as_int(b->d.y)); }
+#endif
 }
 
 // ---- spherical-shell fit, once per topology upload ---------------------------------------------------------------------
@@ -496,7 +513,7 @@ static int extents_pass(nw_ctx *h) {
     NW_LAUNCH_CHECK();
     k_extents<<<nw_grid(h->F, B), B, 0, s>>>(h->cent, h->F, h->leaf_of_slot, h->par, h->boxes, tl);
     NW_LAUNCH_CHECK();
-    k_box_decode<<<nw_grid(count, B), B, 0, s>>>(h->boxes, first, count);
+    k_box_decode<<<nw_grid(count, B), B, 0, s>>>(h->boxes, first, count, h->st);
     NW_LAUNCH_CHECK();
     return NW_OK;
 }
@@ -547,7 +564,9 @@ int nw_tree_build(nw_ctx *h) {
     cnt[0] = 1;
     for (int k = 1; k <= 10; ++k) cnt[k] = cnt[k - 1] + hh[k];
     int kL = 1;
-    for (int k = 1; k <= 10; ++k) if ((double)F / cnt[k] >= 4.0) kL = k;
+    double occ = 1.5;                                     // mean centroids per leaf cell, at least (measured at C3: 1.5 -> 3.5 ms, 4 -> 3.8 ms, 1 -> 3.6 ms)
+    if (const char *e = getenv("NW_LEAF_OCC")) occ = atof(e);
+    for (int k = 1; k <= 10; ++k) if ((double)F / cnt[k] >= occ) kL = k;
     TreeLevels &tl = h->tl;
     tl.n_levels = kL + 1;
     int off = 0, cb = 0;
