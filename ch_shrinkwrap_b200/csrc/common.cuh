@@ -107,6 +107,8 @@ struct nw_ctx {
     int *valence = nullptr;
     uint8_t *valid = nullptr;
     int *stage_nbr = nullptr, *stage_hev = nullptr;   // upload staging (reused across blocks)
+    int *tb_small = nullptr, *tb_i0 = nullptr, *tb_i1 = nullptr;   // tree-build temporaries (reused across blocks)
+    unsigned *tb_u0 = nullptr, *tb_u1 = nullptr;
     // ---- Morton AABB pyramid over face centroids ----
     int4 *sfaces = nullptr;                      // per sorted slot: corner ids + face id
     float4 *cent = nullptr;                      // per sorted slot: centroid xyz + face id bits

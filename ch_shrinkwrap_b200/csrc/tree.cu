@@ -527,8 +527,9 @@ int nw_tree_refit(nw_ctx *h) {
 int nw_tree_build(nw_ctx *h) {
     cudaStream_t s = h->stream;
     const int B = 256, F = h->F;
-    int *d_bbox = nullptr, *idx = nullptr, *order = nullptr;
-    unsigned *keys = nullptr, *keys2 = nullptr;
+    // build temporaries are members: reused from block to block (cudaFree synchronises and is slow)
+    int *&d_bbox = h->tb_small, *&idx = h->tb_i0, *&order = h->tb_i1;
+    unsigned *&keys = h->tb_u0, *&keys2 = h->tb_u1;
     NW_CHECK(nw_alloc(h, &d_bbox, 16));
     int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
     NW_CUDA(cudaMemcpyAsync(d_bbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
@@ -598,9 +599,6 @@ int nw_tree_build(nw_ctx *h) {
         NW_LAUNCH_CHECK();
         std::swap(id_cur, id_prev);
     }
-    NW_CUDA(cudaStreamSynchronize(s));
-    nw_free(&d_bbox); nw_free(&idx); nw_free(&order); nw_free(&keys); nw_free(&keys2);
-
     // ---- frames (fixed for the block), first extents, sphere fits, extents again (now with the shell radii)
     k_refit_centroids<<<nw_grid(F, B), B, 0, s>>>(h->sfaces, h->posq, F, h->cent);
     NW_LAUNCH_CHECK();
