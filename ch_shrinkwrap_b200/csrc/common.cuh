@@ -11,12 +11,6 @@
 #define NW_SHELL 0       // 1: node bound = oriented box AND spherical shell; 0: oriented box only.
                          // Measured at C3: the shell removes only ~4 % of the node tests but makes each test ~15 % dearer -> off.
 #endif
-#ifndef NW_LEAF
-#define NW_LEAF 8        // sorted centroids per leaf of the Hilbert-sorted box pyramid
-#endif
-#ifndef NW_FAN
-#define NW_FAN 4         // children per interior node
-#endif
 #define NW_MAX_LEVELS 12
 #define NW_MAX_ITERS 4096
 #define NW_N_STAGES 9    // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders
@@ -109,7 +103,7 @@ struct nw_ctx {
     int *stage_nbr = nullptr, *stage_hev = nullptr;   // upload staging (reused across blocks)
     int *tb_small = nullptr, *tb_i0 = nullptr, *tb_i1 = nullptr;   // tree-build temporaries (reused across blocks)
     unsigned *tb_u0 = nullptr, *tb_u1 = nullptr;
-    // ---- Morton AABB pyramid over face centroids ----
+    // ---- search hierarchy over the face centroids (tree.cu) ----
     int4 *sfaces = nullptr;                      // per sorted slot: corner ids + face id
     float4 *cent = nullptr;                      // per sorted slot: centroid xyz + face id bits
     Box *boxes = nullptr;

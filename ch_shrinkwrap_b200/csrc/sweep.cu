@@ -1,6 +1,6 @@
 // sweep.cu -- the per-point kernels of the hot loop.
 //
-//   k_sweep1 : exact nearest face centroid (fp64 compare, Morton AABB pyramid) -> inverse-distance
+//   k_sweep1 : exact nearest face centroid (fp64 compare, octree of Hilbert cells) -> inverse-distance
 //              weights -> A f -> weighted, distance-de-weighted residual -> deterministic adjoint
 //              scatter of AH res and AH 1            (mesh_conj_grad.py:222-253, 433-516, 518-588)
 //   k_sweep2 : A applied to all search directions at once + Gram sums Hc, Gc, c0 in fp64, without

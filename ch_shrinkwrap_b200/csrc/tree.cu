@@ -1,10 +1,10 @@
-// tree.cu -- mesh upload and the Morton-sorted AABB pyramid over face centroids.
+// tree.cu -- mesh upload and the nearest-face search hierarchy over the face centroids.
 //
 // The reference finds each point's nearest face centroid with a host kd-tree rebuilt every iteration
-// (mesh_conj_grad.py:443-454).  Here the faces are Morton-sorted ONCE per remesh block (topology is
-// fixed inside a block); every iteration only re-evaluates the centroids at the current f and refits
-// the boxes: leaves are NW_LEAF consecutive sorted centroids, interior nodes are NW_FAN consecutive
-// children, so the hierarchy is implicit (no child pointers) and a node's children are one 128 B line.
+// (mesh_conj_grad.py:443-454).  Here the faces are sorted ONCE per remesh block by the 3-D Hilbert key of
+// their centroid (topology is fixed inside a block) and the hierarchy is the octree of occupied Hilbert cells
+// (see the block comment further down); every iteration only re-evaluates the centroids at the current f and
+// re-measures each node's oriented box.
 #include <cub/cub.cuh>
 #include <cfloat>
 #include <cstdlib>

@@ -8,7 +8,7 @@ def launches(path):
     for r in rows[1:]:
         try: v=float(r[vi].replace(',',''))
         except ValueError: continue
-        name=re.sub(r'\(.*','',r[ki]); name=re.sub(r'.*::','',name)
+        name=re.sub(r'\(.*','',r[ki]); name=re.sub(r'.*::','',name).replace(', ','_').replace(',','_')
         agg[name][0]+=1; agg[name][1]+=v
     tot=sum(v[1] for v in agg.values())
     out=['kernel,launches,total_ns,share']
@@ -30,7 +30,7 @@ def full(path):
     ki=hdr.index('Kernel Name')
     out=['kernel,'+','.join('%s[%s]'%(w,units[i]) for w,i in idx)]
     for r in rows[2:]:
-        name=re.sub(r'\(.*','',r[ki]); name=re.sub(r'.*::','',name)
+        name=re.sub(r'\(.*','',r[ki]); name=re.sub(r'.*::','',name).replace(', ','_').replace(',','_')
         out.append(name+','+','.join(r[i].replace(',','') for w,i in idx))
     return '\n'.join(out)
 
