@@ -244,3 +244,25 @@ def test_ring_regularisers_bitwise():
     assert np.array_equal(g.Lfunc3(f), orc.lw_func(f, nb, ref))
     assert np.array_equal(g.Lhfunc3(f), orc.lhw_func(f, nb, ref))
     assert np.array_equal(g.wfunc(f), f * orc.vertex_area_weights(ref, nb))
+
+
+def test_final_mesh_at_moderate_scale():
+    """200k localisations, 9 002 vertices, 6 iterations in two blocks (topology re-uploaded, seeds from foot points).
+    Tolerance: mean vertex displacement <= 0.01 nm, 99.9th percentile <= 0.2 nm, max <= 3 nm -- the reference's own
+    float32-vs-float64 Gram-sum variants differ by that much."""
+    from ch_shrinkwrap_b200 import synth
+    shape = synth.two_lobed()
+    pts, sig = synth.smlm_cloud(shape, 200000, seed=91)
+    mesh = synth.star_mesh(shape, 30, scale=1.15)
+    mo, mg = _clone(mesh), _clone(mesh)
+    s = (1.0 / sig.ravel()).astype(np.float32)
+    for blk in range(2):
+        oc = _oracle(mo, pts)
+        mo.cg = oc
+        vo = oc.search(pts, lams=[5.0], num_iters=3, sigma_inv=s)
+        mo.update_geometry()
+        g = _gpu(mg, pts)
+        vg = g.search(pts, lams=[5.0], num_iters=3, sigma_inv=s)
+        mg.update_geometry()
+    d = np.sqrt(((vg.astype(np.float64) - vo) ** 2).sum(1))
+    assert d.mean() <= 1e-2 and np.percentile(d, 99.9) <= 0.2 and d.max() <= 3.0, (d.mean(), np.percentile(d, 99.9), d.max())
