@@ -10,6 +10,7 @@
 // Determinism: the adjoint accumulates in 64-bit fixed point (integer atomics are order-independent,
 // float atomics are not); the Gram sums use a fixed thread->point assignment and a fixed two-stage tree.
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include "common.cuh"
@@ -735,7 +736,8 @@ int nw_launch_seed_leaders(nw_ctx *h) {
         // iteration costs 8.3 ms instead of 27 ms at C3).  On the very first block the localisations themselves are
         // too far from the surface for this lookup to pay off (measured slower than the 1-in-32 root search below).
         k_seed_from_feet<<<nw_grid(h->P, B), B, 0, h->stream>>>(a, h->fx, h->fy, h->fz, h->fkeys,
-                                                                make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv, 48u);
+                                                                make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv,
+                                                                0u);   // measured: polishing the looked-up seed (budgets 12..48) does not make k_sweep1 any faster
         NW_LAUNCH_CHECK();
         h->seeds_cold = false;
         return NW_OK;
