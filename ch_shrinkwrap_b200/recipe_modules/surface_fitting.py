@@ -101,3 +101,73 @@ class ShrinkwrapMembrane(ModuleBase):
             md['Processing.ShrinkwrapMembrane.' + k] = getattr(self, k)
         mesh.mdh = md
         return mesh
+
+
+_IMAGE_DEFAULTS = dict(
+    input='surf', output='membrane', input_image='input',
+    max_iters=100, curvature_weight=10.0, shrink_weight=1.0, kc=1.0, remesh_frequency=5, cut_frequency=0,
+    min_hole_radius=100.0, sigma_x='sigma_x', sigma_y='sigma_y', sigma_z='sigma_z',
+    neck_threshold_low=-1e-4, neck_threshold_high=1e-2, neck_first_iter=9, minimum_edge_length=-1.0)
+
+
+def image_to_weighted_points(data, voxelsize_nm, origin):
+    """Voxels with positive intensity as weighted localisations (recipe_modules/surface_fitting.py:305-327):
+    returns (pts (P,3) float64, weights (3P,), sigma scalar = vx)."""
+    weights = np.asarray(data)
+    vx, vy, vz = voxelsize_nm
+    ox, oy, oz = origin
+    x, y, z = np.mgrid[0:weights.shape[0], 0:weights.shape[1], 0:weights.shape[2]]
+    x = ox + vx * x.ravel()
+    y = oy + vy * y.ravel()
+    z = oz + vz * z.ravel()
+    weights = weights.ravel()
+    mask = weights > 0
+    weights = weights[mask]
+    pts = np.ascontiguousarray(np.vstack([x[mask], y[mask], z[mask]]).T)
+    return pts, np.repeat(weights, 3), vx
+
+
+@register_module('ImageShrinkwrapMembrane')
+class ImageShrinkwrapMembrane(ModuleBase):
+    """Same solver driven by an image: every voxel with positive intensity is a point, its intensity the weight, the
+    voxel size the (scalar, un-inverted) sigma -- reference: recipe_modules/surface_fitting.py:246-341."""
+    if _HAVE_PYME:                                         # pragma: no cover
+        input = Input('surf'); output = Output('membrane'); input_image = Input('input')
+        max_iters = Int(100); curvature_weight = Float(10.0); shrink_weight = Float(1.0); kc = Float(1.0)
+        remesh_frequency = Int(5); cut_frequency = Int(0); min_hole_radius = Float(100.0)
+        sigma_x = CStr('sigma_x'); sigma_y = CStr('sigma_y'); sigma_z = CStr('sigma_z')
+        neck_threshold_low = Float(-1e-4); neck_threshold_high = Float(1e-2); neck_first_iter = Int(9)
+        minimum_edge_length = Float(-1.0)
+    else:
+        def __init__(self, **kwargs):
+            for k, v in _IMAGE_DEFAULTS.items():
+                setattr(self, k, v)
+            for k, v in kwargs.items():
+                if k not in _IMAGE_DEFAULTS:
+                    raise TypeError('unknown parameter %r' % k)
+                setattr(self, k, v)
+
+    def execute(self, namespace):
+        inp = namespace[self.input]
+        n_faces = len(inp.faces)
+        if not n_faces > 4:
+            raise RuntimeError('Input mesh only has %d faces, a valid surface needs at least 4 faces' % n_faces)
+        mesh = _mesh_factory(inp, kc=self.kc, max_iter=self.max_iters, step_size=self.curvature_weight,
+                             remesh_frequency=self.remesh_frequency, delaunay_remesh_frequency=self.cut_frequency,
+                             delaunay_eps=self.min_hole_radius, neck_threshold_low=self.neck_threshold_low,
+                             neck_threshold_high=self.neck_threshold_high, neck_first_iter=self.neck_first_iter,
+                             shrink_weight=self.shrink_weight)
+        if hasattr(mesh, 'repair'):                        # host topology (PYME): close holes before starting (:291-293)
+            mesh.repair()
+            mesh.remesh()
+        namespace[self.output] = mesh
+        im = namespace[self.input_image]
+        data = im.data_xyztc[:, :, :, 0, 0] if hasattr(im, 'data_xyztc') else np.asarray(im.data)
+        pts, weights, sigma = image_to_weighted_points(data, im.voxelsize_nm, im.origin)
+        mesh.shrink_wrap(pts, sigma=sigma, weights=weights, method='conjugate_gradient',
+                         minimum_edge_length=self.minimum_edge_length)
+        md = dict(getattr(inp, 'mdh', None) or {})
+        for k in _IMAGE_DEFAULTS:
+            md['Processing.ImageShrinkwrapMembrane.' + k] = getattr(self, k)
+        mesh.mdh = md
+        return mesh

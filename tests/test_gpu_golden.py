@@ -153,3 +153,37 @@ def test_stop_rule_carries_over():
     before = m._vertices['position'].copy()
     cg.search(p, lams=[5.0], num_iters=4, sigma_inv=10.0)
     assert cg.loopcount == 0 and np.array_equal(m._vertices['position'], before)
+
+
+def test_image_front_end_weights_with_scalar_sigma():
+    """ImageShrinkwrapMembrane path: voxels as points, intensities as weights, voxel size as un-inverted scalar sigma
+    (recipe_modules/surface_fitting.py:305-331) -- parity with the oracle on the same inputs, then the module end to end."""
+    import copy
+    from types import SimpleNamespace
+    from ch_shrinkwrap_b200 import synth
+    from ch_shrinkwrap_b200.mesh_conj_grad import ShrinkwrapMeshConjGrad
+    from ch_shrinkwrap_b200.recipe_modules.surface_fitting import ImageShrinkwrapMembrane, image_to_weighted_points
+    from oracle import nanowrap_oracle as orc
+    g = np.arange(-12, 13)
+    x, y, z = np.meshgrid(g, g, g, indexing='ij')
+    r = np.sqrt(x * x + y * y + z * z) * 25.0                       # voxel 25 nm, sphere shell of radius 200 nm
+    data = np.exp(-0.5 * ((r - 200.0) / 20.0) ** 2)
+    data[data < 0.2] = 0.0
+    pts, weights, sigma = image_to_weighted_points(data, (25.0, 25.0, 25.0), (-300.0, -300.0, -300.0))
+    base = synth.star_mesh(synth.Sphere(200.0), 5, scale=1.3)
+    mo, mg = copy.deepcopy(base), copy.deepcopy(base)
+    vo = orc.OracleConjGrad(mo, pts).search(pts, lams=[5.0], num_iters=4, sigma_inv=float(sigma), weights=weights)
+    vg = ShrinkwrapMeshConjGrad(mg, pts).search(pts, lams=[5.0], num_iters=4, sigma_inv=float(sigma), weights=weights)
+    assert np.sqrt(((vg.astype(np.float64) - vo) ** 2).sum(1)).max() <= 1e-2
+    im = SimpleNamespace(data=data, voxelsize_nm=(25.0, 25.0, 25.0), origin=(-300.0, -300.0, -300.0))
+    ns = {'surf': copy.deepcopy(base), 'input': im}
+    mesh = ImageShrinkwrapMembrane(max_iters=6, remesh_frequency=3).execute(ns)
+    assert ns['membrane'] is mesh
+    # the module is exactly shrink_wrap(pts, sigma=vx, weights=repeat(I, 3)) on a MembraneMesh built with its parameters
+    from ch_shrinkwrap_b200.membrane_mesh import MembraneMesh
+    direct = MembraneMesh(mesh=copy.deepcopy(base), kc=1.0, max_iter=6, step_size=10.0, remesh_frequency=3,
+                          delaunay_remesh_frequency=0, delaunay_eps=100.0, neck_threshold_low=-1e-4,
+                          neck_threshold_high=1e-2, neck_first_iter=9, shrink_weight=1.0)
+    direct.shrink_wrap(pts, sigma=sigma, weights=weights, method='conjugate_gradient', minimum_edge_length=-1.0)
+    assert np.array_equal(np.asarray(mesh.vertices), np.asarray(direct.vertices))
+    assert np.abs(np.asarray(mesh.vertices) - np.asarray(base.vertices)).max() > 0.1

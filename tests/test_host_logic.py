@@ -110,3 +110,19 @@ def test_recipe_module_surface():
     assert mod.max_iters == 39 and mod.curvature_weight == 20.0 and mod.remesh_frequency == 5
     assert mod.neck_threshold_low == -1e-3 and mod.neck_threshold_high == 1e-2 and mod.neck_first_iter == 9
     assert mod.kc == 1.0 and mod.minimum_edge_length == 5 and mod.sigma_x == 'error_x'
+
+
+def test_image_module_surface_and_voxel_conversion():
+    from ch_shrinkwrap_b200.recipe_modules.surface_fitting import ImageShrinkwrapMembrane, image_to_weighted_points
+    mod = ImageShrinkwrapMembrane()
+    # defaults of the reference module (surface_fitting.py:252-273)
+    assert mod.max_iters == 100 and mod.curvature_weight == 10.0 and mod.shrink_weight == 1.0 and mod.minimum_edge_length == -1.0
+    assert mod.neck_threshold_low == -1e-4 and mod.cut_frequency == 0
+    data = np.zeros((3, 4, 2))
+    data[1, 2, 0] = 5.0
+    data[2, 3, 1] = 7.0
+    data[0, 0, 0] = -1.0
+    pts, w, sigma = image_to_weighted_points(data, (10.0, 20.0, 30.0), (100.0, 200.0, 300.0))
+    assert sigma == 10.0 and pts.shape == (2, 3) and w.shape == (6,)
+    assert np.array_equal(pts, [[110.0, 240.0, 300.0], [120.0, 260.0, 330.0]])
+    assert np.array_equal(w, [5, 5, 5, 7, 7, 7])
