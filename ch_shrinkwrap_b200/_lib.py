@@ -26,9 +26,10 @@ SIGNATURES = {
     'nw_set_points': (c_int, [c_void_p, c_void_p, c_int, c_int64, _f, c_float, _f]),
     'nw_set_topology': (c_int, [c_void_p, _f, _f, _i, _i, POINTER(c_uint8), c_int, c_int]),
     'nw_set_topology_halfedge': (c_int, [c_void_p, _f, _f, _i, _i, _i, c_int, POINTER(c_uint8), c_int, c_int]),
-    'nw_set_topology_records': (c_int, [c_void_p, c_void_p, _i, _i, c_int, c_int, c_int]),
+    'nw_set_topology_records': (c_int, [c_void_p, c_void_p, _i, c_void_p, c_int, c_int, c_int, c_int]),
     'nw_set_positions': (c_int, [c_void_p, _f]),
     'nw_get_positions': (c_int, [c_void_p, _f]),
+    'nw_get_positions_strided': (c_int, [c_void_p, c_void_p, c_int, c_int]),
     'nw_search': (c_int, [c_void_p, c_float, c_int, c_int, _d, c_int, _f, _d, _d, _d, _d, _d, POINTER(c_int)]),
     'nw_compute_weights': (c_int, [c_void_p]),
     'nw_get_weights': (c_int, [c_void_p, _i, _f, _d, _i]),

@@ -13,7 +13,7 @@ ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('NW_EXTRA_FLAGS', '').split()
 # curvature.cu needs one IEEE operation per source operation (see its header)
 SOURCES = {'api.cu': [], 'points.cu': [], 'tree.cu': [], 'sweep.cu': [], 'mesh_ops.cu': [], 'comm.cu': [],
-           'ring.cu': [], 'benchhook.cu': [], 'curvature.cu': ['-fmad=false']}
+           'ring.cu': [], 'benchhook.cu': [], 'xfer.cu': [], 'curvature.cu': ['-fmad=false']}
 
 
 def _nvcc():

@@ -53,8 +53,12 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free(&h->partials); nw_free(&h->st); nw_free(&h->hist);
     nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP);
     nw_free((char **)&h->cvV); nw_free((char **)&h->cvF); nw_free((char **)&h->cvH); nw_free(&h->cvOut); nw_free(&h->cvJ); nw_free(&h->cvOff);
+    nw_free(&h->sp_pts); nw_free(&h->sp_k0); nw_free(&h->sp_k1); nw_free(&h->sp_idx); nw_free(&h->sp_tmp3);
+    nw_uploader_destroy(h);
+    if (h->pin_host) cudaFreeHost(h->pin_host);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev_search0) { cudaEventDestroy(h->ev_search0); cudaEventDestroy(h->ev_search1); }
+    if (h->ev_seg0) { cudaEventDestroy(h->ev_seg0); cudaEventDestroy(h->ev_seg1); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

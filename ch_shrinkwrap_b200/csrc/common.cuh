@@ -13,7 +13,8 @@
 #endif
 #define NW_MAX_LEVELS 12
 #define NW_MAX_ITERS 4096
-#define NW_N_STAGES 9    // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders
+#define NW_N_STAGES 10   // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders,
+                         // topology_build (device side of nw_set_topology*: feet, unpack, Hilbert sort, tables, frames)
 
 // Node bound = ORIENTED box INTERSECTED with a SPHERICAL SHELL.
 //  * oriented box: a surface patch is thin along its normal and tilted against the coordinate axes, so an axis-aligned
@@ -147,6 +148,11 @@ struct nw_ctx {
     double stage_ms[NW_N_STAGES] = {0};
     int64_t stage_launches[NW_N_STAGES] = {0};
     cudaEvent_t ev_search0 = nullptr, ev_search1 = nullptr;
+    // nw_set_points temporaries, grow-only like everything else (a fit uploads its points once, a session many times)
+    char *sp_pts = nullptr; unsigned long long *sp_k0 = nullptr, *sp_k1 = nullptr; int *sp_idx = nullptr; float *sp_tmp3 = nullptr;
+    char *pin_host = nullptr; size_t pin_bytes = 0;   // pinned read-back staging (nw_get_positions_strided)
+    struct nw_uploader *uploader = nullptr;       // xfer.cu: pinned staging lanes for large host->device copies
+    cudaEvent_t ev_seg0 = nullptr, ev_seg1 = nullptr;   // topology_build segments (profiling only)
     double last_search_ms = 0.0;
 
     // ---- comm ----
@@ -182,22 +188,30 @@ struct nw_ctx {
 template <typename T>
 static inline int nw_alloc(nw_ctx *h, T **p, size_t n) {
     const size_t bytes = n * sizeof(T);
+    size_t cap = bytes;
     if (*p) {
         auto it = h->caps.find((void *)p);
         if (it != h->caps.end() && it->second >= bytes && bytes > 0) return NW_OK;
+        // growing an existing array: a remesh changes M and F a little every block, so leave headroom instead of
+        // paying cudaFree + cudaMalloc (measured: 0.14 ms per MB, and stalls of hundreds of ms) on every upload
+        cap = bytes + bytes / 4;
         cudaFree(*p);
         *p = nullptr;
     }
     h->caps.erase((void *)p);
     if (n == 0) return NW_OK;
-    NW_CUDA(cudaMalloc((void **)p, bytes));
-    h->caps[(void *)p] = bytes;
+    NW_CUDA(cudaMalloc((void **)p, cap));
+    h->caps[(void *)p] = cap;
     return NW_OK;
 }
 template <typename T>
 static inline void nw_free(T **p) {
     if (*p) { cudaFree(*p); *p = nullptr; }
 }
+
+int nw_h2d(nw_ctx *h, void *dst, const void *src, size_t bytes);   // xfer.cu
+int nw_h2d_strided32(nw_ctx *h, void *dst, const void *src, size_t bytes, size_t stride);
+void nw_uploader_destroy(nw_ctx *h);
 
 static inline int nw_grid(int64_t n, int block) { return (int)((n + block - 1) / block); }
 

@@ -134,15 +134,12 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
                            const float *weights) {
     cudaStream_t s = h->stream;
     const int B = 256;
-    T *d_pts = nullptr;
-    unsigned long long *keys = nullptr, *keys2 = nullptr;
-    int *idx = nullptr;
-    float *d_bbox = nullptr, *d_tmp3 = nullptr;
+    unsigned long long *&keys = h->sp_k0, *&keys2 = h->sp_k1;
+    int *&idx = h->sp_idx;
+    float *d_bbox = nullptr, *&d_tmp3 = h->sp_tmp3;
     double *d_part = nullptr;
     int rc = NW_OK;
-    auto cleanup = [&]() {
-        nw_free(&d_pts); nw_free(&keys); nw_free(&keys2); nw_free(&idx); nw_free(&d_bbox); nw_free(&d_tmp3); nw_free(&d_part);
-    };
+    auto cleanup = [&]() { nw_free(&d_bbox); nw_free(&d_part); };
 #define NWX(x) do { rc = (x); if (rc != NW_OK) { cleanup(); return rc; } } while (0)
 #define NWC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { h->err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); return NW_ERR_CUDA; } } while (0)
 
@@ -150,8 +147,9 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
     h->weights_valid = false;
     h->seeds_cold = true;
     h->feet_valid = false;
-    NWX(nw_alloc(h, &d_pts, (size_t)3 * P));
-    NWC(cudaMemcpyAsync(d_pts, pts_host, sizeof(T) * 3 * P, cudaMemcpyHostToDevice, s));
+    NWX(nw_alloc(h, &h->sp_pts, sizeof(T) * 3 * (size_t)P));
+    T *d_pts = (T *)h->sp_pts;
+    NWX(nw_h2d(h, d_pts, pts_host, sizeof(T) * 3 * (size_t)P));
     NWX(nw_alloc(h, &d_bbox, 6));
     {
         int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
@@ -181,7 +179,6 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
         NWC(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, keys, keys2, idx, h->perm, (int64_t)P, 0, 63, s));
         h->launches += 4;
     }
-    nw_free(&keys); nw_free(&keys2); nw_free(&idx);
 
     NWX(nw_alloc(h, &h->px, (size_t)P)); NWX(nw_alloc(h, &h->py, (size_t)P)); NWX(nw_alloc(h, &h->pz, (size_t)P));
     if (sizeof(T) == 8) {
@@ -194,13 +191,13 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
         h->launches++;
     }
     NWC(cudaStreamSynchronize(s));
-    nw_free(&d_pts);
 
     // sigma_inv / weights
     h->sinv_scalar = sinv_scalar;
-    nw_free(&h->sx); nw_free(&h->sy); nw_free(&h->sz);
-    nw_free(&h->wx); nw_free(&h->wy); nw_free(&h->wz);
-    nw_free(&h->pmask);
+    // non-NULL arrays double as mode flags for the kernels: release the ones this call does not provide, keep (grow-only)
+    // the ones it does
+    if (!sigma_inv) { nw_free(&h->sx); nw_free(&h->sy); nw_free(&h->sz); }
+    if (!weights) { nw_free(&h->wx); nw_free(&h->wy); nw_free(&h->wz); }
     h->has_mask = 0;
     h->wmean = 1.f;
     h->wn_max = fabs((double)sinv_scalar);
@@ -209,7 +206,7 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
     if (sigma_inv) {
         NWX(nw_alloc(h, &h->sx, (size_t)P)); NWX(nw_alloc(h, &h->sy, (size_t)P)); NWX(nw_alloc(h, &h->sz, (size_t)P));
         if (P) {
-            NWC(cudaMemcpyAsync(d_tmp3, sigma_inv, sizeof(float) * 3 * P, cudaMemcpyHostToDevice, s));
+            NWX(nw_h2d(h, d_tmp3, sigma_inv, sizeof(float) * 3 * (size_t)P));
             k_permute_f3<<<nw_grid(P, B), B, 0, s>>>(d_tmp3, h->perm, P, h->sx, h->sy, h->sz);
             h->launches++;
         }
@@ -219,7 +216,7 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
         NWX(nw_alloc(h, &h->wx, (size_t)P)); NWX(nw_alloc(h, &h->wy, (size_t)P)); NWX(nw_alloc(h, &h->wz, (size_t)P));
         if (P) {
             NWC(cudaStreamSynchronize(s));
-            NWC(cudaMemcpyAsync(d_tmp3, weights, sizeof(float) * 3 * P, cudaMemcpyHostToDevice, s));
+            NWX(nw_h2d(h, d_tmp3, weights, sizeof(float) * 3 * (size_t)P));
             k_permute_f3<<<nw_grid(P, B), B, 0, s>>>(d_tmp3, h->perm, P, h->wx, h->wy, h->wz);
             h->launches++;
         }
@@ -267,6 +264,7 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
         h->wmean = stats[3] > 0 ? (float)(stats[0] / stats[3]) : 1.f;
         h->wn_max = h->wmean != 0.f ? stats[1] / fabs((double)h->wmean) : stats[1];
         h->has_mask = stats[2] > 0 ? 1 : 0;
+        if (!h->has_mask) nw_free(&h->pmask);
         if (h->has_mask && P) {
             NWX(nw_alloc(h, &h->pmask, (size_t)P));
             const float *ax = h->weights_mode == 2 ? h->wx : h->sx, *ay = h->weights_mode == 2 ? h->wy : h->sy,
@@ -275,10 +273,12 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
             h->launches++;
         }
     }
+    if (h->weights_mode == 0) nw_free(&h->pmask);
     // per-point outputs
     NWX(nw_alloc(h, &h->slot, (size_t)P));
     NWX(nw_alloc(h, &h->w0, (size_t)P)); NWX(nw_alloc(h, &h->w1, (size_t)P)); NWX(nw_alloc(h, &h->w2, (size_t)P));
     NWX(nw_alloc(h, &h->rx, (size_t)P)); NWX(nw_alloc(h, &h->ry, (size_t)P)); NWX(nw_alloc(h, &h->rz, (size_t)P));
+    NWX(nw_alloc(h, &h->fx, (size_t)P)); NWX(nw_alloc(h, &h->fy, (size_t)P)); NWX(nw_alloc(h, &h->fz, (size_t)P));   // foot points (seeds across uploads)
     if (P) {
         k_fill_int<<<nw_grid(P, B), B, 0, s>>>(h->slot, P, -1);
         h->launches++;

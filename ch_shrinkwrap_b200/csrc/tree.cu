@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <cstdlib>
 #include "common.cuh"
+#include <chrono>
 
 namespace {
 
@@ -419,7 +420,7 @@ inline float ordered_to_float(int v) {
 }  // namespace
 
 static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces, const int32_t *nbr,
-                             const int32_t *he_vertex, int n_he, const uint8_t *valid, int M, int F);
+                             const int32_t *he_vertex, int n_he, const uint8_t *valid, int M, int F, int he_stride = 4);
 
 extern "C" int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces,
                                const int32_t *nbr, const uint8_t *valid, int M, int F) {
@@ -434,14 +435,47 @@ extern "C" int nw_set_topology_halfedge(nw_ctx *h, const float *pos, const float
 }
 
 extern "C" int nw_set_topology_records(nw_ctx *h, const void *vertex_records, const int32_t *faces, const int32_t *he_vertex,
-                                       int n_halfedges, int M, int F) {
+                                       int he_stride_bytes, int n_halfedges, int M, int F) {
     if (h && !(vertex_records && he_vertex && n_halfedges > 0)) { h->err = "nw_set_topology_records: NULL array"; return NW_ERR_ARG; }
-    return set_topology_impl(h, (const float *)vertex_records, nullptr, faces, nullptr, he_vertex, n_halfedges, nullptr, M, F);
+    if (h && !(he_stride_bytes >= 4 && he_stride_bytes % 4 == 0)) { h->err = "nw_set_topology_records: he_stride_bytes must be a multiple of 4"; return NW_ERR_ARG; }
+    return set_topology_impl(h, (const float *)vertex_records, nullptr, faces, nullptr, he_vertex, n_halfedges, nullptr, M, F, he_stride_bytes);
+}
+
+// NW_TRACE_BUILD=1: wall-clock checkpoints (with a stream sync each) through nw_tree_build, on stderr
+struct BuildTrace {
+    bool on; cudaStream_t s; std::chrono::steady_clock::time_point t;
+    BuildTrace(cudaStream_t s_) : on(getenv("NW_TRACE_BUILD") != nullptr), s(s_) { if (on) { cudaStreamSynchronize(s); t = std::chrono::steady_clock::now(); } }
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[nw build] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
+// profiling: device time of the compute segments of an upload (the host->device copies between them are not counted)
+static int seg_begin(nw_ctx *h) {
+    if (!h->profile) return NW_OK;
+    if (!h->ev_seg0) { NW_CUDA(cudaEventCreate(&h->ev_seg0)); NW_CUDA(cudaEventCreate(&h->ev_seg1)); }
+    NW_CUDA(cudaEventRecord(h->ev_seg0, h->stream));
+    h->stage_launches[9] -= h->launches;
+    return NW_OK;
+}
+static int seg_end(nw_ctx *h) {
+    if (!h->profile) return NW_OK;
+    NW_CUDA(cudaEventRecord(h->ev_seg1, h->stream));
+    NW_CUDA(cudaEventSynchronize(h->ev_seg1));
+    float ms = 0.f;
+    NW_CUDA(cudaEventElapsedTime(&ms, h->ev_seg0, h->ev_seg1));
+    h->stage_ms[9] += ms;
+    h->stage_launches[9] += h->launches;
+    return NW_OK;
 }
 
 // nrm == NULL && nbr == NULL: `pos` points at M raw vertex_t records
 static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces, const int32_t *nbr,
-                             const int32_t *he_vertex, int n_he, const uint8_t *valid, int M, int F) {
+                             const int32_t *he_vertex, int n_he, const uint8_t *valid, int M, int F, int he_stride) {
     if (!h) return NW_ERR_ARG;
     NW_ARG(M > 0 && F > 0, "nw_set_topology: empty mesh");
     const bool records = (nrm == nullptr && nbr == nullptr);
@@ -449,7 +483,10 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     NW_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const int B = 256;
+    BuildTrace trace_up(s);
+    NW_CHECK(seg_begin(h));
     NW_CHECK(nw_save_feet(h));       // seeds for the next block, taken from the mesh that is about to be replaced
+    NW_CHECK(seg_end(h));
     h->M = M; h->F = F;
     h->weights_valid = false;
     NW_CHECK(nw_alloc(h, &h->posq, (size_t)M)); NW_CHECK(nw_alloc(h, &h->nrmq, (size_t)M));
@@ -465,34 +502,47 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     // staging buffers are members so that they are reused from block to block (grow-only)
     if (he_vertex) {
         NW_CHECK(nw_alloc(h, &h->stage_hev, (size_t)n_he));
-        NW_CUDA(cudaMemcpyAsync(h->stage_hev, he_vertex, sizeof(int) * n_he, cudaMemcpyHostToDevice, s));
+        NW_CHECK(nw_h2d_strided32(h, h->stage_hev, he_vertex, sizeof(int) * (size_t)n_he, (size_t)he_stride));
     }
-    NW_CUDA(cudaMemcpyAsync(h->faces, faces, sizeof(int) * 3 * F, cudaMemcpyHostToDevice, s));
+    NW_CHECK(nw_h2d(h, h->faces, faces, sizeof(int) * 3 * (size_t)F));
     if (records) {
         NW_CHECK(nw_alloc(h, &h->stage_nbr, (size_t)30 * M));
-        NW_CUDA(cudaMemcpyAsync(h->stage_nbr, pos, (size_t)120 * M, cudaMemcpyHostToDevice, s));
+        NW_CHECK(nw_h2d(h, h->stage_nbr, pos, (size_t)120 * M));
+        NW_CHECK(seg_begin(h));
         k_unpack_vertex_records<<<nw_grid(M, B), B, 0, s>>>(h->stage_nbr, M, h->stage_hev, n_he, h->posq, h->nrmq, h->valid, h->nbrT, h->valence);
         h->launches += 1;
+        NW_CHECK(seg_end(h));
     } else {
         NW_CHECK(nw_alloc(h, &h->stage_nbr, (size_t)NW_NEIGHBORSIZE * M));
         NW_CUDA(cudaMemcpyAsync(h->scratchM, pos, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+        NW_CHECK(seg_begin(h));
         k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->posq);
+        h->launches += 1;
+        NW_CHECK(seg_end(h));
         NW_CUDA(cudaStreamSynchronize(s));
         NW_CUDA(cudaMemcpyAsync(h->scratchM, nrm, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+        NW_CHECK(seg_begin(h));
         k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->nrmq);
-        NW_CUDA(cudaMemcpyAsync(h->stage_nbr, nbr, sizeof(int) * NW_NEIGHBORSIZE * M, cudaMemcpyHostToDevice, s));
+        h->launches += 1;
+        NW_CHECK(seg_end(h));
+        NW_CHECK(nw_h2d(h, h->stage_nbr, nbr, sizeof(int) * NW_NEIGHBORSIZE * (size_t)M));
+        NW_CHECK(seg_begin(h));
         k_transpose_nbr<<<nw_grid(M, B), B, 0, s>>>(h->stage_nbr, he_vertex ? h->stage_hev : nullptr, n_he, M, h->nbrT, h->valence);
-        h->launches += 3;
+        h->launches += 1;
+        NW_CHECK(seg_end(h));
         if (valid) NW_CUDA(cudaMemcpyAsync(h->valid, valid, M, cudaMemcpyHostToDevice, s));
         else NW_CUDA(cudaMemsetAsync(h->valid, 1, M, s));
     }
+    NW_CUDA(cudaStreamSynchronize(s));
+    trace_up.mark("feet + uploads + unpack");
+    NW_CHECK(seg_begin(h));
     NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * M, s));
     NW_CUDA(cudaMemsetAsync(h->Sq, 0, sizeof(float4) * 3 * M, s));
-    NW_CUDA(cudaStreamSynchronize(s));
     // nearest-face slots refer to the previous block's sort order
     if (h->slot && h->P) NW_CUDA(cudaMemsetAsync(h->slot, 0xff, sizeof(int) * h->P, s));
     h->seeds_cold = true;
-    return nw_tree_build(h);
+    NW_CHECK(nw_tree_build(h));
+    return seg_end(h);
 }
 
 static int scan_inclusive(nw_ctx *h, const int *in, int *out, int n) {
@@ -527,6 +577,7 @@ int nw_tree_refit(nw_ctx *h) {
 int nw_tree_build(nw_ctx *h) {
     cudaStream_t s = h->stream;
     const int B = 256, F = h->F;
+    BuildTrace trace(s);
     // build temporaries are members: reused from block to block (cudaFree synchronises and is slow)
     int *&d_bbox = h->tb_small, *&idx = h->tb_i0, *&order = h->tb_i1;
     unsigned *&keys = h->tb_u0, *&keys2 = h->tb_u1;
@@ -537,6 +588,7 @@ int nw_tree_build(nw_ctx *h) {
     int bb[6];
     NW_CUDA(cudaMemcpyAsync(bb, d_bbox, sizeof(bb), cudaMemcpyDeviceToHost, s));
     NW_CUDA(cudaStreamSynchronize(s));
+    trace.mark("face bbox");
     float lo[3], hi[3];
     for (int a = 0; a < 3; ++a) { lo[a] = ordered_to_float(bb[a]); hi[a] = ordered_to_float(bb[3 + a]); }
     float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
@@ -553,6 +605,7 @@ int nw_tree_build(nw_ctx *h) {
     h->key_lo[0] = lo[0]; h->key_lo[1] = lo[1]; h->key_lo[2] = lo[2]; h->key_inv = inv;
     k_sorted_faces<<<nw_grid(F, B), B, 0, s>>>(h->faces, order, F, h->sfaces);
     h->launches += 7;
+    trace.mark("keys + sort");
 
     // ---- level sizes: nodes of level k = distinct 3k-bit key prefixes; leaf level = deepest with >= 4 centroids per node
     int *hist = d_bbox;                                   // 16 ints
@@ -561,6 +614,7 @@ int nw_tree_build(nw_ctx *h) {
     int hh[16];
     NW_CUDA(cudaMemcpyAsync(hh, hist, sizeof(hh), cudaMemcpyDeviceToHost, s));
     NW_CUDA(cudaStreamSynchronize(s));
+    trace.mark("level histogram");
     int cnt[11];
     cnt[0] = 1;
     for (int k = 1; k <= 10; ++k) cnt[k] = cnt[k - 1] + hh[k];
@@ -576,9 +630,15 @@ int nw_tree_build(nw_ctx *h) {
         off += cnt[k]; cb += cnt[k] + 1;
     }
     const int total = off;
-    NW_CHECK(nw_alloc(h, &h->boxes, (size_t)total)); NW_CHECK(nw_alloc(h, &h->par, (size_t)total));
-    NW_CHECK(nw_alloc(h, &h->cbegin, (size_t)cb)); NW_CHECK(nw_alloc(h, &h->leaf_of_slot, (size_t)F));
-    NW_CHECK(nw_alloc(h, &h->node_f, (size_t)NW_NMOM * total));
+    // the node count follows the shape of the mesh: the leaf level can change from one block to the next, which changes
+    // the total 4-fold, and re-allocating stalls the upload (measured: 3 ms to 480 ms).  There are <= F/1.5 leaf cells
+    // and, for a surface, a third of that above them (0.9 F in all; 1.33 F if the levels only double), so 1.5 F nodes is
+    // a size that depends on the topology alone.
+    const size_t room = std::max((size_t)total + total / 4, (size_t)F + F / 2) + 64;
+    NW_CHECK(nw_alloc(h, &h->boxes, room)); NW_CHECK(nw_alloc(h, &h->par, room));
+    NW_CHECK(nw_alloc(h, &h->cbegin, room + NW_MAX_LEVELS + 1)); NW_CHECK(nw_alloc(h, &h->leaf_of_slot, (size_t)F));
+    NW_CHECK(nw_alloc(h, &h->node_f, (size_t)NW_NMOM * room));
+    trace.mark("allocations");
     // ---- per-level tables
     int *flag = idx, *id_cur = order, *id_prev = (int *)keys, *start = (int *)keys2;     // reuse the sort buffers (F ints each)
     for (int k = 0; k <= kL; ++k) {
@@ -599,6 +659,7 @@ int nw_tree_build(nw_ctx *h) {
         NW_LAUNCH_CHECK();
         std::swap(id_cur, id_prev);
     }
+    trace.mark("level tables");
     // ---- frames (fixed for the block), first extents, sphere fits, extents again (now with the shell radii)
     k_refit_centroids<<<nw_grid(F, B), B, 0, s>>>(h->sfaces, h->posq, F, h->cent);
     NW_LAUNCH_CHECK();
@@ -617,7 +678,10 @@ int nw_tree_build(nw_ctx *h) {
     k_shell_fit<<<nw_grid(total - tl.off[1], B), B, 0, s>>>(h->boxes, h->node_f, tl.off[1], total - tl.off[1]);
     NW_LAUNCH_CHECK();
 #endif
-    return extents_pass(h);
+    trace.mark("normals + frames");
+    NW_CHECK(extents_pass(h));
+    trace.mark("extents");
+    return NW_OK;
 }
 
 extern "C" int nw_set_positions(nw_ctx *h, const float *pos) {
@@ -629,6 +693,33 @@ extern "C" int nw_set_positions(nw_ctx *h, const float *pos) {
     NW_LAUNCH_CHECK();
     NW_CUDA(cudaStreamSynchronize(h->stream));
     h->weights_valid = false;
+    return NW_OK;
+}
+
+// f written straight into the host mesh's records: position of vertex i (3 x float32) at dst + i * stride_bytes; with
+// only_valid rows whose halfedge is -1 keep their bytes (mesh_conj_grad.py:289 without a strided numpy assignment)
+extern "C" int nw_get_positions_strided(nw_ctx *h, void *dst, int stride_bytes, int only_valid) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(h->M > 0, "nw_get_positions_strided: no topology");
+    NW_ARG(dst && stride_bytes >= 12, "nw_get_positions_strided: bad destination");
+    NW_CUDA(cudaSetDevice(h->device));
+    const size_t M = (size_t)h->M, need = M * 12 + M;
+    if (h->pin_bytes < need) {
+        if (h->pin_host) cudaFreeHost(h->pin_host);
+        h->pin_host = nullptr; h->pin_bytes = 0;
+        NW_CUDA(cudaHostAlloc((void **)&h->pin_host, need, cudaHostAllocDefault));
+        h->pin_bytes = need;
+    }
+    k_unpack_vec3<<<nw_grid(h->M, 256), 256, 0, h->stream>>>(h->posq, h->M, h->scratchM);
+    NW_LAUNCH_CHECK();
+    NW_CUDA(cudaMemcpyAsync(h->pin_host, h->scratchM, M * 12, cudaMemcpyDeviceToHost, h->stream));
+    if (only_valid) NW_CUDA(cudaMemcpyAsync(h->pin_host + M * 12, h->valid, M, cudaMemcpyDeviceToHost, h->stream));
+    NW_CUDA(cudaStreamSynchronize(h->stream));
+    const char *src = h->pin_host;
+    const unsigned char *ok = (const unsigned char *)h->pin_host + M * 12;
+    char *d = (char *)dst;
+    for (size_t i = 0; i < M; ++i)
+        if (!only_valid || ok[i]) memcpy(d + i * (size_t)stride_bytes, src + i * 12, 12);
     return NW_OK;
 }
 

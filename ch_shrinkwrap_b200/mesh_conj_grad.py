@@ -96,7 +96,7 @@ class ShrinkwrapMeshConjGrad(object):
         self.mesh = mesh
         self._points = points
         self.sigma = sigma
-        self._mesh_vertex_mask = mesh._vertices['halfedge'] != -1   # :44
+        self._vertex_mask = None                                    # :44, built lazily
         self.vertices = mesh._vertices['position']                  # :46
         self.faces = mesh.faces                                     # :47
         self._vertex_neighbors = None                              # :50-54, built lazily (the device does its own lookup)
@@ -122,6 +122,12 @@ class ShrinkwrapMeshConjGrad(object):
         return self._points
 
     @property
+    def _mesh_vertex_mask(self):
+        if self._vertex_mask is None:
+            self._vertex_mask = self.mesh._vertices['halfedge'] != -1
+        return self._vertex_mask
+
+    @property
     def vertex_neighbors(self):
         """(M,20) neighbour vertex ids, -1 padded (mesh_conj_grad.py:50-54)."""
         if self._vertex_neighbors is None:
@@ -138,15 +144,20 @@ class ShrinkwrapMeshConjGrad(object):
     def _upload_topology(self):
         mesh = self.mesh
         faces = np.ascontiguousarray(self.faces, dtype=np.int32)
-        he_vertex = np.ascontiguousarray(mesh._halfedges['vertex'], dtype=np.int32)
+        he_field = mesh._halfedges['vertex']
         verts = mesh._vertices
         nrm = mesh.vertex_normals
         if (verts.dtype.itemsize == 120 and verts.flags.c_contiguous and isinstance(nrm, np.ndarray)
                 and np.shares_memory(nrm, verts) and nrm.shape == (len(verts), 3)):
-            # fast path: the records go up as they lie in memory (position, normal, halfedge, neighbors all inside)
-            self._h.call('nw_set_topology_records', ctypes.c_void_p(verts.ctypes.data), _lib.iptr(faces), _lib.iptr(he_vertex),
-                         int(he_vertex.shape[0]), int(len(verts)), int(faces.shape[0]))
+            # fast path: the records go up as they lie in memory (position, normal, halfedge, neighbors all inside); the
+            # half-edge 'vertex' field is gathered out of its records by the library's upload threads
+            if he_field.dtype != np.int32 or he_field.ndim != 1 or he_field.strides[0] % 4 != 0 or he_field.strides[0] < 4:
+                he_field = np.ascontiguousarray(he_field, dtype=np.int32)
+            self._h.call('nw_set_topology_records', ctypes.c_void_p(verts.ctypes.data), _lib.iptr(faces),
+                         ctypes.c_void_p(he_field.ctypes.data), int(he_field.strides[0]),
+                         int(he_field.shape[0]), int(len(verts)), int(faces.shape[0]))
         else:
+            he_vertex = np.ascontiguousarray(he_field, dtype=np.int32)
             pos = _lib.as_f32(verts['position'])
             nrm = _lib.as_f32(nrm)
             nbr_he = np.ascontiguousarray(verts['neighbors'], dtype=np.int32)
@@ -201,11 +212,13 @@ class ShrinkwrapMeshConjGrad(object):
             self.cpred, self.wpreds = float(hist[3][k - 1]), [float(hist[4][k - 1])]
         self.fs = out
         self.f = out.ravel()
-        valid = self._mesh_vertex_mask
-        if valid.all():
-            self.mesh._vertices['position'][:] = out                    # :289 (all rows valid: plain strided copy)
+        dst = self.mesh._vertices['position']
+        if isinstance(dst, np.ndarray) and dst.dtype == np.float32 and dst.ndim == 2 and dst.shape == out.shape and dst.strides[1] == 4:
+            # :289, written by the library row by row into the records (valid rows only)
+            self._h.call('nw_get_positions_strided', ctypes.c_void_p(dst.ctypes.data), int(dst.strides[0]), 1)
         else:
-            self.mesh._vertices['position'][valid] = out[valid]
+            valid = self._mesh_vertex_mask
+            dst[valid] = out[valid]
         self.mesh._initialize_curvature_vectors()                        # :290
         return self.fs
 

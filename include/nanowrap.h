@@ -74,11 +74,17 @@ int nw_set_topology_halfedge(nw_ctx *h, const float *pos, const float *nrm, cons
                              const uint8_t *valid, int M, int F);
 /* Same from the raw records: vertex_records = mesh._vertices as it lies in memory (M x vertex_t, 120 B each,
  * membrane_mesh_utils.h:57-65: position, normal, halfedge, valence, neighbors[20], component, locally_manifold).
- * One contiguous upload, no host-side packing; position / normal / valid / neighbours are unpacked on the device. */
+ * One contiguous upload, no host-side packing; position / normal / valid / neighbours are unpacked on the device.
+ * he_vertex points at the first 'vertex' entry and he_stride_bytes is the distance between entries: 4 for a packed
+ * int32 array, 28 (halfedge_t, membrane_mesh_utils.h:31-39) when it points into mesh._halfedges as it lies in memory. */
 int nw_set_topology_records(nw_ctx *h, const void *vertex_records, const int32_t *faces, const int32_t *he_vertex,
-                            int n_halfedges, int M, int F);
+                            int he_stride_bytes, int n_halfedges, int M, int F);
 int nw_set_positions(nw_ctx *h, const float *pos);           /* overwrite f (3M) */
 int nw_get_positions(nw_ctx *h, float *pos);                 /* read f (3M)      */
+/* f written straight into the host mesh: vertex i's (x, y, z) float32 at dst + i * stride_bytes (dst =
+ * &mesh._vertices['position'][0], stride 120 for vertex_t records); only_valid != 0 leaves the rows with
+ * halfedge == -1 untouched: mesh._vertices['position'][mask] = f[mask] (mesh_conj_grad.py:289) */
+int nw_get_positions_strided(nw_ctx *h, void *dst, int stride_bytes, int only_valid);
 
 /* ---- the hot loop -------------------------------------------------------------------------------
  * Replaces ShrinkwrapMeshConjGrad.search (mesh_conj_grad.py:150-292) with Lfuncs = ["I"]
@@ -141,9 +147,11 @@ int nw_neck_candidates(nw_ctx *h, float low, float high, int32_t *idx, int *n);
 int nw_bench_kernel(nw_ctx *h, const char *name, int reps, float *ms_per_launch);
 int nw_sync(nw_ctx *h);
 /* CUDA-event timing on the handle's stream: on = 1 brackets every stage of every iteration inside
- * nw_search.  nw_get_profile returns accumulated ms and kernel launches per stage (9 stages: refit,
- * shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders) and the event-
- * timed duration of the last nw_search call (first kernel to last kernel). */
+ * nw_search and the device-side segments of nw_set_topology*.  nw_get_profile returns accumulated ms and kernel
+ * launches per stage (10 stages: refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars,
+ * solve_update, seed_leaders, topology_build = foot points + record unpack + Hilbert sort + octree tables + frames of
+ * every upload, host->device copies excluded) and the event-timed duration of the last nw_search call (first kernel to
+ * last kernel). */
 int nw_set_profile(nw_ctx *h, int on);
 int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms);
 /* nearest-face traversal statistics accumulated since the last nw_search / nw_ncc / nw_bench_kernel state reset:

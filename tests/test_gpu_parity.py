@@ -198,6 +198,11 @@ def test_deleted_vertices_stay_put():
     vg = _gpu(mg, pts).search(pts, lams=[5.0], num_iters=3, sigma_inv=s)
     assert np.array_equal(vg[-2:], extra['position'])
     assert np.sqrt(((vg.astype(np.float64) - vo) ** 2).sum(1)).max() <= 1e-2
+    # side effect of search() (:289): the library writes f into the records row by row, valid rows only
+    assert np.array_equal(mg._vertices['position'][:-2], vg[:-2])
+    assert np.array_equal(mg._vertices['position'][-2:], extra['position'])
+    assert np.array_equal(mg._vertices['normal'], mesh._vertices['normal'])      # neighbouring fields untouched
+    assert np.array_equal(mg._vertices['halfedge'], mesh._vertices['halfedge'])
 
 
 def test_curvature_sphere_and_plane_known_answers():

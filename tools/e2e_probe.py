@@ -12,3 +12,13 @@ for blk in range(3):
     cg._upload_topology(); t3=time.perf_counter()
     cg.search(pts, lams=[5.0], num_iters=5, sigma_inv=s_inv); t4=time.perf_counter()
     print('block %d: ctor %.3f set_points %.3f topo %.3f search %.3f'%(blk, t1-t0, t2-t1, t3-t2, t4-t3))
+# warm re-upload of the points (what bench.py's e2e leg pays after its warm-up run)
+for rep in range(2):
+    cg._session.points_key = None
+    t0=time.perf_counter(); cg._session.set_points(pts, s_inv, None); t1=time.perf_counter()
+    print('warm set_points %.3f s' % (t1-t0))
+import cProfile, pstats
+cg._session.points_key = None
+pr = cProfile.Profile(); pr.enable()
+cg=mcg.ShrinkwrapMeshConjGrad(mesh, pts); cg.search(pts, lams=[5.0], num_iters=5, sigma_inv=s_inv)
+pr.disable(); pstats.Stats(pr).sort_stats('cumulative').print_stats(18)
