@@ -61,6 +61,7 @@ struct SolverState {
     int bbox[6];                  // ordered-int bounding box of the vertices (k_shift_partial -> k_shift_final)
     float coord_l1;               // bound on |x|+|y|+|z| over vertices and points (rounding slack of the box tests)
     float lam;
+    float cell_escape;            // grid units: how far any centroid has left the 1024^3 cell it was keyed into at upload (k_refit_centroids)
 #ifdef NW_LEVEL_STATS
     unsigned long long lvl_tests[32], lvl_pass[32];   // diagnosis builds only: node tests / passes per tree level
 #endif
@@ -103,7 +104,7 @@ struct nw_ctx {
     uint8_t *valid = nullptr;
     int *stage_nbr = nullptr, *stage_hev = nullptr;   // upload staging (reused across blocks)
     int *tb_small = nullptr, *tb_i0 = nullptr, *tb_i1 = nullptr;   // tree-build temporaries (reused across blocks)
-    unsigned *tb_u0 = nullptr, *tb_u1 = nullptr;
+    unsigned *tb_u0 = nullptr, *tb_u1 = nullptr, *tb_u2 = nullptr;
     // ---- search hierarchy over the face centroids (tree.cu) ----
     int4 *sfaces = nullptr;                      // per sorted slot: corner ids + face id
     float4 *cent = nullptr;                      // per sorted slot: centroid xyz + face id bits
@@ -116,6 +117,7 @@ struct nw_ctx {
     bool feet_valid = false;
     unsigned *fkeys = nullptr;                   // sorted Hilbert keys of the face centroids at upload time
     float key_lo[3] = {0, 0, 0}, key_inv = 0.f;  // quantisation used for those keys
+    unsigned *fcells = nullptr;                  // per sorted slot: grid cell of the centroid at upload time, x | y << 10 | z << 20
     // ---- solver vectors ----
     unsigned long long *acc = nullptr;           // (M,4) int64 fixed point: AH res xyz, AH 1
     float4 *Sq = nullptr;                        // search directions, interleaved: S_k of vertex v at Sq[3v + k] (48 B per vertex)

@@ -62,6 +62,10 @@ struct QueryF64 {
     }
 };
 
+#ifndef NW_PACKET
+#define NW_PACKET 1      // 1: warp-packet search in k_sweep1 (see Traversal); 0: one private search per lane
+#endif
+
 struct Nearest {
     double d2;
     float ub;      // d2 rounded up to float: prune bound for the float32 lower bounds
@@ -137,12 +141,39 @@ struct TreeView {
     const int *__restrict__ par;        // parent index | (last child of its parent) << 31
     const int *__restrict__ cbegin;     // first child (leaf level: first slot), count+1 entries per level
     const int *__restrict__ leaf_of_slot;
+    const unsigned *__restrict__ fcells;   // grid cell (x | y << 10 | z << 20) each sorted centroid was keyed into at upload
+    float3 grid_lo;                        // the 1024^3 grid of those keys: g = (p - grid_lo) * grid_inv
+    float grid_inv, grid_cellw;            // cells per nm, nm per cell (0 when the mesh has no extent)
 };
 
-template <typename Q>
+//
+// PACKET = true: the 32 queries of a warp (Hilbert-sorted neighbours, so their searches overlap almost completely) walk
+// the tree TOGETHER: one shared (level, node) cursor, a node is entered if ANY lane cannot prune it, every lane keeps
+// its own best and prunes with its own bound.  Each lane still sees every node it could not prune itself, so the
+// result per lane is exactly that of a private search; what changes is that the warp never diverges (node data are
+// warp-uniform broadcast loads) and pays for the union of the lanes' node sets instead of 32 interleaved private walks.
+// All 32 lanes must call the methods (inactive lanes with active = false).
+template <typename Q, bool PACKET = false>
 struct Traversal {
     Q q;
     Nearest best;
+    bool active = true;            // packet mode: lanes past the end of the array take part in the votes only
+    int lead = 0;                  // packet mode: lane whose query steers the greedy descent of top_down()
+    // packet mode: one lane's query as the packet's centre and the largest distance of any lane's query from it.  A box
+    // at distance D from the centre is at least D - pk_r from every lane, so ONE evaluation settles a node for the
+    // whole packet -- which lets the lanes test DIFFERENT nodes in the same step (all siblings of a level at once).
+    QueryF32 pk_c;
+    float pk_r = 0.f;
+    __device__ __forceinline__ void set_packet_centre(int lane) {
+        pk_c.x = __shfl_sync(0xffffffffu, q.fx(), lane); pk_c.y = __shfl_sync(0xffffffffu, q.fy(), lane); pk_c.z = __shfl_sync(0xffffffffu, q.fz(), lane);
+        const float dx = q.fx() - pk_c.x, dy = q.fy() - pk_c.y, dz = q.fz() - pk_c.z;
+        // rounded up, plus the float32 rounding of a float64 query (eps is 8 ulp of the coordinates)
+        float r = active ? __fadd_ru(__fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz))), eps) : 0.f;
+        if (!(r >= 0.f)) r = __int_as_float(0x7f800000);                       // NaN query: the prefilter never prunes
+        pk_r = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(r)));
+    }
+    __device__ __forceinline__ bool any(bool p) const { if constexpr (PACKET) return __any_sync(0xffffffffu, p); else return p; }
+    __device__ __forceinline__ bool all(bool p) const { if constexpr (PACKET) return __all_sync(0xffffffffu, p); else return p; }
     TreeView tv;
     const TreeLevels &tl;          // lives in the kernel's __grid_constant__ parameter space (LDC with a dynamic index)
     float eps;
@@ -151,9 +182,37 @@ struct Traversal {
     SolverState *dbg = nullptr;
 #endif
     unsigned budget = 0xffffffffu;   // seeds only: stop refining after this many node tests (the result is then approximate)
+    // Cell clearance.  A level-k node holds exactly the centroids keyed into one aligned cube of 2^(10-k) grid cells.
+    // Once everything under the level-k ancestor of the seed has been searched, and that cube is the one the query
+    // lies in, every other centroid was keyed OUTSIDE the cube; it has since moved at most `escape` cells (L-infinity,
+    // k_refit_centroids), so it is at least (distance from the query to the cube's walls - escape) away.  If that
+    // exceeds the best distance the climb can stop: the levels above cannot hold anything closer.
+    float gx, gy, gz;                // query in grid units; gx < 0: outside the grid / no grid -> no early-out
+    float escape;
 
-    __device__ __forceinline__ Traversal(const Q &q_, const Nearest &b_, const TreeView &tv_, const TreeLevels &tl_, float eps_)
-        : q(q_), best(b_), tv(tv_), tl(tl_), eps(eps_) {}
+    __device__ __forceinline__ Traversal(const Q &q_, const Nearest &b_, const TreeView &tv_, const TreeLevels &tl_, float eps_, float escape_)
+        : q(q_), best(b_), tv(tv_), tl(tl_), eps(eps_), escape(escape_) {
+        gx = (q.fx() - tv.grid_lo.x) * tv.grid_inv; gy = (q.fy() - tv.grid_lo.y) * tv.grid_inv; gz = (q.fz() - tv.grid_lo.z) * tv.grid_inv;
+        if (!(gx >= 0.f && gx < 1024.f && gy >= 0.f && gy < 1024.f && gz >= 0.f && gz < 1024.f && tv.grid_inv > 0.f && escape < 1024.f)) gx = -1.f;
+    }
+    // deepest level whose cube around `cell` also contains the query
+    __device__ __forceinline__ int shared_levels(unsigned cell) const {
+        if (gx < 0.f) return 0;
+        const unsigned d = cell ^ ((unsigned)gx | ((unsigned)gy << 10) | ((unsigned)gz << 20));
+        const unsigned m = (d | (d >> 10) | (d >> 20)) & 1023u;       // highest differing bit over the three axes
+        return m ? __clz(m) - 22 : 10;
+    }
+    // true if nothing outside the query's level-`level` cube can beat the current best
+    __device__ __forceinline__ bool cube_clear(int level) const {
+        const int s = 10 - level;
+        const float w = (float)(1u << s);
+        const float fx = gx - (float)(((unsigned)gx >> s) << s), fy = gy - (float)(((unsigned)gy >> s) << s),
+                    fz = gz - (float)(((unsigned)gz >> s) << s);
+        const float cl = fminf(fminf(fminf(fx, w - fx), fminf(fy, w - fy)), fminf(fz, w - fz));
+        // slack: rounding of g for the query and for the centroids (a few ulp of 1024 each), of the coordinates (eps)
+        const float m = (cl - escape - 1e-3f) * tv.grid_cellw - 2.f * eps;
+        return m > 0.f && __fmul_rd(__fmul_rd(m, m), 0.99999f) > best.ub;
+    }
 
     __device__ __forceinline__ void leaf(int idx) {
         const int *cb = tv.cbegin + tl.cb_off[tl.n_levels - 1] + idx;
@@ -161,7 +220,7 @@ struct Traversal {
         ++n_leaves;
         for (int s = s0; s < s1; ++s) {
             const float4 c = __ldg(&tv.cent[s]);
-            if (q.lb_box(c, c) <= best.ub) { ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
+            if (active && q.lb_box(c, c) <= best.ub) { ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
         }
     }
     // Depth-first search of the subtree rooted at node I of level L.  Children and next siblings come from two small
@@ -173,11 +232,11 @@ struct Traversal {
         while (true) {
             if (++n_tests > budget) return;
 #ifdef NW_LEVEL_STATS
-            const bool pass_ = node_lb(q, &tv.boxes[tl.off[level] + idx], eps) <= best.ub;
-            if (dbg) { atomicAdd(&dbg->lvl_tests[level], 1ull); if (pass_) atomicAdd(&dbg->lvl_pass[level], 1ull); }
+            const bool pass_ = any(active && node_lb(q, &tv.boxes[tl.off[level] + idx], eps) <= best.ub);
+            if (dbg && active) { atomicAdd(&dbg->lvl_tests[level], 1ull); if (pass_) atomicAdd(&dbg->lvl_pass[level], 1ull); }
             if (pass_) {
 #else
-            if (node_lb(q, &tv.boxes[tl.off[level] + idx], eps) <= best.ub) {
+            if (any(active && node_lb(q, &tv.boxes[tl.off[level] + idx], eps) <= best.ub)) {
 #endif
                 if (level == leafL) leaf(idx);
                 else { idx = __ldg(&tv.cbegin[tl.cb_off[level] + idx]); ++level; continue; }
@@ -190,35 +249,68 @@ struct Traversal {
             }
         }
     }
-    // climb from a leaf: at every level only the sibling subtrees are searched
-    __device__ __forceinline__ void from_leaf(int node) {
+    // Packet prefilter for the climb: all (<= 8) siblings of a level are bounded in ONE step -- lane j evaluates sibling j
+    // against the packet centre, which settles it for every lane (set_packet_centre).  Survivors are then searched with
+    // every lane's own, tighter bound (dfs_subtree).  Measured at C3: using the same prefilter for the children inside
+    // dfs_subtree (survivor masks per level in registers) cut the steps from 82 to 65 per point but cost 16 registers
+    // and ran 8 % slower; relying on the packet bound ALONE is hopeless (warps that straddle a jump of the Hilbert curve
+    // have a large radius: 80-190 ms instead of 3).
+    __device__ __forceinline__ float packet_reach() const {
+        float ubm = active ? best.ub : 0.f;
+        if (!(ubm >= 0.f)) ubm = __int_as_float(0x7f800000);
+        return __fadd_ru(__fsqrt_ru(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ubm)))), pk_r);
+    }
+    // mask of the children [c0, c1) of a level-(level-1) node that the packet cannot prune; `skip` is left out
+    __device__ __forceinline__ unsigned family_mask(int level, int c0, int c1, int skip) {
+        const float reach = packet_reach();
+        const int cand = c0 + (int)(threadIdx.x & 31);
+        bool hit = false;
+        if (cand < c1 && cand != skip) hit = !(__fsqrt_rd(node_lb(pk_c, &tv.boxes[tl.off[level] + cand], eps)) > reach);
+        ++n_tests;
+        return __ballot_sync(0xffffffffu, hit);
+    }
+    // climb from a leaf (one of whose centroids was keyed into `cell`): at every level only the sibling subtrees are searched
+    __device__ __forceinline__ void from_leaf(int node, unsigned cell) {
         leaf(node);
+        const int shared = shared_levels(cell);
         for (int level = tl.n_levels - 1; level >= 1; --level) {
+            if (all(!active || (level <= shared && cube_clear(level)))) return;
             const int p = __ldg(&tv.par[tl.off[level] + node]) & 0x7fffffff;
             const int *cb = tv.cbegin + tl.cb_off[level - 1] + p;
             const int c0 = __ldg(cb), c1 = __ldg(cb + 1);
-            for (int sib = c0; sib < c1; ++sib)
-                if (sib != node) dfs_subtree(level, sib);
+            if constexpr (PACKET) {
+                // all (<= 8) siblings in one step: lane j bounds sibling j for the whole packet
+                unsigned todo = family_mask(level, c0, c1, node) & 0xffu;
+                while (todo) { const int j = __ffs(todo) - 1; todo &= todo - 1; dfs_subtree(level, c0 + j); }
+            } else {
+                for (int sib = c0; sib < c1; ++sib)
+                    if (sib != node) dfs_subtree(level, sib);
+            }
             node = p;
         }
     }
     // warm query: start at the seed's leaf
-    __device__ __forceinline__ void from_seed(int seed_slot) { from_leaf(__ldg(&tv.leaf_of_slot[seed_slot])); }
+    __device__ __forceinline__ void from_seed(int seed_slot) { from_leaf(__ldg(&tv.leaf_of_slot[seed_slot]), __ldg(&tv.fcells[seed_slot])); }
     // cold query: greedy descent (always into the child with the smallest bound) to get a first candidate, then the
     // exact search from the leaf it reached
-    __device__ __forceinline__ void top_down() {
+    __device__ __forceinline__ int greedy_leaf() {
         int node = 0;
         for (int level = 0; level < tl.n_levels - 1; ++level) {
             const int *cb = tv.cbegin + tl.cb_off[level] + node;
             const int c0 = __ldg(cb), c1 = __ldg(cb + 1);
             float bl = FLT_MAX * 2.0f;
             for (int ch = c0; ch < c1; ++ch) {
-                const float l = node_score(q, &tv.boxes[tl.off[level + 1] + ch], eps);
+                float l = node_score(q, &tv.boxes[tl.off[level + 1] + ch], eps);
+                if constexpr (PACKET) l = __shfl_sync(0xffffffffu, l, lead);
                 ++n_tests;
                 if (l < bl) { bl = l; node = ch; }
             }
         }
-        from_leaf(node);
+        return node;
+    }
+    __device__ __forceinline__ void top_down() {
+        const int node = greedy_leaf();
+        from_leaf(node, __ldg(&tv.fcells[__ldg(&tv.cbegin[tl.cb_off[tl.n_levels - 1] + node])]));
     }
 };
 
@@ -265,7 +357,35 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
     if constexpr (F64) q.set(xd, yd, zd);
     else { q.x = x; q.y = y; q.z = z; }
-    Traversal<decltype(q)> tr(q, best, a.tv, a.tl, eps);
+#if NW_PACKET
+    Traversal<decltype(q), true> tr(q, best, a.tv, a.tl, eps, a.st->cell_escape);
+    tr.active = active;
+#ifdef NW_LEVEL_STATS
+    tr.dbg = a.st;
+#endif
+    int seed = active ? a.slot[i] : -1;
+    const unsigned alive = __ballot_sync(0xffffffffu, active);
+    if (alive) {                                             // warp-uniform
+        // The packet climbs from ONE leaf.  Lanes with a seed of their own first take its exact distance as their
+        // bound; lanes without (first iteration after an upload: k_seed_leaders / k_seed_from_feet may have covered
+        // only some) borrow the packet's.  If no lane has one, the first lane's query picks a leaf by greedy descent.
+        const unsigned warm = __ballot_sync(0xffffffffu, active && seed >= 0);
+        int start;
+        if (warm) start = __shfl_sync(0xffffffffu, seed, __ffs(warm) - 1);
+        else {
+            tr.lead = __ffs(alive) - 1;
+            start = __ldg(&a.tv.cbegin[a.tl.cb_off[a.tl.n_levels - 1] + tr.greedy_leaf()]);
+        }
+        if (active && tr.best.slot < 0) {
+            if (seed < 0) seed = start;
+            const float4 c = __ldg(&a.tv.cent[seed]);
+            tr.best.offer(tr.q.d2(c), seed, __float_as_int(c.w));
+        }
+        tr.set_packet_centre(__ffs(alive) - 1);
+        tr.from_seed(start);
+    }
+#else
+    Traversal<decltype(q)> tr(q, best, a.tv, a.tl, eps, a.st->cell_escape);
 #ifdef NW_LEVEL_STATS
     tr.dbg = a.st;
 #endif
@@ -291,14 +411,26 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
         tr.best.offer(tr.q.d2(c), seed, __float_as_int(c.w));
         tr.from_seed(seed);
     }
+#endif
     best = tr.best;
     // traversal statistics (one atomic per warp and counter)
-    const unsigned t = __reduce_add_sync(0xffffffffu, tr.n_tests), l = __reduce_add_sync(0xffffffffu, tr.n_leaves),
+    const unsigned t = __reduce_add_sync(0xffffffffu, active ? tr.n_tests : 0u), l = __reduce_add_sync(0xffffffffu, active ? tr.n_leaves : 0u),
                    e = __reduce_add_sync(0xffffffffu, tr.n_exact), m = __reduce_max_sync(0xffffffffu, tr.n_tests);
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&a.st->trav[0], (unsigned long long)t); atomicAdd(&a.st->trav[1], (unsigned long long)l);
         atomicAdd(&a.st->trav[2], (unsigned long long)e); atomicMax(&a.st->trav[3], (unsigned long long)m);
+#ifdef NW_LEVEL_STATS
+        atomicAdd(&a.st->lvl_tests[31], 32ull * m);          // lane slots a warp pays for: 32 x its slowest lane
+#endif
     }
+#ifdef NW_LEVEL_STATS
+    if (active) {                                            // histogram of node tests per point, log2 buckets from 16
+        int b = 0;
+        while (b < 10 && (16u << b) <= tr.n_tests) ++b;
+        atomicAdd(&a.st->lvl_pass[16 + b], 1ull);
+        atomicAdd(&a.st->lvl_tests[16 + b], (unsigned long long)tr.n_tests);
+    }
+#endif
 }
 
 // Cold-start pre-pass: the first point of every 32 (= lane 0 of each warp of k_sweep1) gets an APPROXIMATE nearest
@@ -316,7 +448,7 @@ __global__ void __launch_bounds__(128) k_seed_leaders(const __grid_constant__ Sw
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
     if constexpr (F64) q.set(a.px64[i], a.py64[i], a.pz64[i]);
     else { q.x = x; q.y = y; q.z = z; }
-    Traversal<decltype(q)> tr(q, best, a.tv, a.tl, eps);
+    Traversal<decltype(q)> tr(q, best, a.tv, a.tl, eps, a.st->cell_escape);
     tr.budget = 512;
     tr.top_down();
     a.slot[i] = tr.best.slot;     // >= 0: the first descent always reaches a leaf before the budget can run out
@@ -373,7 +505,7 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
     QueryF32 q;
     q.x = x; q.y = y; q.z = z;
-    Traversal<QueryF32> tr(q, best, a.tv, a.tl, eps);
+    Traversal<QueryF32> tr(q, best, a.tv, a.tl, eps, a.st->cell_escape);
     const int s1 = min(lo, a.F - 1), s0 = max(s1 - 1, 0);
     { const float4 c = a.tv.cent[s0]; tr.best.offer(q.d2(c), s0, __float_as_int(c.w)); }
     { const float4 c = a.tv.cent[s1]; tr.best.offer(q.d2(c), s1, __float_as_int(c.w)); }
@@ -383,8 +515,11 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
 }
 
 // MODE 0: nearest face + weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
+#ifndef NW_S1_MINB
+#define NW_S1_MINB 12     // measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 -- the packet walk is a dependent chain, occupancy hides it
+#endif
 template <bool F64, int MODE>
-__global__ void __launch_bounds__(128) k_sweep1(const __grid_constant__ Sweep1Args a) {
+__global__ void __launch_bounds__(128, NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
     if (MODE == 1 && a.st->stop) return;
 
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -713,6 +848,10 @@ static Sweep1Args make_args(nw_ctx *h) {
     a.w0 = h->w0; a.w1 = h->w1; a.w2 = h->w2; a.rx = h->rx; a.ry = h->ry; a.rz = h->rz;
     a.posq = h->posq; a.sfaces = h->sfaces; a.tl = h->tl; a.F = h->F;
     a.tv.cent = h->cent; a.tv.boxes = h->boxes; a.tv.par = h->par; a.tv.cbegin = h->cbegin; a.tv.leaf_of_slot = h->leaf_of_slot;
+    a.tv.fcells = h->fcells; a.tv.grid_lo = make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]); a.tv.grid_inv = h->key_inv;
+    a.tv.grid_cellw = h->key_inv > 0.f ? 1.f / h->key_inv : 0.f;
+    static const bool no_clear = getenv("NW_NO_CELL_CLEARANCE") != nullptr;      // A/B switch for measurements
+    if (no_clear) a.tv.grid_inv = 0.f;
     a.acc = h->acc; a.st = h->st;
     return a;
 }

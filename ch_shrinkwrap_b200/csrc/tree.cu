@@ -103,23 +103,26 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {
 }
 
 __global__ void k_face_keys(const int *__restrict__ faces, const float4 *__restrict__ pos, int F, float3 lo, float inv,
-                            unsigned *__restrict__ keys, int *__restrict__ idx) {
+                            unsigned *__restrict__ keys, int *__restrict__ idx, unsigned *__restrict__ cells) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     float3 c = centroid_f32(pos[faces[3 * f]], pos[faces[3 * f + 1]], pos[faces[3 * f + 2]]);
     unsigned qx = (unsigned)fminf(fmaxf((c.x - lo.x) * inv, 0.f), 1023.f);
     unsigned qy = (unsigned)fminf(fmaxf((c.y - lo.y) * inv, 0.f), 1023.f);
     unsigned qz = (unsigned)fminf(fmaxf((c.z - lo.z) * inv, 0.f), 1023.f);
+    cells[f] = qx | (qy << 10) | (qz << 20);
     hilbert_axes_to_transpose(qx, qy, qz, 10);
     keys[f] = (spread10(qx) << 2) | (spread10(qy) << 1) | spread10(qz);
     idx[f] = f;
 }
 
-__global__ void k_sorted_faces(const int *__restrict__ faces, const int *__restrict__ order, int F, int4 *__restrict__ sfaces) {
+__global__ void k_sorted_faces(const int *__restrict__ faces, const int *__restrict__ order, int F, int4 *__restrict__ sfaces,
+                               const unsigned *__restrict__ cells, unsigned *__restrict__ fcells) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= F) return;
     int f = order[i];
     sfaces[i] = make_int4(faces[3 * f], faces[3 * f + 1], faces[3 * f + 2], f);
+    fcells[i] = cells[f];
 }
 
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -197,12 +200,26 @@ __global__ void k_copy_minus1(const int *__restrict__ id, int F, int *__restrict
 }
 
 // centroids at the current f, in sorted order
-__global__ void k_refit_centroids(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F, float4 *__restrict__ cent) {
+// Also measures how far (L-infinity, grid units, evaluated with the operations of k_face_keys) any centroid now lies
+// outside the grid cell it was keyed into at upload: the slack of the cell-clearance early-out of the search (sweep.cu).
+__global__ void k_refit_centroids(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F, float4 *__restrict__ cent,
+                                  const unsigned *__restrict__ fcells, float3 lo, float inv, SolverState *st) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= F) return;
-    const int4 sf = sfaces[i];
-    const float3 cc = centroid_f32(pos[sf.x], pos[sf.y], pos[sf.z]);
-    cent[i] = make_float4(cc.x, cc.y, cc.z, __int_as_float(sf.w));
+    float esc = 0.f;
+    if (i < F) {
+        const int4 sf = sfaces[i];
+        const float3 cc = centroid_f32(pos[sf.x], pos[sf.y], pos[sf.z]);
+        cent[i] = make_float4(cc.x, cc.y, cc.z, __int_as_float(sf.w));
+        const unsigned cell = fcells[i];
+        const float gx = (cc.x - lo.x) * inv, gy = (cc.y - lo.y) * inv, gz = (cc.z - lo.z) * inv;
+        const float cx = (float)(cell & 1023u), cy = (float)((cell >> 10) & 1023u), cz = (float)(cell >> 20);
+        // the last cell of an axis also holds everything that was clamped into it
+        esc = fmaxf(fmaxf(fmaxf(cx - gx, cx == 1023.f ? 0.f : gx - (cx + 1.f)), fmaxf(cy - gy, cy == 1023.f ? 0.f : gy - (cy + 1.f))),
+                    fmaxf(fmaxf(cz - gz, cz == 1023.f ? 0.f : gz - (cz + 1.f)), 0.f));
+        if (!(esc >= 0.f)) esc = __int_as_float(0x7f800000);      // NaN positions: no early-outs
+    }
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(esc));    // non-negative floats order like their bits
+    if ((threadIdx.x & 31) == 0 && m) atomicMax((unsigned *)&st->cell_escape, m);
 }
 
 // warp-level "sum over lanes with the same key" for floats (build time only): every lane returns its group's sum
@@ -568,8 +585,14 @@ static int extents_pass(nw_ctx *h) {
     return NW_OK;
 }
 
+static void launch_refit_centroids(nw_ctx *h) {
+    cudaMemsetAsync(&h->st->cell_escape, 0, sizeof(float), h->stream);
+    k_refit_centroids<<<nw_grid(h->F, 256), 256, 0, h->stream>>>(h->sfaces, h->posq, h->F, h->cent, h->fcells,
+                                                                 make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv, h->st);
+}
+
 int nw_tree_refit(nw_ctx *h) {
-    k_refit_centroids<<<nw_grid(h->F, 256), 256, 0, h->stream>>>(h->sfaces, h->posq, h->F, h->cent);
+    launch_refit_centroids(h);
     NW_LAUNCH_CHECK();
     return extents_pass(h);
 }
@@ -595,7 +618,9 @@ int nw_tree_build(nw_ctx *h) {
     float inv = (ext > 0.f && ext < FLT_MAX) ? 1023.f / ext : 0.f;
     NW_CHECK(nw_alloc(h, &keys, (size_t)F)); NW_CHECK(nw_alloc(h, &keys2, (size_t)F));
     NW_CHECK(nw_alloc(h, &idx, (size_t)F)); NW_CHECK(nw_alloc(h, &order, (size_t)F));
-    k_face_keys<<<nw_grid(F, B), B, 0, s>>>(h->faces, h->posq, F, make_float3(lo[0], lo[1], lo[2]), inv, keys, idx);
+    unsigned *&cells = h->tb_u2;
+    NW_CHECK(nw_alloc(h, &cells, (size_t)F)); NW_CHECK(nw_alloc(h, &h->fcells, (size_t)F));
+    k_face_keys<<<nw_grid(F, B), B, 0, s>>>(h->faces, h->posq, F, make_float3(lo[0], lo[1], lo[2]), inv, keys, idx, cells);
     size_t tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, keys2, idx, order, F, 0, 30, s);
     if (tmp > h->cub_tmp_bytes) { NW_CHECK(nw_alloc(h, (char **)&h->cub_tmp, tmp)); h->cub_tmp_bytes = tmp; }
@@ -603,7 +628,7 @@ int nw_tree_build(nw_ctx *h) {
     NW_CHECK(nw_alloc(h, &h->fkeys, (size_t)F));
     NW_CUDA(cudaMemcpyAsync(h->fkeys, keys2, sizeof(unsigned) * F, cudaMemcpyDeviceToDevice, s));
     h->key_lo[0] = lo[0]; h->key_lo[1] = lo[1]; h->key_lo[2] = lo[2]; h->key_inv = inv;
-    k_sorted_faces<<<nw_grid(F, B), B, 0, s>>>(h->faces, order, F, h->sfaces);
+    k_sorted_faces<<<nw_grid(F, B), B, 0, s>>>(h->faces, order, F, h->sfaces, cells, h->fcells);
     h->launches += 7;
     trace.mark("keys + sort");
 
@@ -661,7 +686,7 @@ int nw_tree_build(nw_ctx *h) {
     }
     trace.mark("level tables");
     // ---- frames (fixed for the block), first extents, sphere fits, extents again (now with the shell radii)
-    k_refit_centroids<<<nw_grid(F, B), B, 0, s>>>(h->sfaces, h->posq, F, h->cent);
+    launch_refit_centroids(h);
     NW_LAUNCH_CHECK();
     NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * NW_NMOM * total, s));
     if (kL >= 1) {
