@@ -117,6 +117,7 @@ struct nw_ctx {
     bool feet_valid = false;
     unsigned *fkeys = nullptr;                   // sorted Hilbert keys of the face centroids at upload time
     float key_lo[3] = {0, 0, 0}, key_inv = 0.f;  // quantisation used for those keys
+    int *parent_g = nullptr; int2 *kids = nullptr;  // the same tree addressed by global node ids (what the search walks)
     unsigned *fcells = nullptr;                  // per sorted slot: grid cell of the centroid at upload time, x | y << 10 | z << 20
     // ---- solver vectors ----
     unsigned long long *acc = nullptr;           // (M,4) int64 fixed point: AH res xyz, AH 1

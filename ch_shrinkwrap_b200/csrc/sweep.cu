@@ -62,6 +62,9 @@ struct QueryF64 {
     }
 };
 
+#if NW_SHELL
+#error "NW_SHELL (spherical-shell bound, a measured dead end) predates the parent link stored in Box::d.w"
+#endif
 #ifndef NW_PACKET
 #define NW_PACKET 1      // 1: warp-packet search in k_sweep1 (see Traversal); 0: one private search per lane
 #endif
@@ -83,7 +86,7 @@ struct Nearest {
 // orthonormal only to float32 accuracy).  A node is skipped only if this bound exceeds the best exact fp64 distance,
 // so skipping can never change the answer.
 template <typename Q>
-__device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps) {
+__device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps, int *link = nullptr) {
     const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
     const float x = q.fx(), y = q.fy(), z = q.fz();
 #if NW_SHELL
@@ -91,6 +94,7 @@ __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp,
 #else
     const float4 d4 = __ldg(&bp->d);                 // without the shell the fourth quarter of the node stores t1
     const float3 t1 = make_float3(d4.x, d4.y, d4.z);
+    if (link) *link = __float_as_int(d4.w);          // ... and first child | last-child flag (k_global_tables)
 #endif
 #if NW_SHELL
     const float t2x = a.y * t1.z - a.z * t1.y, t2y = a.z * t1.x - a.x * t1.z, t2z = a.x * t1.y - a.y * t1.x;
@@ -134,52 +138,47 @@ __device__ __forceinline__ float node_score(const Q &q, const Box *__restrict__ 
 
 // Stackless search of the octree of occupied Hilbert cells (tree.cu).  All state is scalar and held BY VALUE so that it
 // stays in registers (a per-thread stack array, or references to the caller's query, made the compiler spill the whole
-// object to local memory and reload it inside every node test).
+// object to local memory and reload it inside every node test).  Nodes are addressed by ONE global id (levels stored
+// back to back, root = 0, leaves = [leaf0, n_nodes)), so a step needs no per-level offset lookups.
 struct TreeView {
     const float4 *__restrict__ cent;
     const Box *__restrict__ boxes;
-    const int *__restrict__ par;        // parent index | (last child of its parent) << 31
-    const int *__restrict__ cbegin;     // first child (leaf level: first slot), count+1 entries per level
-    const int *__restrict__ leaf_of_slot;
+    const int *__restrict__ parent;     // global id of the parent | (the parent is the last child of its parent) << 31
+    const int2 *__restrict__ kids;      // inner node: {global id of the first child, children}; leaf: {first slot, centroids}
+    const int *__restrict__ leaf_of_slot;   // index of the leaf WITHIN the leaf level
     const unsigned *__restrict__ fcells;   // grid cell (x | y << 10 | z << 20) each sorted centroid was keyed into at upload
     float3 grid_lo;                        // the 1024^3 grid of those keys: g = (p - grid_lo) * grid_inv
     float grid_inv, grid_cellw;            // cells per nm, nm per cell (0 when the mesh has no extent)
+    int leaf0, leaf_level;                 // global id of the first leaf; its level (= number of climb steps to the root)
 };
 
 //
 // PACKET = true: the 32 queries of a warp (Hilbert-sorted neighbours, so their searches overlap almost completely) walk
-// the tree TOGETHER: one shared (level, node) cursor, a node is entered if ANY lane cannot prune it, every lane keeps
-// its own best and prunes with its own bound.  Each lane still sees every node it could not prune itself, so the
-// result per lane is exactly that of a private search; what changes is that the warp never diverges (node data are
-// warp-uniform broadcast loads) and pays for the union of the lanes' node sets instead of 32 interleaved private walks.
-// All 32 lanes must call the methods (inactive lanes with active = false).
+// the tree TOGETHER: one shared cursor, a node is entered if ANY lane cannot prune it, every lane keeps its own best
+// and prunes with its own bound.  Each lane still sees every node it could not prune itself, so the result per lane is
+// exactly that of a private search; what changes is that the warp never diverges (node data are warp-uniform
+// broadcast loads) and pays for the union of the lanes' node sets instead of 32 interleaved private walks.
+// All 32 lanes must call the methods; lanes past the end of the array are constructed with active_ = false, which
+// gives them a bound no node can satisfy (no branch on `active` inside the walk).
 template <typename Q, bool PACKET = false>
 struct Traversal {
     Q q;
     Nearest best;
-    bool active = true;            // packet mode: lanes past the end of the array take part in the votes only
+    bool active;
     int lead = 0;                  // packet mode: lane whose query steers the greedy descent of top_down()
+    __device__ __forceinline__ bool any(bool p) const { if constexpr (PACKET) return __any_sync(0xffffffffu, p); else return p; }
+    __device__ __forceinline__ bool all(bool p) const { if constexpr (PACKET) return __all_sync(0xffffffffu, p); else return p; }
     // packet mode: one lane's query as the packet's centre and the largest distance of any lane's query from it.  A box
     // at distance D from the centre is at least D - pk_r from every lane, so ONE evaluation settles a node for the
     // whole packet -- which lets the lanes test DIFFERENT nodes in the same step (all siblings of a level at once).
     QueryF32 pk_c;
     float pk_r = 0.f;
-    __device__ __forceinline__ void set_packet_centre(int lane) {
-        pk_c.x = __shfl_sync(0xffffffffu, q.fx(), lane); pk_c.y = __shfl_sync(0xffffffffu, q.fy(), lane); pk_c.z = __shfl_sync(0xffffffffu, q.fz(), lane);
-        const float dx = q.fx() - pk_c.x, dy = q.fy() - pk_c.y, dz = q.fz() - pk_c.z;
-        // rounded up, plus the float32 rounding of a float64 query (eps is 8 ulp of the coordinates)
-        float r = active ? __fadd_ru(__fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz))), eps) : 0.f;
-        if (!(r >= 0.f)) r = __int_as_float(0x7f800000);                       // NaN query: the prefilter never prunes
-        pk_r = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(r)));
-    }
-    __device__ __forceinline__ bool any(bool p) const { if constexpr (PACKET) return __any_sync(0xffffffffu, p); else return p; }
-    __device__ __forceinline__ bool all(bool p) const { if constexpr (PACKET) return __all_sync(0xffffffffu, p); else return p; }
     TreeView tv;
-    const TreeLevels &tl;          // lives in the kernel's __grid_constant__ parameter space (LDC with a dynamic index)
     float eps;
     unsigned n_tests = 0, n_leaves = 0, n_exact = 0;
 #ifdef NW_LEVEL_STATS
     SolverState *dbg = nullptr;
+    const TreeLevels *dbg_tl = nullptr;
 #endif
     unsigned budget = 0xffffffffu;   // seeds only: stop refining after this many node tests (the result is then approximate)
     // Cell clearance.  A level-k node holds exactly the centroids keyed into one aligned cube of 2^(10-k) grid cells.
@@ -190,10 +189,19 @@ struct Traversal {
     float gx, gy, gz;                // query in grid units; gx < 0: outside the grid / no grid -> no early-out
     float escape;
 
-    __device__ __forceinline__ Traversal(const Q &q_, const Nearest &b_, const TreeView &tv_, const TreeLevels &tl_, float eps_, float escape_)
-        : q(q_), best(b_), tv(tv_), tl(tl_), eps(eps_), escape(escape_) {
+    __device__ __forceinline__ Traversal(const Q &q_, const Nearest &b_, const TreeView &tv_, float eps_, float escape_, bool active_ = true)
+        : q(q_), best(b_), active(active_), tv(tv_), eps(eps_), escape(escape_) {
+        if (!active) best.ub = -1.f;                                           // every bound is >= 0
         gx = (q.fx() - tv.grid_lo.x) * tv.grid_inv; gy = (q.fy() - tv.grid_lo.y) * tv.grid_inv; gz = (q.fz() - tv.grid_lo.z) * tv.grid_inv;
         if (!(gx >= 0.f && gx < 1024.f && gy >= 0.f && gy < 1024.f && gz >= 0.f && gz < 1024.f && tv.grid_inv > 0.f && escape < 1024.f)) gx = -1.f;
+    }
+    __device__ __forceinline__ void set_packet_centre(int lane) {
+        pk_c.x = __shfl_sync(0xffffffffu, q.fx(), lane); pk_c.y = __shfl_sync(0xffffffffu, q.fy(), lane); pk_c.z = __shfl_sync(0xffffffffu, q.fz(), lane);
+        const float dx = q.fx() - pk_c.x, dy = q.fy() - pk_c.y, dz = q.fz() - pk_c.z;
+        // rounded up, plus the float32 rounding of a float64 query (eps is 8 ulp of the coordinates)
+        float r = active ? __fadd_ru(__fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz))), eps) : 0.f;
+        if (!(r >= 0.f)) r = __int_as_float(0x7f800000);                       // NaN query: the prefilter never prunes
+        pk_r = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(r)));
     }
     // deepest level whose cube around `cell` also contains the query
     __device__ __forceinline__ int shared_levels(unsigned cell) const {
@@ -214,38 +222,44 @@ struct Traversal {
         return m > 0.f && __fmul_rd(__fmul_rd(m, m), 0.99999f) > best.ub;
     }
 
-    __device__ __forceinline__ void leaf(int idx) {
-        const int *cb = tv.cbegin + tl.cb_off[tl.n_levels - 1] + idx;
-        const int s0 = __ldg(cb), s1 = __ldg(cb + 1);
+    __device__ __forceinline__ void leaf(int node) {
+        const int2 k = __ldg(&tv.kids[node]);
         ++n_leaves;
-        for (int s = s0; s < s1; ++s) {
+        for (int s = k.x; s < k.x + k.y; ++s) {
             const float4 c = __ldg(&tv.cent[s]);
-            if (active && q.lb_box(c, c) <= best.ub) { ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
+            if (q.lb_box(c, c) <= best.ub) { ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
         }
     }
-    // Depth-first search of the subtree rooted at node I of level L.  Children and next siblings come from two small
-    // integer tables, so no per-thread stack is needed.  Children are visited in index (= Hilbert) order: with a seed
-    // the bound is already (nearly) exact, so nearest-first ordering would buy nothing.
-    __device__ __forceinline__ void dfs_subtree(int L, int I) {
-        const int leafL = tl.n_levels - 1;
-        int level = L, idx = I;
+#ifdef NW_LEVEL_STATS
+    __device__ __forceinline__ void count_test(int node, bool pass) {
+        if (!dbg || !active) return;
+        int level = 0;
+        while (level + 1 < dbg_tl->n_levels && node >= dbg_tl->off[level + 1]) ++level;
+        atomicAdd(&dbg->lvl_tests[level], 1ull);
+        if (pass) atomicAdd(&dbg->lvl_pass[level], 1ull);
+    }
+#endif
+    // Depth-first search of the subtree rooted at node I.  First child and next sibling come from two small integer
+    // tables, so no per-thread stack is needed.  Children are visited in index (= Hilbert) order: with a seed the bound
+    // is already (nearly) exact, so nearest-first ordering would buy nothing.
+    __device__ __forceinline__ void dfs_subtree(int I) {
+        int node = I;
         while (true) {
             if (++n_tests > budget) return;
+            int link;                                      // first child | (node is a last child) << 31, stored in the node itself
+            const bool pass = any(node_lb(q, &tv.boxes[node], eps, &link) <= best.ub);
 #ifdef NW_LEVEL_STATS
-            const bool pass_ = any(active && node_lb(q, &tv.boxes[tl.off[level] + idx], eps) <= best.ub);
-            if (dbg && active) { atomicAdd(&dbg->lvl_tests[level], 1ull); if (pass_) atomicAdd(&dbg->lvl_pass[level], 1ull); }
-            if (pass_) {
-#else
-            if (any(active && node_lb(q, &tv.boxes[tl.off[level] + idx], eps) <= best.ub)) {
+            count_test(node, pass);
 #endif
-                if (level == leafL) leaf(idx);
-                else { idx = __ldg(&tv.cbegin[tl.cb_off[level] + idx]); ++level; continue; }
+            if (pass) {
+                if (node >= tv.leaf0) leaf(node);
+                else { node = link & 0x7fffffff; continue; }
             }
             while (true) {
-                if (level == L) return;
-                const int pv = __ldg(&tv.par[tl.off[level] + idx]);
-                if (pv >= 0) { ++idx; break; }            // not the last child: next sibling
-                --level; idx = pv & 0x7fffffff;
+                if (node == I) return;
+                if (link >= 0) { ++node; break; }          // not the last child: next sibling
+                link = __ldg(&tv.parent[node]);            // parent | (parent is a last child) << 31
+                node = link & 0x7fffffff;
             }
         }
     }
@@ -260,12 +274,12 @@ struct Traversal {
         if (!(ubm >= 0.f)) ubm = __int_as_float(0x7f800000);
         return __fadd_ru(__fsqrt_ru(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ubm)))), pk_r);
     }
-    // mask of the children [c0, c1) of a level-(level-1) node that the packet cannot prune; `skip` is left out
-    __device__ __forceinline__ unsigned family_mask(int level, int c0, int c1, int skip) {
+    // mask of the nodes [c0, c0 + n) that the packet cannot prune; `skip` is left out
+    __device__ __forceinline__ unsigned family_mask(int c0, int n, int skip) {
         const float reach = packet_reach();
-        const int cand = c0 + (int)(threadIdx.x & 31);
+        const int j = (int)(threadIdx.x & 31);
         bool hit = false;
-        if (cand < c1 && cand != skip) hit = !(__fsqrt_rd(node_lb(pk_c, &tv.boxes[tl.off[level] + cand], eps)) > reach);
+        if (j < n && c0 + j != skip) hit = !(__fsqrt_rd(node_lb(pk_c, &tv.boxes[c0 + j], eps)) > reach);
         ++n_tests;
         return __ballot_sync(0xffffffffu, hit);
     }
@@ -273,34 +287,31 @@ struct Traversal {
     __device__ __forceinline__ void from_leaf(int node, unsigned cell) {
         leaf(node);
         const int shared = shared_levels(cell);
-        for (int level = tl.n_levels - 1; level >= 1; --level) {
+        for (int level = tv.leaf_level; level >= 1; --level) {
             if (all(!active || (level <= shared && cube_clear(level)))) return;
-            const int p = __ldg(&tv.par[tl.off[level] + node]) & 0x7fffffff;
-            const int *cb = tv.cbegin + tl.cb_off[level - 1] + p;
-            const int c0 = __ldg(cb), c1 = __ldg(cb + 1);
+            const int p = __ldg(&tv.parent[node]) & 0x7fffffff;
+            const int2 k = __ldg(&tv.kids[p]);
             if constexpr (PACKET) {
-                // all (<= 8) siblings in one step: lane j bounds sibling j for the whole packet
-                unsigned todo = family_mask(level, c0, c1, node) & 0xffu;
-                while (todo) { const int j = __ffs(todo) - 1; todo &= todo - 1; dfs_subtree(level, c0 + j); }
+                unsigned todo = family_mask(k.x, k.y, node) & 0xffu;           // an octree node has <= 8 children
+                while (todo) { const int j = __ffs(todo) - 1; todo &= todo - 1; dfs_subtree(k.x + j); }
             } else {
-                for (int sib = c0; sib < c1; ++sib)
-                    if (sib != node) dfs_subtree(level, sib);
+                for (int sib = k.x; sib < k.x + k.y; ++sib)
+                    if (sib != node) dfs_subtree(sib);
             }
             node = p;
         }
     }
     // warm query: start at the seed's leaf
-    __device__ __forceinline__ void from_seed(int seed_slot) { from_leaf(__ldg(&tv.leaf_of_slot[seed_slot]), __ldg(&tv.fcells[seed_slot])); }
+    __device__ __forceinline__ void from_seed(int seed_slot) { from_leaf(tv.leaf0 + __ldg(&tv.leaf_of_slot[seed_slot]), __ldg(&tv.fcells[seed_slot])); }
     // cold query: greedy descent (always into the child with the smallest bound) to get a first candidate, then the
     // exact search from the leaf it reached
     __device__ __forceinline__ int greedy_leaf() {
         int node = 0;
-        for (int level = 0; level < tl.n_levels - 1; ++level) {
-            const int *cb = tv.cbegin + tl.cb_off[level] + node;
-            const int c0 = __ldg(cb), c1 = __ldg(cb + 1);
+        while (node < tv.leaf0) {
+            const int2 k = __ldg(&tv.kids[node]);
             float bl = FLT_MAX * 2.0f;
-            for (int ch = c0; ch < c1; ++ch) {
-                float l = node_score(q, &tv.boxes[tl.off[level + 1] + ch], eps);
+            for (int ch = k.x; ch < k.x + k.y; ++ch) {
+                float l = node_score(q, &tv.boxes[ch], eps);
                 if constexpr (PACKET) l = __shfl_sync(0xffffffffu, l, lead);
                 ++n_tests;
                 if (l < bl) { bl = l; node = ch; }
@@ -310,7 +321,7 @@ struct Traversal {
     }
     __device__ __forceinline__ void top_down() {
         const int node = greedy_leaf();
-        from_leaf(node, __ldg(&tv.fcells[__ldg(&tv.cbegin[tl.cb_off[tl.n_levels - 1] + node])]));
+        from_leaf(node, __ldg(&tv.fcells[__ldg(&tv.kids[node]).x]));
     }
 };
 
@@ -358,10 +369,9 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
     if constexpr (F64) q.set(xd, yd, zd);
     else { q.x = x; q.y = y; q.z = z; }
 #if NW_PACKET
-    Traversal<decltype(q), true> tr(q, best, a.tv, a.tl, eps, a.st->cell_escape);
-    tr.active = active;
+    Traversal<decltype(q), true> tr(q, best, a.tv, eps, a.st->cell_escape, active);
 #ifdef NW_LEVEL_STATS
-    tr.dbg = a.st;
+    tr.dbg = a.st; tr.dbg_tl = &a.tl;
 #endif
     int seed = active ? a.slot[i] : -1;
     const unsigned alive = __ballot_sync(0xffffffffu, active);
@@ -374,7 +384,7 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
         if (warm) start = __shfl_sync(0xffffffffu, seed, __ffs(warm) - 1);
         else {
             tr.lead = __ffs(alive) - 1;
-            start = __ldg(&a.tv.cbegin[a.tl.cb_off[a.tl.n_levels - 1] + tr.greedy_leaf()]);
+            start = __ldg(&a.tv.kids[tr.greedy_leaf()]).x;
         }
         if (active && tr.best.slot < 0) {
             if (seed < 0) seed = start;
@@ -385,9 +395,9 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
         tr.from_seed(start);
     }
 #else
-    Traversal<decltype(q)> tr(q, best, a.tv, a.tl, eps, a.st->cell_escape);
+    Traversal<decltype(q)> tr(q, best, a.tv, eps, a.st->cell_escape);
 #ifdef NW_LEVEL_STATS
-    tr.dbg = a.st;
+    tr.dbg = a.st; tr.dbg_tl = &a.tl;
 #endif
     int seed = active ? a.slot[i] : 0;
     // Cold start (first iteration after a topology upload): lanes without a seed borrow one from a lane that has it
@@ -448,7 +458,7 @@ __global__ void __launch_bounds__(128) k_seed_leaders(const __grid_constant__ Sw
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
     if constexpr (F64) q.set(a.px64[i], a.py64[i], a.pz64[i]);
     else { q.x = x; q.y = y; q.z = z; }
-    Traversal<decltype(q)> tr(q, best, a.tv, a.tl, eps, a.st->cell_escape);
+    Traversal<decltype(q)> tr(q, best, a.tv, eps, a.st->cell_escape);
     tr.budget = 512;
     tr.top_down();
     a.slot[i] = tr.best.slot;     // >= 0: the first descent always reaches a leaf before the budget can run out
@@ -505,7 +515,7 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
     QueryF32 q;
     q.x = x; q.y = y; q.z = z;
-    Traversal<QueryF32> tr(q, best, a.tv, a.tl, eps, a.st->cell_escape);
+    Traversal<QueryF32> tr(q, best, a.tv, eps, a.st->cell_escape);
     const int s1 = min(lo, a.F - 1), s0 = max(s1 - 1, 0);
     { const float4 c = a.tv.cent[s0]; tr.best.offer(q.d2(c), s0, __float_as_int(c.w)); }
     { const float4 c = a.tv.cent[s1]; tr.best.offer(q.d2(c), s1, __float_as_int(c.w)); }
@@ -516,10 +526,10 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
 
 // MODE 0: nearest face + weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
 #ifndef NW_S1_MINB
-#define NW_S1_MINB 12     // measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 -- the packet walk is a dependent chain, occupancy hides it
+#define NW_S1_MINB 16     // 32 registers, 64 warps per SM.  Measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 before the global-id tables; after them 48 regs 2.47, 40 regs 2.51, 32 regs 2.33 -- the packet walk is a dependent chain, occupancy hides it
 #endif
 template <bool F64, int MODE>
-__global__ void __launch_bounds__(128, NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
+__global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB) : NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
     if (MODE == 1 && a.st->stop) return;
 
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -847,7 +857,8 @@ static Sweep1Args make_args(nw_ctx *h) {
     a.slot = h->slot;
     a.w0 = h->w0; a.w1 = h->w1; a.w2 = h->w2; a.rx = h->rx; a.ry = h->ry; a.rz = h->rz;
     a.posq = h->posq; a.sfaces = h->sfaces; a.tl = h->tl; a.F = h->F;
-    a.tv.cent = h->cent; a.tv.boxes = h->boxes; a.tv.par = h->par; a.tv.cbegin = h->cbegin; a.tv.leaf_of_slot = h->leaf_of_slot;
+    a.tv.cent = h->cent; a.tv.boxes = h->boxes; a.tv.parent = h->parent_g; a.tv.kids = h->kids; a.tv.leaf_of_slot = h->leaf_of_slot;
+    a.tv.leaf_level = h->tl.n_levels - 1; a.tv.leaf0 = h->tl.n_levels > 0 ? h->tl.off[h->tl.n_levels - 1] : 0;
     a.tv.fcells = h->fcells; a.tv.grid_lo = make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]); a.tv.grid_inv = h->key_inv;
     a.tv.grid_cellw = h->key_inv > 0.f ? 1.f / h->key_inv : 0.f;
     static const bool no_clear = getenv("NW_NO_CELL_CLEARANCE") != nullptr;      // A/B switch for measurements

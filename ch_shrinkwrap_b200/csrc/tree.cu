@@ -458,6 +458,28 @@ extern "C" int nw_set_topology_records(nw_ctx *h, const void *vertex_records, co
     return set_topology_impl(h, (const float *)vertex_records, nullptr, faces, nullptr, he_vertex, n_halfedges, nullptr, M, F, he_stride_bytes);
 }
 
+// The per-level tables (local indices, what the build and refit kernels use) rewritten with global node ids for the
+// search:  kids = {first child (global) or first slot, count};  parent_g = global parent | (the PARENT is the last child
+// of ITS parent) << 31, so that popping a level is one load;  and inside the node itself (Box::d.w, free without the
+// shell) first child / first slot | (this node is a last child) << 31 -- what a search step needs next, whether the
+// node is pruned (next sibling or pop) or opened (first child), arrives with the box it has just loaded.
+__global__ void k_global_tables(const int *__restrict__ par, const int *__restrict__ cbegin_level, int count, int off, int off_parent,
+                                int off_child, bool is_leaf_level, int *__restrict__ parent_g, int2 *__restrict__ kids,
+                                Box *__restrict__ boxes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int pv = par[off + i];
+    const int p = (pv & 0x7fffffff) + off_parent;
+    const unsigned parent_last = off ? ((unsigned)par[p] & 0x80000000u) : 0x80000000u;
+    parent_g[off + i] = (int)((unsigned)p | parent_last);
+    const int c0 = cbegin_level[i], c1 = cbegin_level[i + 1];
+    const int first = is_leaf_level ? c0 : off_child + c0;
+    kids[off + i] = make_int2(first, c1 - c0);
+#if !NW_SHELL
+    boxes[off + i].d.w = __int_as_float((int)((unsigned)first | ((unsigned)pv & 0x80000000u)));
+#endif
+}
+
 // NW_TRACE_BUILD=1: wall-clock checkpoints (with a stream sync each) through nw_tree_build, on stderr
 struct BuildTrace {
     bool on; cudaStream_t s; std::chrono::steady_clock::time_point t;
@@ -695,6 +717,12 @@ int nw_tree_build(nw_ctx *h) {
     }
     k_node_frames<<<nw_grid(total, B), B, 0, s>>>(h->boxes, h->node_f, 0, total);
     NW_LAUNCH_CHECK();
+    NW_CHECK(nw_alloc(h, &h->parent_g, room)); NW_CHECK(nw_alloc(h, &h->kids, room));
+    for (int k = 0; k <= kL; ++k) {
+        k_global_tables<<<nw_grid(tl.count[k], B), B, 0, s>>>(h->par, h->cbegin + tl.cb_off[k], tl.count[k], tl.off[k], k ? tl.off[k - 1] : 0,
+                                                              k < kL ? tl.off[k + 1] : 0, k == kL, h->parent_g, h->kids, h->boxes);
+        NW_LAUNCH_CHECK();
+    }
 #if NW_SHELL
     NW_CHECK(extents_pass(h));
     NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * NW_NMOM * total, s));
