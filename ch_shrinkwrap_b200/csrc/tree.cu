@@ -158,12 +158,16 @@ __device__ __forceinline__ void project3(const float3 n, const float4 c, float &
 // histogram of the level at which consecutive keys first differ (-> number of nodes of every level)
 __global__ void k_level_histogram(const unsigned *__restrict__ keys, int F, int *__restrict__ hist) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= F || i == 0) return;
-    const unsigned x = keys[i] ^ keys[i - 1];
-    if (!x) return;
-    const int hb = 31 - __clz(x);                 // highest differing bit, 0..29
-    const int lvl = (29 - hb) / 3 + 1;            // first level whose prefix differs, 1..10
-    atomicAdd(&hist[lvl], 1);
+    int lvl = 0;
+    if (i < F && i > 0) {
+        const unsigned x = keys[i] ^ keys[i - 1];
+        if (x) lvl = (29 - (31 - __clz(x))) / 3 + 1;   // first level whose prefix differs from the predecessor's, 1..10
+    }
+    // one atomic per warp and level instead of one per face (11 hot addresses)
+    for (int k = 1; k <= 10; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, lvl == k);
+        if (m && (threadIdx.x & 31) == 0) atomicAdd(&hist[k], __popc(m));
+    }
 }
 
 __global__ void k_level_flags(const unsigned *__restrict__ keys, int F, int shift, int *__restrict__ flag) {
@@ -315,12 +319,16 @@ __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent
             shell = b->d.z > 0.5f;
 #endif
             project3(make_float3(ba.x, ba.y, ba.z), c, p[0], p[1], p[2]);
+#if NW_SHELL
             const float dx = c.x - bc.y, dy = c.y - bc.z, dz = c.z - bc.w;
             p[3] = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+#else
+            (void)bc;
+#endif
         }
         unsigned mn[4], mx[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < (NW_SHELL ? 4 : 3); ++k) {
             const unsigned lo = finite ? f2u(p[k]) : 0xffffffffu, hi = finite ? f2u(p[k]) : 0u;
             mn[k] = __reduce_min_sync(grp, lo);
             mx[k] = __reduce_max_sync(grp, hi);
