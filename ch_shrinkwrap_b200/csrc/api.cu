@@ -90,7 +90,7 @@ static int upload_state(nw_ctx *h, const SolverState &s0) {
 
 // per-stage CUDA events (only when profiling is switched on)
 static int stage_begin(nw_ctx *h, int stage) {
-    if (!h->profile) return NW_OK;
+    if (!(h->profile & 1)) return NW_OK;
     if (h->ev_used + 2 > h->ev_pool.size()) {
         for (int k = 0; k < 64; ++k) { cudaEvent_t e; NW_CUDA(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
     }
@@ -100,7 +100,7 @@ static int stage_begin(nw_ctx *h, int stage) {
     return NW_OK;
 }
 static int stage_end(nw_ctx *h, int stage) {
-    if (!h->profile) return NW_OK;
+    if (!(h->profile & 1)) return NW_OK;
     NW_CUDA(cudaEventRecord(h->ev_pool[h->ev_used++], h->stream));
     h->stage_launches[stage] += h->launches;
     return NW_OK;

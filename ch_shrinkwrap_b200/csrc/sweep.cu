@@ -160,7 +160,7 @@ struct TreeView {
 // broadcast loads) and pays for the union of the lanes' node sets instead of 32 interleaved private walks.
 // All 32 lanes must call the methods; lanes past the end of the array are constructed with active_ = false, which
 // gives them a bound no node can satisfy (no branch on `active` inside the walk).
-template <typename Q, bool PACKET = false>
+template <typename Q, bool PACKET = false, bool COUNT = true>
 struct Traversal {
     Q q;
     Nearest best;
@@ -171,8 +171,13 @@ struct Traversal {
     // packet mode: one lane's query as the packet's centre and the largest distance of any lane's query from it.  A box
     // at distance D from the centre is at least D - pk_r from every lane, so ONE evaluation settles a node for the
     // whole packet -- which lets the lanes test DIFFERENT nodes in the same step (all siblings of a level at once).
-    QueryF32 pk_c;
     float pk_r = 0.f;
+    int pk_lane = 0;
+    __device__ __forceinline__ QueryF32 packet_centre() const {
+        QueryF32 c;
+        c.x = __shfl_sync(0xffffffffu, q.fx(), pk_lane); c.y = __shfl_sync(0xffffffffu, q.fy(), pk_lane); c.z = __shfl_sync(0xffffffffu, q.fz(), pk_lane);
+        return c;
+    }
     TreeView tv;
     float eps;
     unsigned n_tests = 0, n_leaves = 0, n_exact = 0;
@@ -181,22 +186,26 @@ struct Traversal {
     const TreeLevels *dbg_tl = nullptr;
 #endif
     unsigned budget = 0xffffffffu;   // seeds only: stop refining after this many node tests (the result is then approximate)
+    // COUNT = false (the production sweep): no statistics, no budget -- three registers and three instructions per step
+    __device__ __forceinline__ bool tick() { if constexpr (COUNT) return ++n_tests > budget; else return false; }
     // Cell clearance.  A level-k node holds exactly the centroids keyed into one aligned cube of 2^(10-k) grid cells.
     // Once everything under the level-k ancestor of the seed has been searched, and that cube is the one the query
     // lies in, every other centroid was keyed OUTSIDE the cube; it has since moved at most `escape` cells (L-infinity,
     // k_refit_centroids), so it is at least (distance from the query to the cube's walls - escape) away.  If that
     // exceeds the best distance the climb can stop: the levels above cannot hold anything closer.
-    float gx, gy, gz;                // query in grid units; gx < 0: outside the grid / no grid -> no early-out
-    float escape;
+    // (the query's grid coordinates are recomputed where needed: three registers less in the inner loop)
+    float escape;                    // < 0: no early-out (no grid, or the query lies outside it)
+    __device__ __forceinline__ float grid(float v, float lo) const { return (v - lo) * tv.grid_inv; }
 
     __device__ __forceinline__ Traversal(const Q &q_, const Nearest &b_, const TreeView &tv_, float eps_, float escape_, bool active_ = true)
         : q(q_), best(b_), active(active_), tv(tv_), eps(eps_), escape(escape_) {
         if (!active) best.ub = -1.f;                                           // every bound is >= 0
-        gx = (q.fx() - tv.grid_lo.x) * tv.grid_inv; gy = (q.fy() - tv.grid_lo.y) * tv.grid_inv; gz = (q.fz() - tv.grid_lo.z) * tv.grid_inv;
-        if (!(gx >= 0.f && gx < 1024.f && gy >= 0.f && gy < 1024.f && gz >= 0.f && gz < 1024.f && tv.grid_inv > 0.f && escape < 1024.f)) gx = -1.f;
+        const float gx = grid(q.fx(), tv.grid_lo.x), gy = grid(q.fy(), tv.grid_lo.y), gz = grid(q.fz(), tv.grid_lo.z);
+        if (!(gx >= 0.f && gx < 1024.f && gy >= 0.f && gy < 1024.f && gz >= 0.f && gz < 1024.f && tv.grid_inv > 0.f && escape < 1024.f)) escape = -1.f;
     }
     __device__ __forceinline__ void set_packet_centre(int lane) {
-        pk_c.x = __shfl_sync(0xffffffffu, q.fx(), lane); pk_c.y = __shfl_sync(0xffffffffu, q.fy(), lane); pk_c.z = __shfl_sync(0xffffffffu, q.fz(), lane);
+        pk_lane = lane;
+        const QueryF32 pk_c = packet_centre();
         const float dx = q.fx() - pk_c.x, dy = q.fy() - pk_c.y, dz = q.fz() - pk_c.z;
         // rounded up, plus the float32 rounding of a float64 query (eps is 8 ulp of the coordinates)
         float r = active ? __fadd_ru(__fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz))), eps) : 0.f;
@@ -205,7 +214,8 @@ struct Traversal {
     }
     // deepest level whose cube around `cell` also contains the query
     __device__ __forceinline__ int shared_levels(unsigned cell) const {
-        if (gx < 0.f) return 0;
+        if (escape < 0.f) return 0;
+        const float gx = grid(q.fx(), tv.grid_lo.x), gy = grid(q.fy(), tv.grid_lo.y), gz = grid(q.fz(), tv.grid_lo.z);
         const unsigned d = cell ^ ((unsigned)gx | ((unsigned)gy << 10) | ((unsigned)gz << 20));
         const unsigned m = (d | (d >> 10) | (d >> 20)) & 1023u;       // highest differing bit over the three axes
         return m ? __clz(m) - 22 : 10;
@@ -214,6 +224,7 @@ struct Traversal {
     __device__ __forceinline__ bool cube_clear(int level) const {
         const int s = 10 - level;
         const float w = (float)(1u << s);
+        const float gx = grid(q.fx(), tv.grid_lo.x), gy = grid(q.fy(), tv.grid_lo.y), gz = grid(q.fz(), tv.grid_lo.z);
         const float fx = gx - (float)(((unsigned)gx >> s) << s), fy = gy - (float)(((unsigned)gy >> s) << s),
                     fz = gz - (float)(((unsigned)gz >> s) << s);
         const float cl = fminf(fminf(fminf(fx, w - fx), fminf(fy, w - fy)), fminf(fz, w - fz));
@@ -224,10 +235,10 @@ struct Traversal {
 
     __device__ __forceinline__ void leaf(int node) {
         const int2 k = __ldg(&tv.kids[node]);
-        ++n_leaves;
+        if constexpr (COUNT) ++n_leaves;
         for (int s = k.x; s < k.x + k.y; ++s) {
             const float4 c = __ldg(&tv.cent[s]);
-            if (q.lb_box(c, c) <= best.ub) { ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
+            if (q.lb_box(c, c) <= best.ub) { if constexpr (COUNT) ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
         }
     }
 #ifdef NW_LEVEL_STATS
@@ -245,7 +256,7 @@ struct Traversal {
     __device__ __forceinline__ void dfs_subtree(int I) {
         int node = I;
         while (true) {
-            if (++n_tests > budget) return;
+            if (tick()) return;
             int link;                                      // first child | (node is a last child) << 31, stored in the node itself
             const bool pass = any(node_lb(q, &tv.boxes[node], eps, &link) <= best.ub);
 #ifdef NW_LEVEL_STATS
@@ -277,10 +288,11 @@ struct Traversal {
     // mask of the nodes [c0, c0 + n) that the packet cannot prune; `skip` is left out
     __device__ __forceinline__ unsigned family_mask(int c0, int n, int skip) {
         const float reach = packet_reach();
+        const QueryF32 pk_c = packet_centre();
         const int j = (int)(threadIdx.x & 31);
         bool hit = false;
         if (j < n && c0 + j != skip) hit = !(__fsqrt_rd(node_lb(pk_c, &tv.boxes[c0 + j], eps)) > reach);
-        ++n_tests;
+        if constexpr (COUNT) ++n_tests;
         return __ballot_sync(0xffffffffu, hit);
     }
     // climb from a leaf (one of whose centroids was keyed into `cell`): at every level only the sibling subtrees are searched
@@ -313,7 +325,7 @@ struct Traversal {
             for (int ch = k.x; ch < k.x + k.y; ++ch) {
                 float l = node_score(q, &tv.boxes[ch], eps);
                 if constexpr (PACKET) l = __shfl_sync(0xffffffffu, l, lead);
-                ++n_tests;
+                if constexpr (COUNT) ++n_tests;
                 if (l < bl) { bl = l; node = ch; }
             }
         }
@@ -361,15 +373,18 @@ struct Sweep1Args {
     SolverState *st;
 };
 
-template <bool F64>
-__device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, bool active, float x, float y, float z,
-                                             double xd, double yd, double zd, Nearest &best) {
+#ifndef NW_FN_INLINE
+#define NW_FN_INLINE __noinline__
+#endif
+template <bool F64, bool STATS>
+__device__ NW_FN_INLINE Nearest find_nearest(const Sweep1Args &a, int64_t i, bool active, float x, float y, float z,
+                                             double xd, double yd, double zd, Nearest best) {
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;   // 2^-20 * L1 magnitude
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
     if constexpr (F64) q.set(xd, yd, zd);
     else { q.x = x; q.y = y; q.z = z; }
 #if NW_PACKET
-    Traversal<decltype(q), true> tr(q, best, a.tv, eps, a.st->cell_escape, active);
+    Traversal<decltype(q), true, STATS> tr(q, best, a.tv, eps, a.st->cell_escape, active);
 #ifdef NW_LEVEL_STATS
     tr.dbg = a.st; tr.dbg_tl = &a.tl;
 #endif
@@ -422,8 +437,8 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
         tr.from_seed(seed);
     }
 #endif
-    best = tr.best;
     // traversal statistics (one atomic per warp and counter)
+    if constexpr (STATS) {
     const unsigned t = __reduce_add_sync(0xffffffffu, active ? tr.n_tests : 0u), l = __reduce_add_sync(0xffffffffu, active ? tr.n_leaves : 0u),
                    e = __reduce_add_sync(0xffffffffu, tr.n_exact), m = __reduce_max_sync(0xffffffffu, tr.n_tests);
     if ((threadIdx.x & 31) == 0) {
@@ -441,6 +456,8 @@ __device__ __forceinline__ void find_nearest(const Sweep1Args &a, int64_t i, boo
         atomicAdd(&a.st->lvl_tests[16 + b], (unsigned long long)tr.n_tests);
     }
 #endif
+    }
+    return tr.best;
 }
 
 // Cold-start pre-pass: the first point of every 32 (= lane 0 of each warp of k_sweep1) gets an APPROXIMATE nearest
@@ -528,7 +545,7 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
 #ifndef NW_S1_MINB
 #define NW_S1_MINB 16     // 32 registers, 64 warps per SM.  Measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 before the global-id tables; after them 48 regs 2.47, 40 regs 2.51, 32 regs 2.33 -- the packet walk is a dependent chain, occupancy hides it
 #endif
-template <bool F64, int MODE>
+template <bool F64, int MODE, bool STATS>
 __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB) : NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
     if (MODE == 1 && a.st->stop) return;
 
@@ -546,7 +563,7 @@ __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB)
     best.ub = FLT_MAX * 2.0f;
     best.slot = -1;
     best.face = 0x7fffffff;
-    find_nearest<F64>(a, i, active, x, y, z, xd, yd, zd, best);
+    best = find_nearest<F64, STATS>(a, i, active, x, y, z, xd, yd, zd, best);
     if (active && best.slot < 0) {      // non-finite query: nothing compares; flag it (the reference asserts on NaN) and stay in bounds
         a.st->nan_flag = 1;
         best.slot = 0;
@@ -906,12 +923,18 @@ int nw_launch_sweep1(nw_ctx *h, bool scatter) {
     Sweep1Args a = make_args(h);
     const int G = nw_grid(h->P, B);
     NW_CHECK(nw_launch_seed_leaders(h));
+    // traversal statistics (nw_get_traversal_stats) are collected only when asked for: nw_set_profile(h, 3)
+#ifdef NW_LEVEL_STATS
+    const bool stats = true;
+#else
+    const bool stats = (h->profile & 2) != 0;
+#endif
     if (h->px64) {
-        if (scatter) k_sweep1<true, 1><<<G, B, 0, h->stream>>>(a);
-        else k_sweep1<true, 0><<<G, B, 0, h->stream>>>(a);
+        if (stats) { if (scatter) k_sweep1<true, 1, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, true><<<G, B, 0, h->stream>>>(a); }
+        else { if (scatter) k_sweep1<true, 1, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, false><<<G, B, 0, h->stream>>>(a); }
     } else {
-        if (scatter) k_sweep1<false, 1><<<G, B, 0, h->stream>>>(a);
-        else k_sweep1<false, 0><<<G, B, 0, h->stream>>>(a);
+        if (stats) { if (scatter) k_sweep1<false, 1, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, true><<<G, B, 0, h->stream>>>(a); }
+        else { if (scatter) k_sweep1<false, 1, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false><<<G, B, 0, h->stream>>>(a); }
     }
     NW_LAUNCH_CHECK();
     return NW_OK;

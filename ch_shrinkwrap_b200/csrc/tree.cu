@@ -503,14 +503,14 @@ struct BuildTrace {
 
 // profiling: device time of the compute segments of an upload (the host->device copies between them are not counted)
 static int seg_begin(nw_ctx *h) {
-    if (!h->profile) return NW_OK;
+    if (!(h->profile & 1)) return NW_OK;
     if (!h->ev_seg0) { NW_CUDA(cudaEventCreate(&h->ev_seg0)); NW_CUDA(cudaEventCreate(&h->ev_seg1)); }
     NW_CUDA(cudaEventRecord(h->ev_seg0, h->stream));
     h->stage_launches[9] -= h->launches;
     return NW_OK;
 }
 static int seg_end(nw_ctx *h) {
-    if (!h->profile) return NW_OK;
+    if (!(h->profile & 1)) return NW_OK;
     NW_CUDA(cudaEventRecord(h->ev_seg1, h->stream));
     NW_CUDA(cudaEventSynchronize(h->ev_seg1));
     float ms = 0.f;

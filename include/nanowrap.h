@@ -146,7 +146,7 @@ int nw_neck_candidates(nw_ctx *h, float low, float high, int32_t *idx, int *n);
 /* device-resident single-kernel launches on the handle's stream, for CUDA-event timing */
 int nw_bench_kernel(nw_ctx *h, const char *name, int reps, float *ms_per_launch);
 int nw_sync(nw_ctx *h);
-/* CUDA-event timing on the handle's stream: on = 1 brackets every stage of every iteration inside
+/* CUDA-event timing on the handle's stream: on & 1 brackets every stage of every iteration inside
  * nw_search and the device-side segments of nw_set_topology*.  nw_get_profile returns accumulated ms and kernel
  * launches per stage (10 stages: refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars,
  * solve_update, seed_leaders, topology_build = foot points + record unpack + Hilbert sort + octree tables + frames of
@@ -154,7 +154,8 @@ int nw_sync(nw_ctx *h);
  * last kernel). */
 int nw_set_profile(nw_ctx *h, int on);
 int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms);
-/* nearest-face traversal statistics accumulated since the last nw_search / nw_ncc / nw_bench_kernel state reset:
+/* nearest-face traversal statistics (collected only while nw_set_profile(h, on) has on & 2; the counting variant of the
+ * kernel is slower) accumulated since the last nw_search / nw_ncc / nw_bench_kernel state reset:
  * node bound tests, leaf visits, exact fp64 distance evaluations, largest node-test count of a single point */
 int nw_get_traversal_stats(nw_ctx *h, uint64_t out[4]);
 /* diagnosis: boxes of one level of the centroid pyramid (16 floats per node, layout of csrc/common.cuh: Box) */

@@ -10,7 +10,7 @@ for blk in range(5):
     cg = ShrinkwrapMeshConjGrad(mesh, pts); mesh.cg = cg
     row = []
     for it in range(5):
-        cg._h.call('nw_set_profile', 1)
+        cg._h.call('nw_set_profile', int(os.environ.get('NW_PROFILE', '1')))
         cg.search(pts, lams=[5.0], num_iters=1, sigma_inv=s_inv)
         cg._h.call('nw_get_traversal_stats', st)
         cg._h.call('nw_get_profile', sg, None, ctypes.byref(sm))
@@ -20,7 +20,7 @@ for blk in range(5):
 mesh, pts, sig, cfg = bench.build_workload('c3', 1234)
 for blk in range(5):
     cg = ShrinkwrapMeshConjGrad(mesh, pts); mesh.cg = cg
-    cg._h.call('nw_set_profile', 1)
+    cg._h.call('nw_set_profile', int(os.environ.get('NW_PROFILE', '1')))
     cg.search(pts, lams=[5.0], num_iters=5, sigma_inv=s_inv)
     cg._h.call('nw_get_profile', sg, None, ctypes.byref(sm))
     print('block %d (5 iterations per call): sweep1 %.2f ms/iter, search %.2f ms/iter, stages %s' % (blk, sg[2] / 5, sm.value / 5, [round(x / 5, 3) for x in sg]))

@@ -10,7 +10,7 @@ s_inv = (1.0 / sig.ravel()).astype(np.float32)
 st = (ctypes.c_uint64 * 4)(); sg = (ctypes.c_double * 10)(); sm = ctypes.c_double()
 for blk in range(n // 5):
     cg = ShrinkwrapMeshConjGrad(mesh, pts); mesh.cg = cg
-    cg._h.call('nw_set_profile', 1)
+    cg._h.call('nw_set_profile', int(os.environ.get('NW_PROFILE', '1')))
     cg.search(pts, lams=[5.0], num_iters=5, sigma_inv=s_inv)
     cg._h.call('nw_get_traversal_stats', st)
     cg._h.call('nw_get_profile', sg, None, ctypes.byref(sm))
