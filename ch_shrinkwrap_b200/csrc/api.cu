@@ -188,6 +188,8 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     if (!s.stop)
         for (int it = 0; it < num_iters; ++it) NW_CHECK(enqueue_iteration(h, it, last_step));
     NW_CUDA(cudaEventRecord(h->ev_search1, h->stream));
+    h->pin_fresh = false;
+    NW_CHECK(nw_fetch_positions_async(h));          // the caller wants the result on the host next: no second round trip
     SolverState r;
     NW_CUDA(cudaMemcpyAsync(&r, h->st, sizeof(SolverState), cudaMemcpyDeviceToHost, h->stream));
     NW_CUDA(cudaStreamSynchronize(h->stream));
@@ -208,6 +210,7 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
         for (int k = 0; k < 5; ++k)
             if (dst[k]) NW_CUDA(cudaMemcpy(dst[k], h->hist + (size_t)k * NW_MAX_ITERS, sizeof(double) * r.n_done, cudaMemcpyDeviceToHost));
     }
+    h->pin_fresh = true;
     if (pos_out) NW_CHECK(nw_get_positions(h, pos_out));
     if (r.nan_flag == 2) { h->err = "nw_search: singular subspace matrix (numpy.linalg.LinAlgError in the reference)"; return NW_ERR_NAN; }
     if (r.nan_flag) { h->err = "nw_search: non-finite value in residual / search directions / update"; return NW_ERR_NAN; }

@@ -153,7 +153,7 @@ struct nw_ctx {
     cudaEvent_t ev_search0 = nullptr, ev_search1 = nullptr;
     // nw_set_points temporaries, grow-only like everything else (a fit uploads its points once, a session many times)
     char *sp_pts = nullptr; unsigned long long *sp_k0 = nullptr, *sp_k1 = nullptr; int *sp_idx = nullptr; float *sp_tmp3 = nullptr;
-    char *pin_host = nullptr; size_t pin_bytes = 0;   // pinned read-back staging (nw_get_positions_strided)
+    char *pin_host = nullptr; size_t pin_bytes = 0; bool pin_fresh = false;   // pinned read-back staging (nw_get_positions_strided)
     struct nw_uploader *uploader = nullptr;       // xfer.cu: pinned staging lanes for large host->device copies
     cudaEvent_t ev_seg0 = nullptr, ev_seg1 = nullptr;   // topology_build segments (profiling only)
     double last_search_ms = 0.0;
@@ -215,6 +215,7 @@ static inline void nw_free(T **p) {
 int nw_h2d(nw_ctx *h, void *dst, const void *src, size_t bytes);   // xfer.cu
 int nw_h2d_strided32(nw_ctx *h, void *dst, const void *src, size_t bytes, size_t stride);
 void nw_uploader_destroy(nw_ctx *h);
+int nw_fetch_positions_async(nw_ctx *h);                            // tree.cu
 
 static inline int nw_grid(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
