@@ -256,8 +256,8 @@ struct Traversal {
     __device__ __forceinline__ void dfs_subtree(int I) {
         int node = I;
         while (true) {
-            if (tick()) return;
             int link;                                      // first child | (node is a last child) << 31, stored in the node itself
+            if (tick()) return;
             const bool pass = any(node_lb(q, &tv.boxes[node], eps, &link) <= best.ub);
 #ifdef NW_LEVEL_STATS
             count_test(node, pass);
@@ -904,7 +904,7 @@ int nw_launch_seed_leaders(nw_ctx *h) {
         // too far from the surface for this lookup to pay off (measured slower than the 1-in-32 root search below).
         k_seed_from_feet<<<nw_grid(h->P, B), B, 0, h->stream>>>(a, h->fx, h->fy, h->fz, h->fkeys,
                                                                 make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv,
-                                                                0u);   // measured (again with the packet search): polishing the looked-up seed (budgets 12..48) does not make k_sweep1 any faster
+                                                                0u);   // measured (again with the packet search, also with feet 30 nm off the new surface): polishing the looked-up seed (budgets 12..48) does not make k_sweep1 any faster
         NW_LAUNCH_CHECK();
         h->seeds_cold = false;
         return NW_OK;

@@ -123,3 +123,48 @@ def test_repeated_topology_uploads_reuse_seeds_correctly():
     oc.f = oc.vertices.copy().ravel()
     vo, wo = oc.compute_weights(oc.f)
     assert np.array_equal(vg, vo) and np.array_equal(wg, wo)
+
+
+def test_large_mesh_uploads_and_write_back_take_the_threaded_paths():
+    """> 2 MB uploads go through the pinned multi-lane uploader (the half-edge 'vertex' field gathered out of its 28-byte
+    records) and >= 65 536 vertices are written back into the 120-byte records by several threads; the result must be
+    what the packed single-threaded paths give: positions round-trip bit-exactly, deleted rows untouched."""
+    import ctypes
+    from ch_shrinkwrap_b200 import synth, _lib
+    from ch_shrinkwrap_b200.mesh_conj_grad import ShrinkwrapMeshConjGrad
+    mesh = synth.star_mesh(synth.Sphere(300.0), 82, scale=1.0)          # 10*82^2+2 = 67 242 vertices
+    assert len(mesh._vertices) >= 65536 and mesh._halfedges['vertex'].strides[0] == 28
+    rng = np.random.default_rng(5)
+    pts = (mesh.vertices[::7] * np.float32(0.98) + rng.normal(0, 2.0, (len(mesh.vertices[::7]), 3))).astype(np.float32)   # jitter: no exact NN ties
+    cg = ShrinkwrapMeshConjGrad(mesh, pts)
+    cg._ensure_ready()                                                  # nw_set_points + nw_set_topology_records (strided half-edges)
+    h = cg._h
+    M = len(mesh._vertices)
+    # neighbour table as seen by the device == the host lookup of mesh_conj_grad.py:50-52
+    ref_nb = cg.vertex_neighbors
+    got = np.empty((M, 3), np.float32)
+    h.call('nw_get_positions', _lib.fptr(got))
+    assert np.array_equal(got, mesh._vertices['position'])
+    # strided write-back: mark two rows deleted on the device by re-uploading, then scatter new positions
+    new_pos = (mesh._vertices['position'] * np.float32(1.5)).astype(np.float32)
+    h.call('nw_set_positions', _lib.fptr(np.ascontiguousarray(new_pos)))
+    rec = mesh._vertices.copy()
+    h.call('nw_get_positions_strided', ctypes.c_void_p(rec['position'].ctypes.data), int(rec['position'].strides[0]), 1)
+    assert np.array_equal(rec['position'], new_pos)
+    for name in rec.dtype.names:
+        if name != 'position':
+            assert np.array_equal(rec[name], mesh._vertices[name]), name
+    # the curvature prior reads the device's neighbour table (built from the gathered half-edge field): compare it with
+    # the oracle's, which uses the host lookup
+    import copy
+    from oracle import nanowrap_oracle as orc
+    h.call('nw_set_positions', _lib.fptr(np.ascontiguousarray(mesh._vertices['position'])))
+    oc = orc.OracleConjGrad(copy.deepcopy(mesh), pts)
+    oc.f = oc.vertices.copy().ravel()
+    oc.w = oc.compute_weights(oc.f)
+    oc.res = np.zeros(3 * len(pts), np.float32)
+    fd_o = oc.ncc()
+    cg.compute_weights()
+    fd_g = cg._ncc()
+    assert ref_nb.shape == (M, 20)
+    assert np.allclose(fd_g, fd_o, rtol=0, atol=1e-6 * np.abs(fd_o).max()), np.abs(fd_g - fd_o).max()

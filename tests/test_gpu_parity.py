@@ -72,6 +72,28 @@ def test_nearest_face_far_and_inside_points():
     _weights_parity(mesh, pts)
 
 
+def test_nearest_face_exact_after_the_mesh_moved_without_a_new_upload():
+    """The octree cells are keyed once per topology upload; the cell-clearance early-out of the search has to stay exact
+    when the vertices have since moved by many cell widths (its slack is re-measured at every refit)."""
+    mesh, pts, sig = make_case(n_points=20000, n_geo=9, seed=41)
+    s = (1.0 / sig.ravel()).astype(np.float32)
+    g = _gpu(mesh, pts)
+    g.search(pts, lams=[5.0], num_iters=6, sigma_inv=s)           # moves every vertex; no re-upload afterwards
+    moved = np.abs(mesh._vertices['position'] - make_case(n_points=10, n_geo=9, seed=41)[0]._vertices['position']).max()
+    assert moved > 1.0
+    # shift a patch of vertices by hand as well: a large, local displacement
+    mesh._vertices['position'][:40] += np.float32(15.0)
+    g.compute_weights()                                            # nw_set_positions + refit on the OLD tables
+    face_g, d_g = g.nearest_face.copy(), g.d[:, 0].copy()
+    mo = _clone(mesh)
+    oc = _oracle(mo, pts)
+    oc.f = oc.vertices.copy().ravel()
+    oc.compute_weights(oc.f)
+    assert np.array_equal(d_g, oc.d[:, 0]), 'nearest distances must be bit-identical (fp64)'
+    diff = np.flatnonzero(face_g != oc.nearest)                    # only exact fp64 ties may differ, and they resolve to the lowest index
+    assert len(diff) == 0
+
+
 def test_forward_and_adjoint():
     mesh, pts, sig = make_case(n_points=8000, n_geo=6, seed=14)
     mo, mg = _clone(mesh), _clone(mesh)
