@@ -310,8 +310,14 @@ __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent
     int node = live ? leaf_of_slot[i] : 0;
     const unsigned lane = threadIdx.x & 31;
     for (int l = tl.n_levels - 1; l >= 1; --l) {
-        const int key = live ? node : -1 - (int)lane;
-        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        // lanes that share the node: the slots are sorted by key, so equal nodes are runs of consecutive lanes -- run
+        // heads from one shuffle and a ballot (match_any costs several times more)
+        const int prev = __shfl_up_sync(0xffffffffu, node, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != node || !live);
+        const unsigned upto = 0xffffffffu >> (31 - lane);                       // lanes 0..lane
+        const int first = 31 - __clz(heads & upto);
+        const unsigned above = heads & ~upto;
+        const unsigned grp = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & ~((1u << first) - 1u);
         Box *b = &boxes[tl.off[l] + node];
         float p[4] = {0.f, 0.f, 0.f, 0.f};
         bool shell = false;
@@ -335,10 +341,16 @@ __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent
             mn[k] = __reduce_min_sync(grp, lo);
             mx[k] = __reduce_max_sync(grp, hi);
         }
-        if (live && lane == (unsigned)(__ffs(grp) - 1) && mn[0] <= mx[0]) {
-            atomicMin((int *)&b->a.w, u2ord(mn[0])); atomicMax((int *)&b->b.x, u2ord(mx[0]));
-            atomicMin((int *)&b->b.y, u2ord(mn[1])); atomicMax((int *)&b->b.z, u2ord(mx[1]));
-            atomicMin((int *)&b->b.w, u2ord(mn[2])); atomicMax((int *)&b->c.x, u2ord(mx[2]));
+        if (live && lane == (unsigned)first && mn[0] <= mx[0]) {
+            // the upper levels are hit by thousands of warps and all but the first few change nothing: look first
+            // (an L2 read; a stale value only costs a redundant atomic, the atomics themselves are monotone)
+            const float4 ca = __ldcg(&b->a), cb = __ldcg(&b->b), cc = __ldcg(&b->c);
+            if (u2ord(mn[0]) < __float_as_int(ca.w)) atomicMin((int *)&b->a.w, u2ord(mn[0]));
+            if (u2ord(mx[0]) > __float_as_int(cb.x)) atomicMax((int *)&b->b.x, u2ord(mx[0]));
+            if (u2ord(mn[1]) < __float_as_int(cb.y)) atomicMin((int *)&b->b.y, u2ord(mn[1]));
+            if (u2ord(mx[1]) > __float_as_int(cb.z)) atomicMax((int *)&b->b.z, u2ord(mx[1]));
+            if (u2ord(mn[2]) < __float_as_int(cb.w)) atomicMin((int *)&b->b.w, u2ord(mn[2]));
+            if (u2ord(mx[2]) > __float_as_int(cc.x)) atomicMax((int *)&b->c.x, u2ord(mx[2]));
             if (shell) { atomicMin((int *)&b->d.x, u2ord(mn[3])); atomicMax((int *)&b->d.y, u2ord(mx[3])); }
         }
         if (live) node = par[tl.off[l] + node] & 0x7fffffff;
