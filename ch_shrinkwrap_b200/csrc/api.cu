@@ -74,7 +74,7 @@ extern "C" int nw_sync(nw_ctx *h) {
 
 static int ensure_partials(nw_ctx *h) {
     // layout: [sweep2 partials: n_partials x 16] [mesh partials: ceil(M/256) x 16] [64 doubles of comm staging]
-    const int want = std::max(1, nw_grid(h->P, 256 * 4));
+    const int want = std::max(1, nw_grid(h->P, 256 * NW_S2_PTS));
     const size_t need = (size_t)want * 16 + (size_t)nw_grid(h->M, 256) * 16 + 64;
     NW_CHECK(nw_alloc(h, &h->partials, need));
     h->n_partials = want;

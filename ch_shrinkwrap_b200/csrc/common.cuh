@@ -13,6 +13,9 @@
 #endif
 #define NW_MAX_LEVELS 12
 #define NW_MAX_ITERS 4096
+#ifndef NW_S2_PTS
+#define NW_S2_PTS 4      // k_sweep2: points per thread (their dependent load chains slot -> face -> S overlap); sizes its partials
+#endif
 #define NW_N_STAGES 10   // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders,
                          // topology_build (device side of nw_set_topology*: feet, unpack, Hilbert sort, tables, frames)
 

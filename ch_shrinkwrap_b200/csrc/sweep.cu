@@ -710,9 +710,11 @@ __global__ void __launch_bounds__(256) k_apply_infl(int64_t P, const int *__rest
 // ---- Gram pass -------------------------------------------------------------------------------------
 #define NW_NSUM 11   // hc00 hc01 hc11 hc02 hc12 hc22 gc0 gc1 gc2 c0 res2
 
-#define NW_S2_PTS 4      // points per thread: their dependent load chains (slot -> face -> S) overlap
+#ifndef NW_S2_MINB
+#define NW_S2_MINB 1
+#endif
 
-__global__ void __launch_bounds__(256) k_sweep2(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
+__global__ void __launch_bounds__(256, NW_S2_MINB) k_sweep2(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
                                                 const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
                                                 const float *__restrict__ rx, const float *__restrict__ ry, const float *__restrict__ rz,
                                                 const float4 *__restrict__ Sq,
