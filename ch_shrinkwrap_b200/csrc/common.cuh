@@ -7,10 +7,6 @@
 #include <vector>
 #include "../../include/nanowrap.h"
 
-#ifndef NW_SHELL
-#define NW_SHELL 0       // 1: node bound = oriented box AND spherical shell; 0: oriented box only.
-                         // Measured at C3: the shell removes only ~4 % of the node tests but makes each test ~15 % dearer -> off.
-#endif
 #define NW_MAX_LEVELS 12
 #define NW_MAX_ITERS 4096
 #ifndef NW_S2_PTS
@@ -19,17 +15,15 @@
 #define NW_N_STAGES 10   // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders,
                          // topology_build (device side of nw_set_topology*: feet, unpack, Hilbert sort, tables, frames)
 
-// Node bound = ORIENTED box INTERSECTED with a SPHERICAL SHELL.
-//  * oriented box: a surface patch is thin along its normal and tilted against the coordinate axes, so an axis-aligned
-//    box is mostly empty space.  Axes n (patch normal), t1 = tangent_of(n), t2 = n x t1; one interval per axis.
-//  * spherical shell: a large patch of a curved surface is thick along its mean normal (sagitta L^2/8R) but still thin
-//    around a sphere fitted to it; {x : r_lo <= |x - o| <= r_hi} removes that thickness from the upper tree levels.
-// Both only ever prune: the answer never depends on how tight they are.
+// Node bound = ORIENTED box: a surface patch is thin along its normal and tilted against the coordinate axes, so an
+// axis-aligned box is mostly empty space.  Axes n (patch normal), t1 = tangent_of(n), t2 = n x t1; one interval per axis.
+// It only ever prunes: the answer never depends on how tight it is.  (A spherical shell fitted to each node, which
+// removes the sagitta of large curved patches, was implemented and measured at C3: -4 % node tests, +15 % per test.)
 struct Box {
     float4 a;   // n.x n.y n.z | n-interval min
     float4 b;   // n-interval max | t1-interval min, max | t2-interval min
-    float4 c;   // t2-interval max | shell centre o.x o.y o.z
-    float4 d;   // shell r_lo, r_hi | 1 if the node has a fitted shell | unused
+    float4 c;   // t2-interval max | t2.x t2.y t2.z
+    float4 d;   // t1.x t1.y t1.z | first child (leaf: first slot) | (node is a last child) << 31, as int bits
 };              // 64 B
 
 // orthonormal completion of a unit vector (Duff et al. 2017, branchless): returns t1; t2 = n x t1 everywhere.

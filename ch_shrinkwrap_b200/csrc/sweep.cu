@@ -355,6 +355,19 @@ __device__ __forceinline__ unsigned long long group_sum(unsigned mask, long long
     return (unsigned long long)l0 + ((unsigned long long)l1 << 22) + ((unsigned long long)l2 << 43);
 }
 
+// Same for values known to satisfy |v| < 2^53 (true whenever the accumulators are scaled for >= 256 points: the scale
+// leaves room for P_global terms below 2^61): two limbs, 18 instead of 27 REDUX per vertex -- REDUX issues once per
+// ~29 cycles per scheduler and is what bounds the adjoint (measured: k_apply_AH 0.37 ms, 0.15 ms without the group sums,
+// and the same with or without the atomics that follow).
+__device__ __forceinline__ unsigned long long group_sum2(unsigned mask, long long v) {
+    const unsigned lo = __reduce_add_sync(mask, (unsigned)((unsigned long long)v & 0x7ffffffu));        // 27 bits x 32 lanes
+    const int hi = __reduce_add_sync(mask, (int)(v >> 27));                                            // |.| < 2^26 x 32 lanes
+    return (unsigned long long)(((long long)hi << 27) + (long long)lo);
+}
+__device__ __forceinline__ unsigned long long group_sum_sel(bool two, unsigned mask, long long v) {
+    return two ? group_sum2(mask, v) : group_sum(mask, v);
+}
+
 struct Sweep1Args {
     int64_t P;
     const float *px, *py, *pz;
@@ -364,6 +377,7 @@ struct Sweep1Args {
     float sinv_scalar, wmean;
     int *slot;
     float *w0, *w1, *w2, *rx, *ry, *rz;
+    int two_limbs;                 // 1: every fixed-point term is below 2^53 in magnitude (group_sum2)
     const float4 *posq;
     const int4 *sfaces;
     TreeView tv;
@@ -635,10 +649,11 @@ __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB)
     const int vid[3] = {sf.x, sf.y, sf.z};
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const unsigned long long gx = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
-        const unsigned long long gy = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
-        const unsigned long long gz = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
-        const unsigned long long gi = group_sum(grp, to_fixed(uw[j], sci));
+        const bool two = a.two_limbs != 0 && a.st->acc_shift > -60;
+        const unsigned long long gx = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
+        const unsigned long long gy = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
+        const unsigned long long gz = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
+        const unsigned long long gi = group_sum_sel(two, grp, to_fixed(uw[j], sci));
         if (lead) {
             unsigned long long *dst = a.acc + 4 * (size_t)vid[j];
             atomicAdd(dst + 0, gx); atomicAdd(dst + 1, gy); atomicAdd(dst + 2, gz); atomicAdd(dst + 3, gi);
@@ -666,7 +681,7 @@ __global__ void __launch_bounds__(256) k_apply_A(int64_t P, const int *__restric
 __global__ void __launch_bounds__(256) k_apply_AH(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
                                                   const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
                                                   const float *__restrict__ rx, const float *__restrict__ ry, const float *__restrict__ rz,
-                                                  unsigned long long *__restrict__ acc, int shift) {
+                                                  unsigned long long *__restrict__ acc, int shift, bool two) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool active = i < P;
     int sl = -1 - (int)(threadIdx.x & 31);
@@ -684,9 +699,9 @@ __global__ void __launch_bounds__(256) k_apply_AH(int64_t P, const int *__restri
     const int vid[3] = {sf.x, sf.y, sf.z};
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const unsigned long long gx = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
-        const unsigned long long gy = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
-        const unsigned long long gz = group_sum(grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
+        const unsigned long long gx = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
+        const unsigned long long gy = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
+        const unsigned long long gz = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
         if (lead) {
             unsigned long long *dst = acc + 4 * (size_t)vid[j];
             atomicAdd(dst + 0, gx); atomicAdd(dst + 1, gy); atomicAdd(dst + 2, gz);
@@ -883,6 +898,7 @@ static Sweep1Args make_args(nw_ctx *h) {
     static const bool no_clear = getenv("NW_NO_CELL_CLEARANCE") != nullptr;      // A/B switch for measurements
     if (no_clear) a.tv.grid_inv = 0.f;
     a.acc = h->acc; a.st = h->st;
+    a.two_limbs = h->P_global >= 256 ? 1 : 0;       // k_shift_final leaves 2^61 / P_global of headroom per term (its clamp at -60 only bites for absurd extents)
     return a;
 }
 
@@ -1064,7 +1080,8 @@ int nw_apply_AH_device(nw_ctx *h, const float *rx, const float *ry, const float 
     int shift = std::max(-60, std::min(40, 61 - e));
     NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * h->M, s));
     if (h->P) {
-        k_apply_AH<<<nw_grid(h->P, B), B, 0, s>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, rx, ry, rz, h->acc, shift);
+        k_apply_AH<<<nw_grid(h->P, B), B, 0, s>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, rx, ry, rz, h->acc, shift,
+                                                   h->P_global >= 256 && shift > -60);
         NW_LAUNCH_CHECK();
     }
     NW_CHECK(nw_allreduce_acc(h));
@@ -1147,7 +1164,7 @@ int nw_bench_launch(nw_ctx *h, const char *name) {
         float *yx = h->scratchP, *yy = yx + P, *yz = yy + P;
         k_apply_A<<<nw_grid(P, B), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->posq, yx, yy, yz);
     } else if (n == "apply_AH") {
-        k_apply_AH<<<nw_grid(P, B), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->acc, 20);
+        k_apply_AH<<<nw_grid(P, B), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->acc, 20, h->P_global >= 256);
     } else if (n == "sweep1") {
         return nw_launch_sweep1(h, true);
     } else if (n == "nn_weights") {

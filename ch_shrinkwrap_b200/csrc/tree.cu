@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) k_node_normals(const int4 *__restrict__ s
     }
 }
 
-// frames from the normal sums; intervals empty; shell disabled
+// frames from the normal sums; intervals empty
 __global__ void k_node_frames(Box *__restrict__ boxes, const float *__restrict__ nsum, int first, int count) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
@@ -278,28 +278,20 @@ __global__ void k_node_frames(Box *__restrict__ boxes, const float *__restrict__
     b->a = make_float4(n.x, n.y, n.z, NW_EMPTY_LO);
     b->b = make_float4(NW_EMPTY_HI, NW_EMPTY_LO, NW_EMPTY_HI, NW_EMPTY_LO);
     b->c = make_float4(NW_EMPTY_HI, 0.f, 0.f, 0.f);
-#if NW_SHELL
-    b->d = make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f);
-#else
     const float3 t1 = nw_tangent_of(n.x, n.y, n.z);
     b->c.y = n.y * t1.z - n.z * t1.y; b->c.z = n.z * t1.x - n.x * t1.z; b->c.w = n.x * t1.y - n.y * t1.x;   // t2, exactly as project3 forms it
-    b->d = make_float4(t1.x, t1.y, t1.z, 0.f);       // d.z doubles as the "shell enabled" flag elsewhere: |t1.z| <= 1, and those
-                                                     // code paths are compiled out without the shell
-#endif
+    b->d = make_float4(t1.x, t1.y, t1.z, 0.f);       // d.w: the search's link, written by k_global_tables
 }
 
-// every iteration: intervals back to "empty" (frames and shell centres are kept for the whole block)
+// every iteration: intervals back to "empty" (frames are kept for the whole block)
 __global__ void k_reset_extents(Box *__restrict__ boxes, int first, int count) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
     Box *b = &boxes[first + j];
     b->a.w = NW_EMPTY_LO; b->b.x = NW_EMPTY_HI; b->b.y = NW_EMPTY_LO; b->b.z = NW_EMPTY_HI; b->b.w = NW_EMPTY_LO; b->c.x = NW_EMPTY_HI;
-#if NW_SHELL
-    if (b->d.z > 0.5f) { b->d.x = NW_EMPTY_LO; b->d.y = NW_EMPTY_HI; }
-#endif
 }
 
-// every iteration: each centroid projects onto the frame (and shell centre) of every ancestor; lanes of a warp that
+// every iteration: each centroid projects onto the frame of every ancestor; lanes of a warp that
 // share the node are reduced with REDUX first, then one ordered-int atomic min/max per quantity
 __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent, int F, const int *__restrict__ leaf_of_slot,
                                                  const int *__restrict__ par, Box *__restrict__ boxes, TreeLevels tl) {
@@ -319,24 +311,14 @@ __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent
         const unsigned above = heads & ~upto;
         const unsigned grp = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & ~((1u << first) - 1u);
         Box *b = &boxes[tl.off[l] + node];
-        float p[4] = {0.f, 0.f, 0.f, 0.f};
-        bool shell = false;
+        float p[3] = {0.f, 0.f, 0.f};
         if (live) {
-            const float4 ba = b->a, bc = b->c;
-#if NW_SHELL
-            shell = b->d.z > 0.5f;
-#endif
+            const float4 ba = b->a;
             project3(make_float3(ba.x, ba.y, ba.z), c, p[0], p[1], p[2]);
-#if NW_SHELL
-            const float dx = c.x - bc.y, dy = c.y - bc.z, dz = c.z - bc.w;
-            p[3] = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-#else
-            (void)bc;
-#endif
         }
-        unsigned mn[4], mx[4];
+        unsigned mn[3], mx[3];
 #pragma unroll
-        for (int k = 0; k < (NW_SHELL ? 4 : 3); ++k) {
+        for (int k = 0; k < 3; ++k) {
             const unsigned lo = finite ? f2u(p[k]) : 0xffffffffu, hi = finite ? f2u(p[k]) : 0u;
             mn[k] = __reduce_min_sync(grp, lo);
             mx[k] = __reduce_max_sync(grp, hi);
@@ -351,7 +333,6 @@ __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent
             if (u2ord(mx[1]) > __float_as_int(cb.z)) atomicMax((int *)&b->b.z, u2ord(mx[1]));
             if (u2ord(mn[2]) < __float_as_int(cb.w)) atomicMin((int *)&b->b.w, u2ord(mn[2]));
             if (u2ord(mx[2]) > __float_as_int(cc.x)) atomicMax((int *)&b->c.x, u2ord(mx[2]));
-            if (shell) { atomicMin((int *)&b->d.x, u2ord(mn[3])); atomicMax((int *)&b->d.y, u2ord(mx[3])); }
         }
         if (live) node = par[tl.off[l] + node] & 0x7fffffff;
     }
@@ -367,87 +348,9 @@ __global__ void k_box_decode(Box *__restrict__ boxes, int first, int count, cons
     b->a.w = ord2f(__float_as_int(b->a.w)) - w; b->b.x = ord2f(__float_as_int(b->b.x)) + w;
     b->b.y = ord2f(__float_as_int(b->b.y)) - w; b->b.z = ord2f(__float_as_int(b->b.z)) + w;
     b->b.w = ord2f(__float_as_int(b->b.w)) - w; b->c.x = ord2f(__float_as_int(b->c.x)) + w;
-#if NW_SHELL
-    if (b->d.z > 0.5f) { b->d.x = ord2f(__float_as_int(b->d.x)); b->d.y = ord2f(__float_as_int(b->d.y)); }
-#endif
 }
 
-// ---- spherical-shell fit, once per topology upload ---------------------------------------------------------------------
-// Algebraic sphere fit in the node's frame (origin = box centre, coordinates u,v,z):  u^2+v^2+z^2 + A u + B v + C z + E = 0
-// is linear in (A,B,C,E); the 14 moments of its normal equations are summed per node.  (Float atomics are fine here: the
-// fit only decides how tight a pruning bound is, never a result.)
-#define NW_NMOM 14
-__global__ void __launch_bounds__(256) k_shell_moments(const float4 *__restrict__ cent, int F, const int *__restrict__ leaf_of_slot,
-                                                       const int *__restrict__ par, const Box *__restrict__ boxes, TreeLevels tl,
-                                                       float *__restrict__ mom) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < F;
-    const float4 c = live ? cent[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    int node = live ? leaf_of_slot[i] : 0;
-    const unsigned lane = threadIdx.x & 31;
-    for (int l = tl.n_levels - 1; l >= 1; --l) {
-        const int key = live ? node : -1 - (int)lane;
-        const unsigned grp = __match_any_sync(0xffffffffu, key);
-        float m[NW_NMOM];
-#pragma unroll
-        for (int k = 0; k < NW_NMOM; ++k) m[k] = 0.f;
-        if (live) {
-            const Box *b = &boxes[tl.off[l] + node];
-            const float4 ba = b->a, bb = b->b, bc = b->c;
-            float pn, p1, p2;
-            project3(make_float3(ba.x, ba.y, ba.z), c, pn, p1, p2);
-            const float z = pn - 0.5f * (ba.w + bb.x), u = p1 - 0.5f * (bb.y + bb.z), v = p2 - 0.5f * (bb.w + bc.x);
-            const float w = -(u * u + v * v + z * z);
-            m[0] = 1.f; m[1] = u; m[2] = v; m[3] = z; m[4] = u * u; m[5] = u * v; m[6] = u * z; m[7] = v * v; m[8] = v * z;
-            m[9] = z * z; m[10] = w; m[11] = w * u; m[12] = w * v; m[13] = w * z;
-        }
-#pragma unroll
-        for (int k = 0; k < NW_NMOM; ++k) m[k] = group_sumf(grp, m[k]);      // all lanes, always: full-mask shuffles inside
-        if (live && lane == (unsigned)(__ffs(grp) - 1))
-            for (int k = 0; k < NW_NMOM; ++k) atomicAdd(&mom[NW_NMOM * (size_t)(tl.off[l] + node) + k], m[k]);
-        if (live) node = par[tl.off[l] + node] & 0x7fffffff;
-    }
-}
-
-__global__ void k_shell_fit(Box *__restrict__ boxes, const float *__restrict__ mom, int first, int count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    Box *b = &boxes[first + i];
-    const float *m = mom + NW_NMOM * (size_t)(first + i);
-    b->d = make_float4(0.f, FLT_MAX * 2.0f, 0.f, 0.f);
-    const double N = m[0];
-    if (!(N >= 24.0)) return;
-    // normal equations  M x = r  for x = (A, B, C, E), columns (u, v, z, 1)
-    double M[4][5] = {{m[4], m[5], m[6], m[1], m[11]}, {m[5], m[7], m[8], m[2], m[12]}, {m[6], m[8], m[9], m[3], m[13]}, {m[1], m[2], m[3], N, m[10]}};
-    for (int k = 0; k < 4; ++k) {
-        int piv = k;
-        for (int r = k + 1; r < 4; ++r) if (fabs(M[r][k]) > fabs(M[piv][k])) piv = r;
-        if (!(fabs(M[piv][k]) > 1e-9 * fmax(fabs(M[k][k]) + fabs(M[3][3]), 1e-300))) return;      // (near-)planar or degenerate patch
-        if (piv != k) for (int c = 0; c < 5; ++c) { const double t = M[k][c]; M[k][c] = M[piv][c]; M[piv][c] = t; }
-        for (int r = k + 1; r < 4; ++r) {
-            const double f = M[r][k] / M[k][k];
-            for (int c = k; c < 5; ++c) M[r][c] -= f * M[k][c];
-        }
-    }
-    double x[4];
-    for (int r = 3; r >= 0; --r) {
-        double t = M[r][4];
-        for (int c = r + 1; c < 4; ++c) t -= M[r][c] * x[c];
-        x[r] = t / M[r][r];
-    }
-    const double cu = -0.5 * x[0], cv = -0.5 * x[1], cz = -0.5 * x[2];
-    const double rho2 = cu * cu + cv * cv + cz * cz - x[3];
-    if (!(rho2 > 0.0) || !(rho2 <= 4e8)) return;                  // radius above 2e4: a plane for our purposes
-    const float4 ba = b->a, bb = b->b, bc = b->c;
-    const float3 n = make_float3(ba.x, ba.y, ba.z);
-    const float3 t1 = nw_tangent_of(n.x, n.y, n.z);
-    const float3 t2 = make_float3(n.y * t1.z - n.z * t1.y, n.z * t1.x - n.x * t1.z, n.x * t1.y - n.y * t1.x);
-    const double cn = 0.5 * ((double)ba.w + bb.x) + cz, c1 = 0.5 * ((double)bb.y + bb.z) + cu, c2 = 0.5 * ((double)bb.w + bc.x) + cv;
-    b->c.y = (float)(cn * n.x + c1 * t1.x + c2 * t2.x);
-    b->c.z = (float)(cn * n.y + c1 * t1.y + c2 * t2.y);
-    b->c.w = (float)(cn * n.z + c1 * t1.z + c2 * t2.z);
-    b->d = make_float4(0.f, FLT_MAX * 2.0f, 1.f, 0.f);      // enabled; the radius interval is measured by the next refit
-}
+#define NW_NMOM 3        // floats per node of the build scratch (area-weighted normal sum)
 
 inline float ordered_to_float(int v) {
     v = v >= 0 ? v : v ^ 0x7fffffff;
@@ -482,8 +385,7 @@ extern "C" int nw_set_topology_records(nw_ctx *h, const void *vertex_records, co
 
 // The per-level tables (local indices, what the build and refit kernels use) rewritten with global node ids for the
 // search:  kids = {first child (global) or first slot, count};  parent_g = global parent | (the PARENT is the last child
-// of ITS parent) << 31, so that popping a level is one load;  and inside the node itself (Box::d.w, free without the
-// shell) first child / first slot | (this node is a last child) << 31 -- what a search step needs next, whether the
+// of ITS parent) << 31, so that popping a level is one load;  and inside the node itself (Box::d.w) first child / first slot | (this node is a last child) << 31 -- what a search step needs next, whether the
 // node is pruned (next sibling or pop) or opened (first child), arrives with the box it has just loaded.
 __global__ void k_global_tables(const int *__restrict__ par, const int *__restrict__ cbegin_level, int count, int off, int off_parent,
                                 int off_child, bool is_leaf_level, int *__restrict__ parent_g, int2 *__restrict__ kids,
@@ -497,9 +399,7 @@ __global__ void k_global_tables(const int *__restrict__ par, const int *__restri
     const int c0 = cbegin_level[i], c1 = cbegin_level[i + 1];
     const int first = is_leaf_level ? c0 : off_child + c0;
     kids[off + i] = make_int2(first, c1 - c0);
-#if !NW_SHELL
     boxes[off + i].d.w = __int_as_float((int)((unsigned)first | ((unsigned)pv & 0x80000000u)));
-#endif
 }
 
 // NW_TRACE_BUILD=1: wall-clock checkpoints (with a stream sync each) through nw_tree_build, on stderr
@@ -689,7 +589,7 @@ int nw_tree_build(nw_ctx *h) {
     cnt[0] = 1;
     for (int k = 1; k <= 10; ++k) cnt[k] = cnt[k - 1] + hh[k];
     int kL = 1;
-    double occ = 1.5;                                     // mean centroids per leaf cell, at least (measured at C3: 1.5 -> 3.5 ms, 4 -> 3.8 ms, 1 -> 3.6 ms)
+    double occ = 3.0;                                     // mean centroids per leaf cell, at least (measured at C3 with the packet search, blocks 0/1/2 of a fit: 1 -> 17.4/2.45/2.27 ms, 1.5 -> 13.6/2.27/2.19, 3 -> 12.1/2.27/2.09, 6 -> 12.3/2.58/2.45, 12 -> 13.4/2.59/2.43)
     if (const char *e = getenv("NW_LEAF_OCC")) occ = atof(e);
     for (int k = 1; k <= 10; ++k) if ((double)F / cnt[k] >= occ) kL = k;
     TreeLevels &tl = h->tl;
@@ -730,7 +630,7 @@ int nw_tree_build(nw_ctx *h) {
         std::swap(id_cur, id_prev);
     }
     trace.mark("level tables");
-    // ---- frames (fixed for the block), first extents, sphere fits, extents again (now with the shell radii)
+    // ---- frames (fixed for the block), then the first extents
     launch_refit_centroids(h);
     NW_LAUNCH_CHECK();
     NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * NW_NMOM * total, s));
@@ -746,14 +646,6 @@ int nw_tree_build(nw_ctx *h) {
                                                               k < kL ? tl.off[k + 1] : 0, k == kL, h->parent_g, h->kids, h->boxes);
         NW_LAUNCH_CHECK();
     }
-#if NW_SHELL
-    NW_CHECK(extents_pass(h));
-    NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * NW_NMOM * total, s));
-    k_shell_moments<<<nw_grid(F, B), B, 0, s>>>(h->cent, F, h->leaf_of_slot, h->par, h->boxes, tl, h->node_f);
-    NW_LAUNCH_CHECK();
-    k_shell_fit<<<nw_grid(total - tl.off[1], B), B, 0, s>>>(h->boxes, h->node_f, tl.off[1], total - tl.off[1]);
-    NW_LAUNCH_CHECK();
-#endif
     trace.mark("normals + frames");
     NW_CHECK(extents_pass(h));
     trace.mark("extents");
