@@ -10,7 +10,7 @@ namespace {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclInt64 = 4, ncclUint64 = 5, ncclFloat64 = 8 };
+enum { ncclUint8 = 1, ncclInt64 = 4, ncclUint64 = 5, ncclFloat64 = 8 };
 enum { ncclSum = 0 };
 struct NcclApi {
     void *lib = nullptr;
@@ -18,6 +18,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_nccl;
@@ -31,8 +32,9 @@ bool load_nccl(std::string &err) {
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+    g_nccl.Broadcast = (decltype(g_nccl.Broadcast))dlsym(lib, "ncclBroadcast");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.Broadcast) {
         err = "libnccl.so.2 lacks required symbols";
         return false;
     }
@@ -99,6 +101,34 @@ int nw_allreduce_acc(nw_ctx *h) {
     if (h->nranks <= 1) return NW_OK;
     NW_ARG(h->nccl, "communicator not initialised");
     NW_NCCL(g_nccl.AllReduce(h->acc, h->acc, (size_t)4 * h->M, ncclInt64, ncclSum, (ncclComm_t)h->nccl, h->stream));
+    return NW_OK;
+}
+
+// The mesh is replicated: rank 0 uploads it from its host copy and the other ranks receive it over NVLink instead of
+// all of them pulling the same 84 MB through the host at once (measured on 8 GPUs: the ranks left the upload several ms
+// apart, and the first accumulator allreduce of every block waited for the last one -- 1.15 ms per iteration on average
+// for a collective that takes 0.09 ms).  It also makes rank 0's mesh authoritative, so the replicas cannot differ.
+int nw_upload_replicated(nw_ctx *h, void *dst, const void *src, size_t bytes, size_t stride) {
+    if (h->nranks <= 1) return nw_h2d_strided32(h, dst, src, bytes, stride);
+    NW_ARG(h->nccl, "communicator not initialised");
+    if (h->rank == 0) NW_CHECK(nw_h2d_strided32(h, dst, src, bytes, stride));
+    NW_NCCL(g_nccl.Broadcast(dst, dst, bytes, ncclUint8, 0, (ncclComm_t)h->nccl, h->stream));
+    return NW_OK;
+}
+// every rank must be talking about the same mesh: compares a few integers with rank 0's
+int nw_check_replicated(nw_ctx *h, const long long *vals, int n, const char *what) {
+    if (h->nranks <= 1) return NW_OK;
+    NW_ARG(h->nccl && n <= 8, "communicator not initialised");
+    long long *d = (long long *)(h->partials ? (void *)h->partials : nullptr), host[8];
+    long long *tmp = nullptr;
+    if (!d) { NW_CUDA(cudaMalloc((void **)&tmp, sizeof(long long) * 8)); d = tmp; }
+    NW_CUDA(cudaMemcpyAsync(d, vals, sizeof(long long) * n, cudaMemcpyHostToDevice, h->stream));
+    NW_NCCL(g_nccl.Broadcast(d, d, sizeof(long long) * n, ncclUint8, 0, (ncclComm_t)h->nccl, h->stream));
+    NW_CUDA(cudaMemcpyAsync(host, d, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->stream));
+    NW_CUDA(cudaStreamSynchronize(h->stream));
+    if (tmp) cudaFree(tmp);
+    for (int k = 0; k < n; ++k)
+        if (host[k] != vals[k]) { h->err = std::string(what) + ": differs from rank 0's (the mesh must be the same on every rank)"; return NW_ERR_ARG; }
     return NW_OK;
 }
 

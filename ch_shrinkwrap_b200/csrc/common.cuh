@@ -255,6 +255,8 @@ int nw_launch_sweep2(nw_ctx *h);
 int nw_launch_mesh_prior(nw_ctx *h, bool write_dirs);
 int nw_launch_solve_update(nw_ctx *h);
 int nw_allreduce_acc(nw_ctx *h);
+int nw_upload_replicated(nw_ctx *h, void *dst, const void *src, size_t bytes, size_t stride = 4);   // comm.cu
+int nw_check_replicated(nw_ctx *h, const long long *vals, int n, const char *what);
 int nw_allreduce_scalars(nw_ctx *h);
 int nw_set_acc_shifts(nw_ctx *h);
 int nw_curvature_relaunch(nw_ctx *h);

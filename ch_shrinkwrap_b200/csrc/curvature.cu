@@ -308,9 +308,9 @@ extern "C" int nw_curvature_grad(nw_ctx *h, const void *vertices, const void *fa
     NW_CHECK(nw_alloc(h, (HeRec **)&h->cvH, (size_t)n_halfedges)); NW_CHECK(nw_alloc(h, &h->cvOut, (size_t)18 * M));
     nw_free(&h->cvJ); nw_free(&h->cvOff);
     h->curvM = M; h->cv_dN = dN; h->cv_kc = kc; h->cv_kg = kg; h->cv_c0 = c0; h->cv_seed = (unsigned long long)jitter_seed;
-    NW_CUDA(cudaMemcpyAsync(h->cvV, vertices, sizeof(VertRec) * M, cudaMemcpyHostToDevice, s));
-    NW_CUDA(cudaMemcpyAsync(h->cvF, faces, sizeof(FaceRec) * n_faces, cudaMemcpyHostToDevice, s));
-    NW_CUDA(cudaMemcpyAsync(h->cvH, halfedges, sizeof(HeRec) * n_halfedges, cudaMemcpyHostToDevice, s));
+    NW_CHECK(nw_h2d(h, h->cvV, vertices, sizeof(VertRec) * (size_t)M));
+    NW_CHECK(nw_h2d(h, h->cvF, faces, sizeof(FaceRec) * (size_t)n_faces));
+    NW_CHECK(nw_h2d(h, h->cvH, halfedges, sizeof(HeRec) * (size_t)n_halfedges));
     CurvOut co;
     size_t offs[12];
     curv_outputs(h, co, offs);

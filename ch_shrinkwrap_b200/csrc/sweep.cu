@@ -1175,6 +1175,8 @@ int nw_bench_launch(nw_ctx *h, const char *name) {
         return nw_launch_mesh_prior(h, true);
     } else if (n == "refit") {
         return nw_tree_refit(h);
+    } else if (n == "allreduce_acc") {
+        return nw_allreduce_acc(h);              // N > 1: the per-iteration collective alone, all ranks in lockstep
     } else {
         h->err = "nw_bench_kernel: unknown kernel name " + n;
         return NW_ERR_ARG;

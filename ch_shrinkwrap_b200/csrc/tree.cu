@@ -444,6 +444,10 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     NW_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const int B = 256;
+    {   // N > 1: a collective call; rank 0's arrays are the ones every rank ends up with
+        const long long shape[7] = {M, F, n_he, records, valid != nullptr, he_vertex != nullptr, he_stride};
+        NW_CHECK(nw_check_replicated(h, shape, 7, "nw_set_topology: mesh shape"));
+    }
     BuildTrace trace_up(s);
     NW_CHECK(seg_begin(h));
     NW_CHECK(nw_save_feet(h));       // seeds for the next block, taken from the mesh that is about to be replaced
@@ -464,35 +468,35 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     // staging buffers are members so that they are reused from block to block (grow-only)
     if (he_vertex) {
         NW_CHECK(nw_alloc(h, &h->stage_hev, (size_t)n_he));
-        NW_CHECK(nw_h2d_strided32(h, h->stage_hev, he_vertex, sizeof(int) * (size_t)n_he, (size_t)he_stride));
+        NW_CHECK(nw_upload_replicated(h, h->stage_hev, he_vertex, sizeof(int) * (size_t)n_he, (size_t)he_stride));
     }
-    NW_CHECK(nw_h2d(h, h->faces, faces, sizeof(int) * 3 * (size_t)F));
+    NW_CHECK(nw_upload_replicated(h, h->faces, faces, sizeof(int) * 3 * (size_t)F));
     if (records) {
         NW_CHECK(nw_alloc(h, &h->stage_nbr, (size_t)30 * M));
-        NW_CHECK(nw_h2d(h, h->stage_nbr, pos, (size_t)120 * M));
+        NW_CHECK(nw_upload_replicated(h, h->stage_nbr, pos, (size_t)120 * M));
         NW_CHECK(seg_begin(h));
         k_unpack_vertex_records<<<nw_grid(M, B), B, 0, s>>>(h->stage_nbr, M, h->stage_hev, n_he, h->posq, h->nrmq, h->valid, h->nbrT, h->valence);
         h->launches += 1;
         NW_CHECK(seg_end(h));
     } else {
         NW_CHECK(nw_alloc(h, &h->stage_nbr, (size_t)NW_NEIGHBORSIZE * M));
-        NW_CUDA(cudaMemcpyAsync(h->scratchM, pos, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+        NW_CHECK(nw_upload_replicated(h, h->scratchM, pos, sizeof(float) * 3 * (size_t)M));
         NW_CHECK(seg_begin(h));
         k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->posq);
         h->launches += 1;
         NW_CHECK(seg_end(h));
         NW_CUDA(cudaStreamSynchronize(s));
-        NW_CUDA(cudaMemcpyAsync(h->scratchM, nrm, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+        NW_CHECK(nw_upload_replicated(h, h->scratchM, nrm, sizeof(float) * 3 * (size_t)M));
         NW_CHECK(seg_begin(h));
         k_pack_vec3<<<nw_grid(M, B), B, 0, s>>>(h->scratchM, M, h->nrmq);
         h->launches += 1;
         NW_CHECK(seg_end(h));
-        NW_CHECK(nw_h2d(h, h->stage_nbr, nbr, sizeof(int) * NW_NEIGHBORSIZE * (size_t)M));
+        NW_CHECK(nw_upload_replicated(h, h->stage_nbr, nbr, sizeof(int) * NW_NEIGHBORSIZE * (size_t)M));
         NW_CHECK(seg_begin(h));
         k_transpose_nbr<<<nw_grid(M, B), B, 0, s>>>(h->stage_nbr, he_vertex ? h->stage_hev : nullptr, n_he, M, h->nbrT, h->valence);
         h->launches += 1;
         NW_CHECK(seg_end(h));
-        if (valid) NW_CUDA(cudaMemcpyAsync(h->valid, valid, M, cudaMemcpyHostToDevice, s));
+        if (valid) NW_CHECK(nw_upload_replicated(h, h->valid, valid, (size_t)M));
         else NW_CUDA(cudaMemsetAsync(h->valid, 1, M, s));
     }
     NW_CUDA(cudaStreamSynchronize(s));
