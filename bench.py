@@ -299,7 +299,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'peak_source': peak_src, 'ms_per_launch': dom_ms, 'algorithmic_bytes_per_launch': alg_bytes[dom],
+                'traffic': traffic, 'peak_source': peak_src, 'frac_of_nominal_8000_gbs': achieved / 8000.0, 'ms_per_launch': dom_ms, 'algorithmic_bytes_per_launch': alg_bytes[dom],
                 'share_of_step': stage[dom]['ms_total'] / dev_ms}
     # isolated single-operator kernels (device resident, CUDA events)
     kernels = {}
