@@ -54,6 +54,7 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP);
     nw_free((char **)&h->cvV); nw_free((char **)&h->cvF); nw_free((char **)&h->cvH); nw_free(&h->cvOut); nw_free(&h->cvJ); nw_free(&h->cvOff);
     nw_free(&h->sp_pts); nw_free(&h->sp_k0); nw_free(&h->sp_k1); nw_free(&h->sp_idx); nw_free(&h->sp_tmp3);
+    nw_free(&h->blk_order); nw_free(&h->blk_idx); nw_free(&h->blk_key); nw_free(&h->blk_key2);
     nw_uploader_destroy(h);
     if (h->pin_host) cudaFreeHost(h->pin_host);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

@@ -151,6 +151,8 @@ struct nw_ctx {
     // nw_set_points temporaries, grow-only like everything else (a fit uploads its points once, a session many times)
     char *sp_pts = nullptr; unsigned long long *sp_k0 = nullptr, *sp_k1 = nullptr; int *sp_idx = nullptr; float *sp_tmp3 = nullptr;
     char *pin_host = nullptr; size_t pin_bytes = 0; bool pin_fresh = false;   // pinned read-back staging (nw_get_positions_strided)
+    // k_sweep1 block schedule: blocks in descending order of their largest seed distance (sweep.cu: build_block_order)
+    int *blk_order = nullptr, *blk_idx = nullptr; unsigned *blk_key = nullptr, *blk_key2 = nullptr; bool order_stale = true;
     struct nw_uploader *uploader = nullptr;       // xfer.cu: pinned staging lanes for large host->device copies
     cudaEvent_t ev_seg0 = nullptr, ev_seg1 = nullptr;   // topology_build segments (profiling only)
     double last_search_ms = 0.0;

@@ -146,6 +146,7 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
     h->P = P;
     h->weights_valid = false;
     h->seeds_cold = true;
+    h->order_stale = true;
     h->feet_valid = false;
     NWX(nw_alloc(h, &h->sp_pts, sizeof(T) * 3 * (size_t)P));
     T *d_pts = (T *)h->sp_pts;

@@ -9,6 +9,7 @@
 //
 // Determinism: the adjoint accumulates in 64-bit fixed point (integer atomics are order-independent,
 // float atomics are not); the Gram sums use a fixed thread->point assignment and a fixed two-stage tree.
+#include <cub/cub.cuh>
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
@@ -378,6 +379,7 @@ struct Sweep1Args {
     int *slot;
     float *w0, *w1, *w2, *rx, *ry, *rz;
     int two_limbs;                 // 1: every fixed-point term is below 2^53 in magnitude (group_sum2)
+    const int *order;              // block schedule (see build_block_order) or NULL
     const float4 *posq;
     const int4 *sfaces;
     TreeView tv;
@@ -563,7 +565,7 @@ template <bool F64, int MODE, bool STATS>
 __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB) : NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
     if (MODE == 1 && a.st->stop) return;
 
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = (a.order ? __ldg(&a.order[blockIdx.x]) : (int)blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
     const bool active = i < a.P;
     float x = 0.f, y = 0.f, z = 0.f;
     double xd = 0.0, yd = 0.0, zd = 0.0;
@@ -898,6 +900,7 @@ static Sweep1Args make_args(nw_ctx *h) {
     static const bool no_clear = getenv("NW_NO_CELL_CLEARANCE") != nullptr;      // A/B switch for measurements
     if (no_clear) a.tv.grid_inv = 0.f;
     a.acc = h->acc; a.st = h->st;
+    a.order = nullptr;
     a.two_limbs = h->P_global >= 256 ? 1 : 0;       // k_shift_final leaves 2^61 / P_global of headroom per term (its clamp at -60 only bites for absurd extents)
     return a;
 }
@@ -935,12 +938,56 @@ int nw_launch_seed_leaders(nw_ctx *h) {
     return NW_OK;
 }
 
+// Longest-first block schedule.  A query deep inside a lobe is (nearly) equidistant to a whole region of the surface and
+// its packet needs 10^4 steps where the average one needs 10^2; such packets are neighbours in the sorted order, so in
+// index order they all start in the middle of the launch and the last of them finishes long after every other SM has
+// gone idle (measured in the first iteration of a fit at C3: SMs active 47 % of the launch).  The distance from a query to
+// its seed is known before the sweep and is a good proxy for that cost: blocks are launched in descending order of it.
+// Rebuilt whenever the seeds are (new points or new topology); the order never affects results.
+__global__ void __launch_bounds__(128) k_block_cost(int64_t P, const float *__restrict__ px, const float *__restrict__ py,
+                                                    const float *__restrict__ pz, const int *__restrict__ slot,
+                                                    const float4 *__restrict__ cent, unsigned *__restrict__ key, int *__restrict__ idx) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    float d2 = 0.f;
+    if (i < P) {
+        const int s = slot[i];
+        if (s >= 0) {
+            const float4 c = __ldg(&cent[s]);
+            const float dx = px[i] - c.x, dy = py[i] - c.y, dz = pz[i] - c.z;
+            d2 = dx * dx + dy * dy + dz * dz;
+            if (!(d2 >= 0.f)) d2 = 0.f;
+        }
+    }
+    __shared__ unsigned sh[4];
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(d2));       // non-negative floats order like their bits
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { key[blockIdx.x] = max(max(sh[0], sh[1]), max(sh[2], sh[3])); idx[blockIdx.x] = blockIdx.x; }
+}
+
+static int build_block_order(nw_ctx *h, int G) {
+    NW_CHECK(nw_alloc(h, &h->blk_key, (size_t)G)); NW_CHECK(nw_alloc(h, &h->blk_key2, (size_t)G));
+    NW_CHECK(nw_alloc(h, &h->blk_idx, (size_t)G)); NW_CHECK(nw_alloc(h, &h->blk_order, (size_t)G));
+    k_block_cost<<<G, 128, 0, h->stream>>>(h->P, h->px, h->py, h->pz, h->slot, h->cent, h->blk_key, h->blk_idx);
+    NW_LAUNCH_CHECK();
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, h->blk_key, h->blk_key2, h->blk_idx, h->blk_order, G, 0, 32, h->stream);
+    if (tmp > h->cub_tmp_bytes) { NW_CHECK(nw_alloc(h, (char **)&h->cub_tmp, tmp)); h->cub_tmp_bytes = tmp; }
+    NW_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->cub_tmp, tmp, h->blk_key, h->blk_key2, h->blk_idx, h->blk_order, G, 0, 32, h->stream));
+    h->launches += 2;
+    h->order_stale = false;
+    return NW_OK;
+}
+
 int nw_launch_sweep1(nw_ctx *h, bool scatter) {
     if (h->P == 0) return NW_OK;
     const int B = 128;
-    Sweep1Args a = make_args(h);
     const int G = nw_grid(h->P, B);
     NW_CHECK(nw_launch_seed_leaders(h));
+    static const bool no_order = getenv("NW_NO_BLOCK_ORDER") != nullptr;          // A/B switch for measurements
+    if (h->order_stale && !no_order) NW_CHECK(build_block_order(h, G));
+    Sweep1Args a = make_args(h);
+    a.order = no_order ? nullptr : h->blk_order;
     // traversal statistics (nw_get_traversal_stats) are collected only when asked for: nw_set_profile(h, 3)
 #ifdef NW_LEVEL_STATS
     const bool stats = true;

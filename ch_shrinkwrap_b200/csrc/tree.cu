@@ -507,6 +507,7 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     // nearest-face slots refer to the previous block's sort order
     if (h->slot && h->P) NW_CUDA(cudaMemsetAsync(h->slot, 0xff, sizeof(int) * h->P, s));
     h->seeds_cold = true;
+    h->order_stale = true;
     NW_CHECK(nw_tree_build(h));
     return seg_end(h);
 }
