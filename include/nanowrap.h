@@ -63,7 +63,10 @@ int nw_set_points(nw_ctx *h, const void *pts, int pts_is_f64, int64_t P, const f
  *  pos, nrm  (M,3) float32: mesh._vertices['position'], mesh.vertex_normals (normals are per block)
  *  faces     (F,3) int32  : mesh.faces; nearest-face results index its rows (:488)
  *  nbr       (M,20) int32 : neighbour VERTEX ids, -1 terminated (:50-54)
- *  valid     (M) uint8 or NULL: mesh._vertices['halfedge'] != -1 (:44); NULL = all valid */
+ *  valid     (M) uint8 or NULL: mesh._vertices['halfedge'] != -1 (:44); NULL = all valid
+ * With a communicator of more than one rank (nw_comm_init) the three nw_set_topology* calls are COLLECTIVE: every rank
+ * calls with the same mesh, rank 0's arrays are uploaded and broadcast to the others (ncclBroadcast), and a rank whose
+ * M, F, half-edge count or optional-array pattern differs from rank 0's gets NW_ERR_ARG. */
 int nw_set_topology(nw_ctx *h, const float *pos, const float *nrm, const int32_t *faces,
                     const int32_t *nbr, const uint8_t *valid, int M, int F);
 /* Same, but the neighbour table holds HALF-EDGE indices exactly as mesh._vertices['neighbors'] stores them and
