@@ -226,7 +226,7 @@ def main():
     from ch_shrinkwrap_b200.mesh_conj_grad import _session_for
     _session_for(mesh, local_rank, comm)
 
-    # ---- e2e: public API with HOST buffers: first block pays the point upload + Morton sort, every block the
+    # ---- e2e: public API with HOST buffers: first block pays the point upload + Hilbert sort, every block the
     #      topology H2D and the position D2H.  Timed by wall clock around constructor + search().
     # warm-up (lazy module loading, first-touch allocations), then forget the uploaded points so that the timed run
     # pays the host->device copy and the Hilbert sort again
@@ -245,7 +245,7 @@ def main():
            'h2d_bytes_per_step': int((P * 24 + n_blocks * (topo_bytes + M * 12)) / K),
            'd2h_bytes_per_step': int(n_blocks * M * 12 / K),
            'note': 'ShrinkwrapMeshConjGrad(...).search() per block of %d iterations, host numpy in/out; includes the one-off upload '
-                   'and Morton sort of the points (pageable host memory), per-block topology upload and position read-back' % block}
+                   'and Hilbert sort of the points (pageable host memory), per-block topology upload and position read-back' % block}
 
     # ---- device-resident: points already in HBM; warm-up then K timed iterations (CUDA events inside nw_search)
     mesh._vertices['position'][:] = start_pos

@@ -72,7 +72,7 @@ struct nw_ctx {
     int64_t launches = 0;
     std::unordered_map<void *, size_t> caps;     // capacity (bytes) of the buffer each pointer variable currently owns
 
-    // ---- points (Morton-sorted SoA) ----
+    // ---- points (Hilbert-sorted SoA) ----
     int64_t P = 0;
     int64_t P_global = 0;
     float *px = nullptr, *py = nullptr, *pz = nullptr;
@@ -248,7 +248,7 @@ __host__ __device__ __forceinline__ void hilbert_axes_to_transpose(U &x, U &y, U
 }
 
 // ---- internal entry points implemented across translation units -------------------------------
-int nw_tree_build(nw_ctx *h);                 // after topology upload: Morton sort of faces
+int nw_tree_build(nw_ctx *h);                 // after topology upload: Hilbert sort of faces, octree tables, frames
 int nw_tree_refit(nw_ctx *h);                 // every iteration: centroids + boxes at the current f
 int nw_launch_sweep1(nw_ctx *h, bool scatter);
 int nw_launch_seed_leaders(nw_ctx *h);

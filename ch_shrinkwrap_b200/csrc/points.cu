@@ -1,4 +1,4 @@
-// points.cu -- nw_set_points: upload one shard of localisations, Morton-sort it once (points never
+// points.cu -- nw_set_points: upload one shard of localisations, Hilbert-sort it once (points never
 // move during a fit) and keep every per-point stream as SoA in that order, so a warp of
 // consecutive points queries neighbouring faces and every per-point load/store is a unit-stride
 // 128 B line per warp.
@@ -164,7 +164,7 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
     for (int a = 0; a < 6; ++a) h->bbox_pts[a] = ordered_to_float(bb[a]);
     if (P == 0) for (int a = 0; a < 6; ++a) h->bbox_pts[a] = 0.f;
 
-    // Morton keys (21 bits per axis) + sort
+    // Hilbert keys (21 bits per axis) + sort
     float3 lo = make_float3(h->bbox_pts[0], h->bbox_pts[1], h->bbox_pts[2]);
     float ext = fmaxf(fmaxf(h->bbox_pts[3] - lo.x, h->bbox_pts[4] - lo.y), h->bbox_pts[5] - lo.z);
     float iv = ext > 0.f ? 2097151.f / ext : 0.f;

@@ -2,7 +2,7 @@
 effects as the reference class (``ch_shrinkwrap/mesh_conj_grad.py:19-292``), executed by libnanowrap.so.
 
 Drop-in seam: ``MembraneMesh.opt_conjugate_gradient`` builds one of these per remesh block and calls
-``search`` (``_membrane_mesh.pyx:1510-1517``).  Points are uploaded and Morton-sorted once per fit and the
+``search`` (``_membrane_mesh.pyx:1510-1517``).  Points are uploaded and Hilbert-sorted once per fit and the
 device session is cached on the mesh object, so the per-block cost is the topology upload only.
 """
 from __future__ import annotations

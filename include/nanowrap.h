@@ -7,7 +7,7 @@
  *
  * Host arrays use the reference's layouts: vectors over vertices are raveled C-order
  * [v0x,v0y,v0z,v1x,...] (mesh_conj_grad.py:594-595), per-point arrays are (P,3) row-major in the
- * CALLER'S point order (the library keeps its own Morton-sorted copy internally).
+ * CALLER'S point order (the library keeps its own Hilbert-sorted copy internally).
  */
 #ifndef NANOWRAP_H_
 #define NANOWRAP_H_
