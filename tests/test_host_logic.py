@@ -126,3 +126,55 @@ def test_image_module_surface_and_voxel_conversion():
     assert sigma == 10.0 and pts.shape == (2, 3) and w.shape == (6,)
     assert np.array_equal(pts, [[110.0, 240.0, 300.0], [120.0, 260.0, 330.0]])
     assert np.array_equal(w, [5, 5, 5, 7, 7, 7])
+
+
+def test_solver_shim_chooses_the_record_upload_and_passes_the_half_edge_stride():
+    """Host logic of ShrinkwrapMeshConjGrad without a GPU: a recording stand-in for the C ABI handle.  PYME-layout meshes
+    go up as raw records with the half-edge 'vertex' field addressed in place (stride 28); search() asks the library to
+    write the positions back into the records and keeps the reference's side effects (mesh_conj_grad.py:289-290)."""
+    import ctypes
+    from ch_shrinkwrap_b200 import mesh_conj_grad as mcg, synth
+    from ch_shrinkwrap_b200.membrane_mesh import MembraneMesh
+
+    calls = []
+
+    class FakeHandle:
+        h = 1
+
+        def call(self, name, *args):
+            calls.append((name, args))
+            if name == 'nw_search':
+                args[-1]._obj.value = args[1]                 # n_done = num_iters
+            return 0
+
+    class FakeSession:
+        handle = FakeHandle()
+        points_key = None
+        P = 0
+
+        def set_points(self, points, sigma_inv, weights):
+            calls.append(('set_points', (points.shape, np.isscalar(sigma_inv), weights is None)))
+            self.P = len(points)
+
+    base = synth.star_mesh(synth.Sphere(100.0), 3, scale=1.1)
+    mesh = MembraneMesh(mesh=base)
+    mesh._nw_session = FakeSession()
+    inited = []
+    mesh._initialize_curvature_vectors = lambda: inited.append(1)
+    pts = (np.asarray(mesh.vertices) * 0.9).astype(np.float32)
+    cg = mcg.ShrinkwrapMeshConjGrad(mesh, pts)
+    assert cg._vertex_mask is None                            # the valid mask is built lazily
+    out = cg.search(pts, lams=[5.0], num_iters=3, sigma_inv=0.1)
+    names = [c[0] for c in calls]
+    assert names == ['set_points', 'nw_set_topology_records', 'nw_search', 'nw_get_positions_strided']
+    rec = dict(calls)['nw_set_topology_records']
+    assert rec[3] == mesh._halfedges.strides[0] == 28         # half-edge 'vertex' field gathered in place
+    assert rec[4] == len(mesh._halfedges) and rec[5] == len(mesh._vertices) and rec[6] == len(mesh.faces)
+    wb = dict(calls)['nw_get_positions_strided']
+    assert wb[1] == mesh._vertices.strides[0] == 120 and wb[2] == 1
+    assert out.shape == (len(mesh._vertices), 3) and cg.loopcount == 3 and len(cg.tests) == 3
+    assert inited == [1]                                       # :290
+    # a second search() on the same object re-sends the (possibly edited) positions, not the topology
+    calls.clear()
+    cg.search(pts, lams=[5.0], num_iters=2, sigma_inv=0.1)
+    assert [c[0] for c in calls] == ['set_points', 'nw_set_positions', 'nw_search', 'nw_get_positions_strided']
