@@ -186,14 +186,47 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     h->ev_used = 0;
     h->ev_stage.clear();
     NW_CUDA(cudaEventRecord(h->ev_search0, h->stream));
-    if (!s.stop)
-        for (int it = 0; it < num_iters; ++it) NW_CHECK(enqueue_iteration(h, it, last_step));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    if (!s.stop) {
+        int it = 0;
+        // the first iteration runs eagerly: it may seed, build the launch schedule and touch allocations
+        if (num_iters > 0) { NW_CHECK(enqueue_iteration(h, 0, last_step)); it = 1; }
+        // every further iteration is the same ~15 launches with the same arguments: capture one, replay it.  For small
+        // fits the iteration is launch-bound (C1: 0.25 ms of launches around microseconds of work).  Not under profiling
+        // (per-stage events) and not with a communicator (the collectives stay eager).
+        static const bool no_graph = getenv("NW_NO_GRAPH") != nullptr;
+        if (!no_graph && !h->profile && h->nranks == 1 && num_iters - it >= 2) {
+            const int64_t l0 = h->launches;
+            bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            int rc = NW_OK;
+            if (ok) {
+                rc = enqueue_iteration(h, it, last_step);
+                ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && rc == NW_OK && graph != nullptr;
+            }
+            const int64_t per_iter = h->launches - l0;
+            h->launches = l0;                                    // nothing has run yet
+            if (ok) ok = cudaGraphInstantiate(&graph_exec, graph, 0) == cudaSuccess;
+            if (ok) {
+                for (; it < num_iters; ++it) {
+                    NW_CUDA(cudaGraphLaunch(graph_exec, h->stream));
+                    h->launches += per_iter;
+                }
+            } else {
+                cudaGetLastError();                              // capture refused: the loop below runs the iterations eagerly
+                if (rc != NW_OK) return rc;
+            }
+        }
+        for (; it < num_iters; ++it) NW_CHECK(enqueue_iteration(h, it, last_step));
+    }
     NW_CUDA(cudaEventRecord(h->ev_search1, h->stream));
     h->pin_fresh = false;
     NW_CHECK(nw_fetch_positions_async(h));          // the caller wants the result on the host next: no second round trip
     SolverState r;
     NW_CUDA(cudaMemcpyAsync(&r, h->st, sizeof(SolverState), cudaMemcpyDeviceToHost, h->stream));
     NW_CUDA(cudaStreamSynchronize(h->stream));
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (graph) cudaGraphDestroy(graph);
     {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_search0, h->ev_search1);

@@ -200,6 +200,8 @@ __global__ void k_solve(const double *__restrict__ mesh_partials, int n_mesh_blo
         __syncthreads();
     }
     if (threadIdx.x != 0) return;
+    iter_index = st->n_done;          // == the host's loop index (n_done starts at 0 in nw_search and is bumped below); reading
+                                      // it here leaves the launch without per-iteration arguments, so it can be replayed from a graph
     for (int k = 0; k < 6; ++k) st->hw[k] = red[k];
     for (int k = 0; k < 3; ++k) st->gw[k] = red[6 + k];
     const int n = st->n_search;
