@@ -38,7 +38,7 @@ WORKLOADS = {
 }
 REFERENCE_SAMPLE = 'c2'   # bounded CPU sample: same shape, same 20 localisations per vertex, 1/10 of c3
 STAGES = ['refit', 'shift', 'sweep1', 'allreduce_acc', 'mesh_prior', 'sweep2', 'allreduce_scalars', 'solve_update', 'seed_leaders',
-          'topology_build']
+          'topology_build', 'sweep1_fast', 'sweep1_select', 'sweep1_list']
 
 
 def build_workload(name, seed):
@@ -265,8 +265,8 @@ def main():
     clk = clocks.stop()
     launches = int(h.lib.nw_launch_count(h.h) - launches0)
     dev_ms = allmax(dev_ms)
-    stage_ms = (ctypes.c_double * 10)()
-    stage_l = (ctypes.c_int64 * 10)()
+    stage_ms = (ctypes.c_double * 16)()
+    stage_l = (ctypes.c_int64 * 16)()
     h.call('nw_get_profile', stage_ms, stage_l, None)
     h.call('nw_set_profile', 0)
     # the timed region is every device-side piece of the K steps: the CG iterations (inside nw_search) AND the per-block

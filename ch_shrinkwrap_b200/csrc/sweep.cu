@@ -10,6 +10,7 @@
 // Determinism: the adjoint accumulates in 64-bit fixed point (integer atomics are order-independent,
 // float atomics are not); the Gram sums use a fixed thread->point assignment and a fixed two-stage tree.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
@@ -63,26 +64,26 @@ struct QueryF64 {
     }
 };
 
-#if NW_SHELL
-#error "NW_SHELL (spherical-shell bound, a measured dead end) predates the parent link stored in Box::d.w"
-#endif
-#ifndef NW_PACKET
-#define NW_PACKET 1      // 1: warp-packet search in k_sweep1 (see Traversal); 0: one private search per lane
-#endif
 
 struct Nearest {
     double d2;
     float ub;      // d2 rounded up to float: prune bound for the float32 lower bounds
+    float lb2;     // lower bound (float32, rounded down) of the SQUARED fp64 distance to every centroid other than `slot`
+                   // that the search has accounted for: pruned nodes, pruned or losing centroids (see k_sweep1_fast)
     int slot, face;
+    __device__ __forceinline__ void lose(float v) { lb2 = fminf(lb2, v); }
     __device__ __forceinline__ void offer(double v, int s, int f) {
+        if (s == slot) return;                 // the current best seen again (its leaf is searched like any other)
         // strict minimum; exact fp64 ties -> lowest face index (contract of SURVEY 7.3)
-        if (v < d2 || (v == d2 && f < face)) { d2 = v; slot = s; face = f; ub = __double2float_ru(v); }
+        if (v < d2 || (v == d2 && f < face)) {
+            lose(__double2float_rd(d2));       // the previous best is now one of the others (+inf when there was none)
+            d2 = v; slot = s; face = f; ub = __double2float_ru(v);
+        } else lose(__double2float_rd(v));
     }
 };
 
-// Conservative lower bound of the squared distance from the query to anything inside a node:
-//   max( sum over the three box axes of (interval gap - eps)^2 ,  (shell gap - eps_s)^2 ).
-// Projections / radii are float32, so every gap is shrunk by an absolute slack (>= 4x the worst-case rounding error of
+// Conservative lower bound of the squared distance from the query to anything inside a node: the sum over the three
+// box axes of (interval gap)^2.  Projections are float32, so every interval is widened by an absolute slack (>= 4x the worst-case rounding error of
 // both the query's and the members' evaluation, DESIGN.md "exactness") and the squares by a relative 1e-5 (axes are
 // orthonormal only to float32 accuracy).  A node is skipped only if this bound exceeds the best exact fp64 distance,
 // so skipping can never change the answer.
@@ -90,18 +91,10 @@ template <typename Q>
 __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps, int *link = nullptr) {
     const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
     const float x = q.fx(), y = q.fy(), z = q.fz();
-#if NW_SHELL
-    const float3 t1 = nw_tangent_of(a.x, a.y, a.z);
-#else
-    const float4 d4 = __ldg(&bp->d);                 // without the shell the fourth quarter of the node stores t1
+    const float4 d4 = __ldg(&bp->d);                 // the fourth quarter of the node stores t1 ...
     const float3 t1 = make_float3(d4.x, d4.y, d4.z);
     if (link) *link = __float_as_int(d4.w);          // ... and first child | last-child flag (k_global_tables)
-#endif
-#if NW_SHELL
-    const float t2x = a.y * t1.z - a.z * t1.y, t2y = a.z * t1.x - a.x * t1.z, t2z = a.x * t1.y - a.y * t1.x;
-#else
-    const float t2x = c.y, t2y = c.z, t2z = c.w;     // ... and the shell-centre slot stores t2 = n x t1
-#endif
+    const float t2x = c.y, t2y = c.z, t2z = c.w;     // t2 = n x t1
     const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
     const float p1 = fmaf(t1.x, x, fmaf(t1.y, y, t1.z * z));
     const float p2 = fmaf(t2x, x, fmaf(t2y, y, t2z * z));
@@ -109,14 +102,7 @@ __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp,
     const float g0 = fmaxf(fmaxf(a.w - pn, pn - b.x), 0.f);
     const float g1 = fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f);
     const float g2 = fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f);
-    float lb = __fadd_rd(__fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1)), __fmul_rd(g2, g2));
-#if NW_SHELL
-    const float4 d = __ldg(&bp->d);
-    const float dx = x - c.y, dy = y - c.z, dz = z - c.w;
-    const float r = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-    const float gs = fmaxf(fmaxf(d.x - r, r - d.y), 0.f) - fmaf(r, 4e-6f, eps);
-    if (gs > 0.f) lb = fmaxf(lb, __fmul_rd(gs, gs));
-#endif
+    const float lb = __fadd_rd(__fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1)), __fmul_rd(g2, g2));
     return __fmul_rd(lb, 0.99999f);
 }
 
@@ -221,8 +207,9 @@ struct Traversal {
         const unsigned m = (d | (d >> 10) | (d >> 20)) & 1023u;       // highest differing bit over the three axes
         return m ? __clz(m) - 22 : 10;
     }
-    // true if nothing outside the query's level-`level` cube can beat the current best
-    __device__ __forceinline__ bool cube_clear(int level) const {
+    // true if nothing outside the query's level-`level` cube can beat the current best; *out2 = the squared distance
+    // everything outside that cube is at least away
+    __device__ __forceinline__ bool cube_clear(int level, float *out2) const {
         const int s = 10 - level;
         const float w = (float)(1u << s);
         const float gx = grid(q.fx(), tv.grid_lo.x), gy = grid(q.fy(), tv.grid_lo.y), gz = grid(q.fz(), tv.grid_lo.z);
@@ -231,7 +218,8 @@ struct Traversal {
         const float cl = fminf(fminf(fminf(fx, w - fx), fminf(fy, w - fy)), fminf(fz, w - fz));
         // slack: rounding of g for the query and for the centroids (a few ulp of 1024 each), of the coordinates (eps)
         const float m = (cl - escape - 1e-3f) * tv.grid_cellw - 2.f * eps;
-        return m > 0.f && __fmul_rd(__fmul_rd(m, m), 0.99999f) > best.ub;
+        *out2 = __fmul_rd(__fmul_rd(m, m), 0.99999f);
+        return m > 0.f && *out2 > best.ub;
     }
 
     __device__ __forceinline__ void leaf(int node) {
@@ -239,7 +227,9 @@ struct Traversal {
         if constexpr (COUNT) ++n_leaves;
         for (int s = k.x; s < k.x + k.y; ++s) {
             const float4 c = __ldg(&tv.cent[s]);
-            if (q.lb_box(c, c) <= best.ub) { if constexpr (COUNT) ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
+            const float l = q.lb_box(c, c);
+            if (l <= best.ub) { if constexpr (COUNT) ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
+            else best.lose(l);
         }
     }
 #ifdef NW_LEVEL_STATS
@@ -259,10 +249,12 @@ struct Traversal {
         while (true) {
             int link;                                      // first child | (node is a last child) << 31, stored in the node itself
             if (tick()) return;
-            const bool pass = any(node_lb(q, &tv.boxes[node], eps, &link) <= best.ub);
+            const float lb = node_lb(q, &tv.boxes[node], eps, &link);
+            const bool pass = any(lb <= best.ub);
 #ifdef NW_LEVEL_STATS
             count_test(node, pass);
 #endif
+            if (!pass) best.lose(lb);                      // skipped for every lane: this lane's bound covers the whole subtree
             if (pass) {
                 if (node >= tv.leaf0) leaf(node);
                 else { node = link & 0x7fffffff; continue; }
@@ -292,8 +284,16 @@ struct Traversal {
         const QueryF32 pk_c = packet_centre();
         const int j = (int)(threadIdx.x & 31);
         bool hit = false;
-        if (j < n && c0 + j != skip) hit = !(__fsqrt_rd(node_lb(pk_c, &tv.boxes[c0 + j], eps)) > reach);
+        float gone = __int_as_float(0x7f800000);              // distance bound of a sibling this lane prunes for the packet
+        if (j < n && c0 + j != skip) {
+            const float dc = __fsqrt_rd(node_lb(pk_c, &tv.boxes[c0 + j], eps));
+            hit = !(dc > reach);
+            if (!hit) gone = dc;
+        }
         if constexpr (COUNT) ++n_tests;
+        // a sibling at distance dc from the packet centre is at least dc - pk_r from every lane (dc > reach >= pk_r)
+        const float g = __fsub_rd(__uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(gone))), pk_r);
+        best.lose(__fmul_rd(g, g));
         return __ballot_sync(0xffffffffu, hit);
     }
     // climb from a leaf (one of whose centroids was keyed into `cell`): at every level only the sibling subtrees are searched
@@ -301,7 +301,9 @@ struct Traversal {
         leaf(node);
         const int shared = shared_levels(cell);
         for (int level = tv.leaf_level; level >= 1; --level) {
-            if (all(!active || (level <= shared && cube_clear(level)))) return;
+            float out2 = 0.f;
+            const bool clear = level <= shared && cube_clear(level, &out2);
+            if (all(!active || clear)) { if (clear) best.lose(out2); return; }
             const int p = __ldg(&tv.parent[node]) & 0x7fffffff;
             const int2 k = __ldg(&tv.kids[p]);
             if constexpr (PACKET) {
@@ -377,6 +379,8 @@ struct Sweep1Args {
     const float *wx, *wy, *wz;     // weight arrays (may alias sigma_inv) or NULL
     float sinv_scalar, wmean;
     int *slot;
+    float *lbd;                    // per point: distance every centroid other than slot[] is at least away (k_sweep1_fast)
+    const int *list, *list_n;      // LIST mode of k_sweep1: the points that need the search
     float *w0, *w1, *w2, *rx, *ry, *rz;
     int two_limbs;                 // 1: every fixed-point term is below 2^53 in magnitude (group_sum2)
     const int *order;              // block schedule (see build_block_order) or NULL
@@ -399,7 +403,6 @@ __device__ NW_FN_INLINE Nearest find_nearest(const Sweep1Args &a, int64_t i, boo
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
     if constexpr (F64) q.set(xd, yd, zd);
     else { q.x = x; q.y = y; q.z = z; }
-#if NW_PACKET
     Traversal<decltype(q), true, STATS> tr(q, best, a.tv, eps, a.st->cell_escape, active);
 #ifdef NW_LEVEL_STATS
     tr.dbg = a.st; tr.dbg_tl = &a.tl;
@@ -425,34 +428,6 @@ __device__ NW_FN_INLINE Nearest find_nearest(const Sweep1Args &a, int64_t i, boo
         tr.set_packet_centre(__ffs(alive) - 1);
         tr.from_seed(start);
     }
-#else
-    Traversal<decltype(q)> tr(q, best, a.tv, eps, a.st->cell_escape);
-#ifdef NW_LEVEL_STATS
-    tr.dbg = a.st; tr.dbg_tl = &a.tl;
-#endif
-    int seed = active ? a.slot[i] : 0;
-    // Cold start (first iteration after a topology upload): lanes without a seed borrow one from a lane that has it
-    // (k_seed_leaders searched lane 0's point from the root) -- Hilbert-sorted neighbours share (nearly) the same
-    // nearest face, and a seed only has to be close, not right.  If no lane has one, the first lane searches from
-    // the root now.
-    const unsigned cold = __ballot_sync(0xffffffffu, active && seed < 0);
-    if (cold) {
-        const unsigned warm = __ballot_sync(0xffffffffu, active && seed >= 0);
-        int donor;
-        if (warm) donor = __ffs(warm) - 1;
-        else {
-            donor = __ffs(cold) - 1;
-            if ((threadIdx.x & 31) == donor) { tr.top_down(); seed = tr.best.slot; }
-        }
-        const int s0 = __shfl_sync(0xffffffffu, seed, donor);
-        if (seed < 0) seed = s0;
-    }
-    if (active && tr.best.slot < 0) {
-        const float4 c = a.tv.cent[seed];
-        tr.best.offer(tr.q.d2(c), seed, __float_as_int(c.w));
-        tr.from_seed(seed);
-    }
-#endif
     // traversal statistics (one atomic per warp and counter)
     if constexpr (STATS) {
     const unsigned t = __reduce_add_sync(0xffffffffu, active ? tr.n_tests : 0u), l = __reduce_add_sync(0xffffffffu, active ? tr.n_leaves : 0u),
@@ -485,7 +460,7 @@ __global__ void __launch_bounds__(128) k_seed_leaders(const __grid_constant__ Sw
     const int64_t i = t * 32;
     if (i >= a.P || a.slot[i] >= 0) return;
     Nearest best;
-    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
+    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.lb2 = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
     const float x = a.px[i], y = a.py[i], z = a.pz[i];
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
@@ -544,7 +519,7 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
         if (__ldg(&fkeys[mid]) < key) lo = mid + 1; else hi = mid;
     }
     Nearest best;
-    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
+    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.lb2 = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
     QueryF32 q;
     q.x = x; q.y = y; q.z = z;
@@ -557,38 +532,17 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
     a.slot[i] = tr.best.slot;
 }
 
-// MODE 0: nearest face + weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
-#ifndef NW_S1_MINB
-#define NW_S1_MINB 16     // 32 registers, 64 warps per SM.  Measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 before the global-id tables; after them 48 regs 2.47, 40 regs 2.51, 32 regs 2.33 -- the packet walk is a dependent chain, occupancy hides it
-#endif
-template <bool F64, int MODE, bool STATS>
-__global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB) : NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
-    if (MODE == 1 && a.st->stop) return;
-
-    const int64_t i = (a.order ? __ldg(&a.order[blockIdx.x]) : (int)blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
-    const bool active = i < a.P;
-    float x = 0.f, y = 0.f, z = 0.f;
-    double xd = 0.0, yd = 0.0, zd = 0.0;
-    if (active) {
-        x = a.px[i]; y = a.py[i]; z = a.pz[i];
-        xd = x; yd = y; zd = z;
-        if (F64) { xd = a.px64[i]; yd = a.py64[i]; zd = a.pz64[i]; }
-    }
-    Nearest best;
-    best.d2 = DBL_MAX * 2.0;   // +inf
-    best.ub = FLT_MAX * 2.0f;
-    best.slot = -1;
-    best.face = 0x7fffffff;
-    best = find_nearest<F64, STATS>(a, i, active, x, y, z, xd, yd, zd, best);
-    if (active && best.slot < 0) {      // non-finite query: nothing compares; flag it (the reference asserts on NaN) and stay in bounds
-        a.st->nan_flag = 1;
-        best.slot = 0;
-    }
+// Everything that follows the nearest-face decision for one point: inverse-distance weights, A f, residual, and (MODE 1)
+// the deterministic adjoint scatter.  All 32 lanes of a warp must call it (the scatter sums inside the warp first);
+// `live` = this lane has a point and its nearest face `slot` at exact squared distance `d2near`.
+// MODE 0: weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
+template <bool F64, int MODE>
+__device__ __forceinline__ void point_tail(const Sweep1Args &a, int64_t i, bool live, int slot, double d2near, float x, float y, float z,
+                                           double xd, double yd, double zd) {
     float u0 = 0.f, u1 = 0.f, u2 = 0.f, r_x = 0.f, r_y = 0.f, r_z = 0.f;
     int4 sf = make_int4(0, 0, 0, 0);
-    if (active) {
-    a.slot[i] = best.slot;
-    sf = a.sfaces[best.slot];
+    if (live) {
+    sf = a.sfaces[slot];
     const float4 v0 = __ldg(&a.posq[sf.x]), v1 = __ldg(&a.posq[sf.y]), v2 = __ldg(&a.posq[sf.z]);
     // corner distances, mesh_conj_grad.py:491-495 (float32 points: all float32; float64 points: float64 then stored float32)
     float d0, d1, d2;
@@ -626,7 +580,7 @@ __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB)
         wny = __fdiv_rn(a.wy == a.sy ? s_y : a.wy[i], a.wmean);
         wnz = __fdiv_rn(a.wz == a.sz ? s_z : a.wz[i], a.wmean);
     } else wnx = wny = wnz = a.sinv_scalar;
-    const double D = sqrt(best.d2);
+    const double D = sqrt(d2near);
     if (F64) {
         r_x = (float)((double)wnx * (xd - (double)afx)); r_y = (float)((double)wny * (yd - (double)afy)); r_z = (float)((double)wnz * (zd - (double)afz));
     } else {
@@ -644,14 +598,15 @@ __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB)
     // Lanes whose point landed on the same face are summed inside the warp first (exact integer sums), so a face
     // costs 12 global RED.64 per warp instead of 12 per point and the lanes of a warp never collide on an address.
     const double sc = pow2d(a.st->acc_shift), sci = pow2d(a.st->infl_shift);
-    const int key = active ? best.slot : -1 - (int)(threadIdx.x & 31);
+    // lanes without a point share ONE group (they add zeros and never lead): REDUX runs once per distinct member mask
+    const int key = live ? slot : -1;
     const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const bool lead = active && ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1));
+    const bool lead = live && ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1));
     const float uw[3] = {u0, u1, u2};
     const int vid[3] = {sf.x, sf.y, sf.z};
+    const bool two = a.two_limbs != 0 && a.st->acc_shift > -60;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const bool two = a.two_limbs != 0 && a.st->acc_shift > -60;
         const unsigned long long gx = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
         const unsigned long long gy = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
         const unsigned long long gz = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
@@ -661,6 +616,141 @@ __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB)
             atomicAdd(dst + 0, gx); atomicAdd(dst + 1, gy); atomicAdd(dst + 2, gz); atomicAdd(dst + 3, gi);
         }
     }
+}
+
+// safety factor between the recorded float32 bounds and the comparison of fp64-evaluated distances (see k_sweep1_fast)
+#define NW_LBD_SAFE 0.999999f
+
+// Full search.  LIST = false: every point, blocks in the longest-first order (build_block_order);
+// LIST = true: only the points k_sweep1_fast could not settle (a.list[0 .. *a.list_n), in Hilbert order).
+#ifndef NW_S1_MINB
+#define NW_S1_MINB 16     // 32 registers, 64 warps per SM.  Measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 before the global-id tables; after them 48 regs 2.47, 40 regs 2.51, 32 regs 2.33 -- the packet walk is a dependent chain, occupancy hides it
+#endif
+template <bool F64, int MODE, bool STATS, bool LIST>
+__global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB) : NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
+    if (MODE == 1 && a.st->stop) return;
+    int64_t i;
+    bool active;
+    if constexpr (LIST) {
+        const int n = *a.list_n;
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.st->n_listed = n;
+        const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if ((int64_t)blockIdx.x * blockDim.x >= n) return;
+        active = t < n;
+        i = active ? a.list[t] : 0;
+    } else {
+        i = (a.order ? __ldg(&a.order[blockIdx.x]) : (int)blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
+        active = i < a.P;
+        if (MODE == 1 && blockIdx.x == 0 && threadIdx.x == 0) a.st->n_listed = -1;
+    }
+    float x = 0.f, y = 0.f, z = 0.f;
+    double xd = 0.0, yd = 0.0, zd = 0.0;
+    if (active) {
+        x = a.px[i]; y = a.py[i]; z = a.pz[i];
+        xd = x; yd = y; zd = z;
+        if (F64) { xd = a.px64[i]; yd = a.py64[i]; zd = a.pz64[i]; }
+    }
+    Nearest best;
+    best.d2 = DBL_MAX * 2.0;   // +inf
+    best.ub = FLT_MAX * 2.0f;
+    best.lb2 = FLT_MAX * 2.0f;
+    best.slot = -1;
+    best.face = 0x7fffffff;
+    best = find_nearest<F64, STATS>(a, i, active, x, y, z, xd, yd, zd, best);
+    if (active && best.slot < 0) {      // non-finite query: nothing compares; flag it (the reference asserts on NaN) and stay in bounds
+        a.st->nan_flag = 1;
+        best.slot = 0;
+        best.lb2 = 0.f;
+    }
+    if (active) {
+        a.slot[i] = best.slot;
+        a.lbd[i] = __fsqrt_rd(best.lb2);          // distance every OTHER centroid is at least away (k_sweep1_fast)
+    }
+    point_tail<F64, MODE>(a, i, active, best.slot, best.d2, x, y, z, xd, yd, zd);
+}
+
+// ---- exact skip of the search (k-means style bounds) ---------------------------------------------------------------
+// Points never move and the centroids move a little per iteration, so most nearest faces do not change.  Every full search
+// leaves, per point, lbd = a lower bound of the distance to every centroid OTHER than the winner.  Before the next sweep
+// k_refit_centroids measures how far every centroid has moved (max per cell of a pyramid of grids over the key grid,
+// levels 0 = whole mesh .. NW_DG_TOP = 2^NW_DG_TOP cells per axis; k_dilate_dgrid takes the max over the 3x3x3
+// neighbourhood).  For a point whose winner s is now at exact distance d1, with L the finest level whose cells are wider than
+// d1 (+ slack):
+//   * a centroid keyed inside the 3x3x3 block of level-L cells around the point was at least lbd away and has moved at
+//     most delta_L(block), so it is at least lbd - delta_L away now;
+//   * a centroid keyed outside that block is at least one cell width W_L, minus how far centroids have left their key
+//     cells (cell_escape), away.
+// If d1 is strictly below both, s is still THE nearest centroid (strictly: no tie to resolve) and the tree is not
+// touched; min(both) is the new lbd.  Otherwise the point goes on the list for the packet search (LIST = true above).
+// Level 0 is one cell = the whole mesh: no "outside", delta_0 = the largest displacement anywhere.
+
+struct FastArgs {
+    const float *dgrid;            // dilated displacement pyramid
+    unsigned char *flag;           // 1 = needs the search
+};
+
+template <bool F64>
+__global__ void __launch_bounds__(256) k_sweep1_fast(const __grid_constant__ Sweep1Args a, const FastArgs fa) {
+    if (a.st->stop) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < a.P;
+    float x = 0.f, y = 0.f, z = 0.f;
+    double xd = 0.0, yd = 0.0, zd = 0.0, d2 = 0.0;
+    int s = -1;
+    bool keep = false;
+    if (active) {
+        x = a.px[i]; y = a.py[i]; z = a.pz[i];
+        xd = x; yd = y; zd = z;
+        if (F64) { xd = a.px64[i]; yd = a.py64[i]; zd = a.pz64[i]; }
+        s = a.slot[i];
+        if (s >= 0) {
+            const float4 c = __ldg(&a.tv.cent[s]);
+            if (F64) { QueryF64 q; q.set(xd, yd, zd); d2 = q.d2(c); }
+            else { QueryF32 q; q.x = x; q.y = y; q.z = z; d2 = q.d2(c); }
+            const float d1 = __fsqrt_ru(__double2float_ru(d2));
+            const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
+            // finest level whose cell width exceeds d1 + what the centroids may have left their key cells by
+            const float gx = (x - a.tv.grid_lo.x) * a.tv.grid_inv, gy = (y - a.tv.grid_lo.y) * a.tv.grid_inv, gz = (z - a.tv.grid_lo.z) * a.tv.grid_inv;
+            const bool inside = gx >= 0.f && gx < 1024.f && gy >= 0.f && gy < 1024.f && gz >= 0.f && gz < 1024.f && a.tv.grid_inv > 0.f;
+            int L = 0;
+            float wall = __int_as_float(0x7f800000);
+            if (inside) {
+                const float lost = (a.st->cell_escape + 1e-3f) * a.tv.grid_cellw + 2.f * eps;
+#pragma unroll
+                for (int l = NW_DG_TOP; l >= 1; --l) {
+                    const float w = __fsub_rd((float)(1024 >> l) * a.tv.grid_cellw, lost);
+                    if (L == 0 && d1 < w) { L = l; wall = w; }
+                }
+            }
+            const int sh = 10 - L;
+            const int cell = L ? (int)(((unsigned)gx >> sh) | (((unsigned)gy >> sh) << L) | (((unsigned)gz >> sh) << (2 * L))) : 0;
+            const float moved = __ldg(&fa.dgrid[nw_dg_off(L) + cell]);
+            const float nb = __fmul_rd(fminf(__fsub_rd(a.lbd[i], moved), wall), NW_LBD_SAFE);
+            keep = d1 < nb;                                  // false for NaN anywhere
+            if (keep) a.lbd[i] = nb;
+        }
+        fa.flag[i] = keep ? 0 : 1;
+    }
+    point_tail<F64, 1>(a, i, keep, s, d2, x, y, z, xd, yd, zd);
+}
+
+// 3x3x3 maximum of every level of the displacement pyramid
+__global__ void __launch_bounds__(256) k_dilate_dgrid(const float *__restrict__ raw, float *__restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NW_DG_CELLS) return;
+    int L = 0;
+    while (L < NW_DG_TOP && t >= nw_dg_off(L + 1)) ++L;
+    const int c = t - nw_dg_off(L), n = 1 << L, m = n - 1;
+    const int cx = c & m, cy = (c >> L) & m, cz = c >> (2 * L);
+    float v = 0.f;
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int X = cx + dx, Y = cy + dy, Z = cz + dz;
+                if (X < 0 || Y < 0 || Z < 0 || X >= n || Y >= n || Z >= n) continue;
+                v = fmaxf(v, raw[nw_dg_off(L) + (X | (Y << L) | (Z << (2 * L)))]);   // +inf (NaN displacement) propagates
+            }
+    out[t] = v;
 }
 
 // ---- single-operator forms ------------------------------------------------------------------------
@@ -891,6 +981,7 @@ static Sweep1Args make_args(nw_ctx *h) {
     else { a.wx = a.wy = a.wz = nullptr; }
     a.sinv_scalar = h->sinv_scalar; a.wmean = h->wmean;
     a.slot = h->slot;
+    a.lbd = h->lbd; a.list = h->slist; a.list_n = h->slist_n;
     a.w0 = h->w0; a.w1 = h->w1; a.w2 = h->w2; a.rx = h->rx; a.ry = h->ry; a.rz = h->rz;
     a.posq = h->posq; a.sfaces = h->sfaces; a.tl = h->tl; a.F = h->F;
     a.tv.cent = h->cent; a.tv.boxes = h->boxes; a.tv.parent = h->parent_g; a.tv.kids = h->kids; a.tv.leaf_of_slot = h->leaf_of_slot;
@@ -995,13 +1086,63 @@ int nw_launch_sweep1(nw_ctx *h, bool scatter) {
     const bool stats = (h->profile & 2) != 0;
 #endif
     if (h->px64) {
-        if (stats) { if (scatter) k_sweep1<true, 1, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, true><<<G, B, 0, h->stream>>>(a); }
-        else { if (scatter) k_sweep1<true, 1, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, false><<<G, B, 0, h->stream>>>(a); }
+        if (stats) { if (scatter) k_sweep1<true, 1, true, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, true, false><<<G, B, 0, h->stream>>>(a); }
+        else { if (scatter) k_sweep1<true, 1, false, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, false, false><<<G, B, 0, h->stream>>>(a); }
     } else {
-        if (stats) { if (scatter) k_sweep1<false, 1, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, true><<<G, B, 0, h->stream>>>(a); }
-        else { if (scatter) k_sweep1<false, 1, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false><<<G, B, 0, h->stream>>>(a); }
+        if (stats) { if (scatter) k_sweep1<false, 1, true, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, true, false><<<G, B, 0, h->stream>>>(a); }
+        else { if (scatter) k_sweep1<false, 1, false, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false, false><<<G, B, 0, h->stream>>>(a); }
     }
     NW_LAUNCH_CHECK();
+    h->bounds_valid = true;             // every point now carries the bound of a complete search at the current centroids
+    return NW_OK;
+}
+
+int nw_dilate_dgrid(nw_ctx *h) {
+    k_dilate_dgrid<<<nw_grid(NW_DG_CELLS, 256), 256, 0, h->stream>>>(h->dg_raw, h->dg);
+    NW_LAUNCH_CHECK();
+    return NW_OK;
+}
+
+// buffers of the fast path; called outside stream capture (nw_search, before the first iteration)
+int nw_sweep1_prepare(nw_ctx *h) {
+    if (h->P == 0) return NW_OK;
+    NW_CHECK(nw_alloc(h, &h->sflag, (size_t)h->P)); NW_CHECK(nw_alloc(h, &h->slist, (size_t)h->P));
+    NW_CHECK(nw_alloc(h, &h->slist_n, 4));
+    size_t tmp = 0;
+    cub::DeviceSelect::Flagged(nullptr, tmp, thrust::counting_iterator<int>(0), h->sflag, h->slist, h->slist_n, (int)h->P, h->stream);
+    if (tmp > h->cub_tmp_bytes) { NW_CHECK(nw_alloc(h, (char **)&h->cub_tmp, tmp)); h->cub_tmp_bytes = tmp; }
+    return NW_OK;
+}
+
+// Sweep with the search skipped wherever the bounds of the previous sweep still prove the nearest face (k_sweep1_fast);
+// the remaining points are compacted in Hilbert order and searched as packets.  Three stages so that they can be timed.
+int nw_launch_sweep1_fast(nw_ctx *h) {
+    if (h->P == 0) return NW_OK;
+    NW_ARG(h->bounds_valid && h->sflag && h->dg, "sweep1_fast: no bounds from a previous sweep");
+    Sweep1Args a = make_args(h);
+    FastArgs fa;
+    fa.dgrid = h->dg; fa.flag = h->sflag;
+    NW_CHECK(nw_stage_begin(h, 10));
+    if (h->px64) k_sweep1_fast<true><<<nw_grid(h->P, 256), 256, 0, h->stream>>>(a, fa);
+    else k_sweep1_fast<false><<<nw_grid(h->P, 256), 256, 0, h->stream>>>(a, fa);
+    NW_LAUNCH_CHECK();
+    NW_CHECK(nw_stage_end(h, 10));
+    NW_CHECK(nw_stage_begin(h, 11));
+    size_t tmp = h->cub_tmp_bytes;
+    NW_CUDA(cub::DeviceSelect::Flagged(h->cub_tmp, tmp, thrust::counting_iterator<int>(0), h->sflag, h->slist, h->slist_n, (int)h->P, h->stream));
+    h->launches += 2;
+    NW_CHECK(nw_stage_end(h, 11));
+    NW_CHECK(nw_stage_begin(h, 12));
+#ifdef NW_LEVEL_STATS
+    const bool stats = true;
+#else
+    const bool stats = (h->profile & 2) != 0;
+#endif
+    const int G = nw_grid(h->P, 128);
+    if (h->px64) { if (stats) k_sweep1<true, 1, true, true><<<G, 128, 0, h->stream>>>(a); else k_sweep1<true, 1, false, true><<<G, 128, 0, h->stream>>>(a); }
+    else { if (stats) k_sweep1<false, 1, true, true><<<G, 128, 0, h->stream>>>(a); else k_sweep1<false, 1, false, true><<<G, 128, 0, h->stream>>>(a); }
+    NW_LAUNCH_CHECK();
+    NW_CHECK(nw_stage_end(h, 12));
     return NW_OK;
 }
 
@@ -1221,6 +1362,7 @@ int nw_bench_launch(nw_ctx *h, const char *name) {
     } else if (n == "mesh_prior") {
         return nw_launch_mesh_prior(h, true);
     } else if (n == "refit") {
+        h->bounds_valid = false;                 // a refit without a sweep: the measured displacements are not consumed
         return nw_tree_refit(h);
     } else if (n == "allreduce_acc") {
         return nw_allreduce_acc(h);              // N > 1: the per-iteration collective alone, all ranks in lockstep

@@ -6,7 +6,7 @@ from ch_shrinkwrap_b200.mesh_conj_grad import ShrinkwrapMeshConjGrad
 mesh, pts, sig, cfg = bench.build_workload('c3', 1234)
 s_inv = (1.0 / sig.ravel()).astype(np.float32)
 start = mesh._vertices['position'].copy()
-sg = (ctypes.c_double * 10)(); sm = ctypes.c_double()
+sg = (ctypes.c_double * 16)(); sm = ctypes.c_double()
 for rep in range(2):
     mesh._vertices['position'][:] = start; mesh.update_geometry()
     cg = ShrinkwrapMeshConjGrad(mesh, pts); mesh.cg = cg

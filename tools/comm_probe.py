@@ -22,7 +22,7 @@ h = mesh._nw_session.handle
 h.call('nw_set_profile', 1)
 dist.barrier()
 bench.run_blocks(mesh, pts, s_inv, 5.0, 10, 5)
-sg = (ctypes.c_double * 10)()
+sg = (ctypes.c_double * 16)()
 h.call('nw_get_profile', sg, None, None)
 ms = ctypes.c_float()
 h.call('nw_bench_kernel', b'allreduce_acc', 20, ctypes.byref(ms))

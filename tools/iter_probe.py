@@ -5,7 +5,7 @@ import bench
 from ch_shrinkwrap_b200.mesh_conj_grad import ShrinkwrapMeshConjGrad
 mesh, pts, sig, cfg = bench.build_workload('c3', 1234)
 s_inv = (1.0 / sig.ravel()).astype(np.float32)
-st = (ctypes.c_uint64 * 4)(); sg = (ctypes.c_double * 10)(); sm = ctypes.c_double()
+st = (ctypes.c_uint64 * 4)(); sg = (ctypes.c_double * 16)(); sm = ctypes.c_double()
 for blk in range(5):
     cg = ShrinkwrapMeshConjGrad(mesh, pts); mesh.cg = cg
     row = []

@@ -7,7 +7,7 @@ from ch_shrinkwrap_b200.mesh_conj_grad import ShrinkwrapMeshConjGrad
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 mesh, pts, sig, cfg = bench.build_workload('c3', 1234)
 s_inv = (1.0 / sig.ravel()).astype(np.float32)
-st = (ctypes.c_uint64 * 4)(); sg = (ctypes.c_double * 10)(); sm = ctypes.c_double()
+st = (ctypes.c_uint64 * 4)(); sg = (ctypes.c_double * 16)(); sm = ctypes.c_double()
 for blk in range(n // 5):
     cg = ShrinkwrapMeshConjGrad(mesh, pts); mesh.cg = cg
     cg._h.call('nw_set_profile', int(os.environ.get('NW_PROFILE', '1')))

@@ -7,7 +7,7 @@ mesh, pts, sig, cfg = bench.build_workload(wl, 1234)
 s_inv=(1.0/sig.ravel()).astype(np.float32)
 cg=ShrinkwrapMeshConjGrad(mesh, pts); mesh.cg=cg
 P=len(pts)
-st=(ctypes.c_uint64*4)(); sg=(ctypes.c_double*10)(); cg._h.call('nw_set_profile', int(os.environ.get('NW_PROFILE', '1')))
+st=(ctypes.c_uint64*4)(); sg=(ctypes.c_double*16)(); cg._h.call('nw_set_profile', int(os.environ.get('NW_PROFILE', '1')))
 sm=ctypes.c_double()
 for it in range(8):
     if it == 4: cg._upload_topology()
