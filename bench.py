@@ -38,7 +38,7 @@ WORKLOADS = {
 }
 REFERENCE_SAMPLE = 'c2'   # bounded CPU sample: same shape, same 20 localisations per vertex, 1/10 of c3
 STAGES = ['refit', 'shift', 'sweep1', 'allreduce_acc', 'mesh_prior', 'sweep2', 'allreduce_scalars', 'solve_update', 'seed_leaders',
-          'topology_build', 'sweep1_fast', 'sweep1_select', 'sweep1_list']
+          'topology_build']
 
 
 def build_workload(name, seed):

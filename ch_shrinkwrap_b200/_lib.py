@@ -51,10 +51,8 @@ SIGNATURES = {
     'nw_sync': (c_int, [c_void_p]),
     'nw_set_profile': (c_int, [c_void_p, c_int]),
     'nw_get_stage_trace': (c_int, [c_void_p, _i, _f, c_int, POINTER(c_int)]),
-    'nw_get_search_counts': (c_int, [c_void_p, _d, c_int]),
     'nw_get_profile': (c_int, [c_void_p, _d, POINTER(c_int64), _d]),
     'nw_get_traversal_stats': (c_int, [c_void_p, POINTER(c_uint64)]),
-    'nw_debug_dgrid': (c_int, [c_void_p, _f, _f, POINTER(c_int)]),
     'nw_debug_tree': (c_int, [c_void_p, c_int, _f, POINTER(c_int), POINTER(c_int)]),
     'nw_launch_count': (c_int64, [c_void_p]),
 }

@@ -23,7 +23,7 @@ extern "C" int nw_create(int device, nw_ctx **out) {
         return NW_ERR_CUDA;
     }
     if (cudaMalloc((void **)&h->st, sizeof(SolverState)) != cudaSuccess ||
-        cudaMalloc((void **)&h->hist, sizeof(double) * 6 * NW_MAX_ITERS) != cudaSuccess) {
+        cudaMalloc((void **)&h->hist, sizeof(double) * 5 * NW_MAX_ITERS) != cudaSuccess) {
         delete h;
         return NW_ERR_CUDA;
     }
@@ -44,7 +44,7 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free(&h->px64); nw_free(&h->py64); nw_free(&h->pz64);
     nw_free(&h->sx); nw_free(&h->sy); nw_free(&h->sz);
     nw_free(&h->wx); nw_free(&h->wy); nw_free(&h->wz);
-    nw_free(&h->pmask); nw_free(&h->perm); nw_free(&h->slot); nw_free(&h->lbd); nw_free(&h->sflag); nw_free(&h->slist); nw_free(&h->slist_n); nw_free(&h->dg_raw); nw_free(&h->dg); nw_free(&h->fx); nw_free(&h->fy); nw_free(&h->fz); nw_free(&h->fkeys);
+    nw_free(&h->pmask); nw_free(&h->perm); nw_free(&h->slot); nw_free(&h->fx); nw_free(&h->fy); nw_free(&h->fz); nw_free(&h->fkeys);
     nw_free(&h->w0); nw_free(&h->w1); nw_free(&h->w2);
     nw_free(&h->rx); nw_free(&h->ry); nw_free(&h->rz);
     nw_free(&h->posq); nw_free(&h->nrmq); nw_free(&h->faces); nw_free(&h->nbrT); nw_free(&h->valence); nw_free(&h->valid); nw_free(&h->stage_nbr); nw_free(&h->stage_hev); nw_free(&h->tb_small); nw_free(&h->tb_i0); nw_free(&h->tb_i1); nw_free(&h->tb_u0); nw_free(&h->tb_u1); nw_free(&h->tb_u2); nw_free(&h->fcells); nw_free(&h->parent_g); nw_free(&h->kids);
@@ -90,7 +90,7 @@ static int upload_state(nw_ctx *h, const SolverState &s0) {
 }
 
 // per-stage CUDA events (only when profiling is switched on)
-int nw_stage_begin(nw_ctx *h, int stage) {
+static int stage_begin(nw_ctx *h, int stage) {
     if (!(h->profile & 1)) return NW_OK;
     if (h->ev_used + 2 > h->ev_pool.size()) {
         for (int k = 0; k < 64; ++k) { cudaEvent_t e; NW_CUDA(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
@@ -100,24 +100,20 @@ int nw_stage_begin(nw_ctx *h, int stage) {
     h->stage_launches[stage] -= h->launches;
     return NW_OK;
 }
-int nw_stage_end(nw_ctx *h, int stage) {
+static int stage_end(nw_ctx *h, int stage) {
     if (!(h->profile & 1)) return NW_OK;
     NW_CUDA(cudaEventRecord(h->ev_pool[h->ev_used++], h->stream));
     h->stage_launches[stage] += h->launches;
     return NW_OK;
 }
-#define NW_STAGE(id, call) do { NW_CHECK(nw_stage_begin(h, id)); NW_CHECK(call); NW_CHECK(nw_stage_end(h, id)); } while (0)
+#define NW_STAGE(id, call) do { NW_CHECK(stage_begin(h, id)); NW_CHECK(call); NW_CHECK(stage_end(h, id)); } while (0)
 
 // one full iteration, enqueued asynchronously
 static int enqueue_iteration(nw_ctx *h, int it, int last_step) {
     NW_STAGE(1, nw_set_acc_shifts(h));             // vertex bbox -> fixed-point scales, rounding slack of the box tests
     NW_STAGE(0, nw_tree_refit(h));                 // centroids + boxes at the current f  (:443)
     if (h->seeds_cold) NW_STAGE(8, nw_launch_seed_leaders(h));   // first iteration after a topology upload only
-    // NN, weights, A f, residual, AH res, AH 1  (:222-253): with the bounds of the previous sweep the search is skipped
-    // wherever they still prove the nearest face (stages 10-12), otherwise every point is searched
-    static const bool no_skip = getenv("NW_NO_SKIP") != nullptr;                  // A/B switch for measurements
-    if (h->bounds_valid && !no_skip && !h->seeds_cold) NW_CHECK(nw_launch_sweep1_fast(h));
-    else NW_STAGE(2, nw_launch_sweep1(h, true));
+    NW_STAGE(2, nw_launch_sweep1(h, true));        // NN, weights, A f, residual, AH res, AH 1  (:222-253)
     if (h->nranks > 1) NW_STAGE(3, nw_allreduce_acc(h));   // N>1: vertex-gradient allreduce
     NW_STAGE(4, nw_launch_mesh_prior(h, true));    // S0, ncc, prefs, S1, S^T S  (:224,253-258)
     NW_STAGE(5, nw_launch_sweep2(h));              // A S_k and Gram sums  (conj_grad.py:197-203)
@@ -144,16 +140,6 @@ extern "C" int nw_get_traversal_stats(nw_ctx *h, uint64_t out[4]) {
     for (int k = 0; k < 4; ++k) out[k] = r.trav[k];
     return NW_OK;
 }
-// diagnosis: the displacement pyramid of the last refit (NW_DG_CELLS floats each: per-cell maxima, 3x3x3-dilated maxima)
-extern "C" int nw_debug_dgrid(nw_ctx *h, float *raw, float *dilated, int *n_cells) {
-    if (!h) return NW_ERR_ARG;
-    if (n_cells) *n_cells = NW_DG_CELLS;
-    NW_ARG(h->dg_raw && h->dg, "nw_debug_dgrid: no topology");
-    NW_CUDA(cudaSetDevice(h->device));
-    if (raw) NW_CUDA(cudaMemcpy(raw, h->dg_raw, sizeof(float) * NW_DG_CELLS, cudaMemcpyDeviceToHost));
-    if (dilated) NW_CUDA(cudaMemcpy(dilated, h->dg, sizeof(float) * NW_DG_CELLS, cudaMemcpyDeviceToHost));
-    return NW_OK;
-}
 // diagnosis: copy the boxes of one tree level (16 floats each) and the level sizes
 extern "C" int nw_debug_tree(nw_ctx *h, int level, float *boxes16, int *counts, int *n_levels) {
     if (!h) return NW_ERR_ARG;
@@ -162,14 +148,6 @@ extern "C" int nw_debug_tree(nw_ctx *h, int level, float *boxes16, int *counts, 
     if (counts) for (int l = 0; l < h->tl.n_levels; ++l) counts[l] = h->tl.count[l];
     if (boxes16 && level >= 0 && level < h->tl.n_levels)
         NW_CUDA(cudaMemcpy(boxes16, h->boxes + h->tl.off[level], sizeof(Box) * h->tl.count[level], cudaMemcpyDeviceToHost));
-    return NW_OK;
-}
-// searched points per iteration of the last nw_search call (-1 = full sweep): how often the bound check of k_sweep1_fast failed
-extern "C" int nw_get_search_counts(nw_ctx *h, double *listed, int n) {
-    if (!h || !listed) return NW_ERR_ARG;
-    NW_ARG(n >= 0 && n <= NW_MAX_ITERS, "nw_get_search_counts: n out of range");
-    NW_CUDA(cudaSetDevice(h->device));
-    NW_CUDA(cudaMemcpy(listed, h->hist + (size_t)5 * NW_MAX_ITERS, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return NW_OK;
 }
 // the stage intervals of the last profiled nw_search call in launch order (stage id, ms); *n = how many there are
@@ -199,7 +177,6 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     NW_ARG(n_prev >= 0 && (n_prev == 0 || prev_tests), "nw_search: bad prev_tests");
     NW_CUDA(cudaSetDevice(h->device));
     NW_CHECK(ensure_partials(h));
-    NW_CHECK(nw_sweep1_prepare(h));
     SolverState s;
     memset(&s, 0, sizeof(s));
     s.lam = lam;

@@ -8,16 +8,12 @@
 #include "../../include/nanowrap.h"
 
 #define NW_MAX_LEVELS 12
-#define NW_DG_TOP 6            // finest level of the displacement pyramid (2^6 cells per axis), see sweep.cu: k_sweep1_fast
-#define NW_DG_CELLS 299593     // cells of levels 0..NW_DG_TOP: (8^(NW_DG_TOP+1) - 1) / 7
-__host__ __device__ __forceinline__ int nw_dg_off(int L) { return (int)(((1u << (3 * L)) - 1u) / 7u); }
 #define NW_MAX_ITERS 4096
 #ifndef NW_S2_PTS
 #define NW_S2_PTS 4      // k_sweep2: points per thread (their dependent load chains slot -> face -> S overlap); sizes its partials
 #endif
-#define NW_N_STAGES 13   // refit, shift, sweep1 (full search), allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders,
-                         // topology_build (device side of nw_set_topology*: feet, unpack, Hilbert sort, tables, frames),
-                         // sweep1_fast (bound check + settled points), sweep1_select (compaction), sweep1_list (search of the rest)
+#define NW_N_STAGES 10   // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders,
+                         // topology_build (device side of nw_set_topology*: feet, unpack, Hilbert sort, tables, frames)
 
 // Node bound = ORIENTED box: a surface patch is thin along its normal and tilted against the coordinate axes, so an
 // axis-aligned box is mostly empty space.  Axes n (patch normal), t1 = tangent_of(n), t2 = n x t1; one interval per axis.
@@ -57,7 +53,6 @@ struct SolverState {
     int stop;                     // stop rule fired: remaining kernels become no-ops
     int nan_flag;
     int n_search;                 // 2 on the first iteration of a call, 3 afterwards (last_step)
-    int n_listed;                 // points the last sweep had to search (-1: all of them, a full sweep); history row 5
     int acc_shift;                // fixed-point fraction bits of the adjoint accumulators
     int infl_shift;               // ditto for the AH*1 accumulator
     int bbox[6];                  // ordered-int bounding box of the vertices (k_shift_partial -> k_shift_final)
@@ -91,11 +86,6 @@ struct nw_ctx {
     uint8_t *pmask = nullptr;    // 3 bits per point when has_mask
     int *perm = nullptr;         // sorted position -> caller's index
     int *slot = nullptr;         // nearest sorted-centroid slot per point (-1 = none yet)
-    float *lbd = nullptr;        // per point: every centroid other than slot[] is at least this far away (sweep.cu: k_sweep1_fast)
-    unsigned char *sflag = nullptr;   // per point: 1 = k_sweep1_fast could not settle it
-    int *slist = nullptr, *slist_n = nullptr;   // those points, compacted in Hilbert order, and their number (device)
-    float *dg_raw = nullptr, *dg = nullptr;     // pyramid of per-cell centroid displacements since the last sweep: raw maxima, 3x3x3-dilated
-    bool bounds_valid = false;   // lbd[], slot[] and cent[] describe the same sweep (cleared by anything that moves the mesh behind its back)
     float *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
     float *rx = nullptr, *ry = nullptr, *rz = nullptr;
     float bbox_pts[6] = {0, 0, 0, 0, 0, 0};
@@ -133,7 +123,7 @@ struct nw_ctx {
     double *partials = nullptr;                  // per-CTA partial sums
     int n_partials = 0;
     SolverState *st = nullptr;                   // device
-    double *hist = nullptr;                      // device: 6 x NW_MAX_ITERS (tests, ress, prefs, cpred, wpred, searched points)
+    double *hist = nullptr;                      // device: 5 x NW_MAX_ITERS (tests, ress, prefs, cpred, wpred)
     void *cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
     float *scratchM = nullptr;                   // 3M floats
@@ -262,8 +252,6 @@ __host__ __device__ __forceinline__ void hilbert_axes_to_transpose(U &x, U &y, U
 int nw_tree_build(nw_ctx *h);                 // after topology upload: Hilbert sort of faces, octree tables, frames
 int nw_tree_refit(nw_ctx *h);                 // every iteration: centroids + boxes at the current f
 int nw_launch_sweep1(nw_ctx *h, bool scatter);
-int nw_launch_sweep1_fast(nw_ctx *h);         // bound check + list search; needs h->bounds_valid
-int nw_sweep1_prepare(nw_ctx *h);             // allocations of the fast path (outside stream capture)
 int nw_launch_seed_leaders(nw_ctx *h);
 int nw_save_feet(nw_ctx *h);
 int nw_launch_sweep2(nw_ctx *h);
@@ -275,5 +263,3 @@ int nw_check_replicated(nw_ctx *h, const long long *vals, int n, const char *wha
 int nw_allreduce_scalars(nw_ctx *h);
 int nw_set_acc_shifts(nw_ctx *h);
 int nw_curvature_relaunch(nw_ctx *h);
-int nw_stage_begin(nw_ctx *h, int stage);      // api.cu: per-stage CUDA events (profiling only)
-int nw_stage_end(nw_ctx *h, int stage);

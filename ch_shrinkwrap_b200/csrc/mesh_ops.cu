@@ -251,7 +251,6 @@ __global__ void k_solve(const double *__restrict__ mesh_partials, int n_mesh_blo
     hist[2 * NW_MAX_ITERS + iter_index] = sqrt(prefs2);
     hist[3 * NW_MAX_ITERS + iter_index] = st->c0 + cHc - cGc;
     hist[4 * NW_MAX_ITERS + iter_index] = prefs2 + cHwc - cGw;
-    hist[5 * NW_MAX_ITERS + iter_index] = (double)st->n_listed;
     // histories for the stop rule (:1009-1016): evaluated at the top of the NEXT iteration
     if (st->n_tests < 3) st->last_tests[st->n_tests++] = test;
     else { st->last_tests[0] = st->last_tests[1]; st->last_tests[1] = st->last_tests[2]; st->last_tests[2] = test; }

@@ -148,7 +148,6 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
     h->seeds_cold = true;
     h->order_stale = true;
     h->feet_valid = false;
-    h->bounds_valid = false;
     NWX(nw_alloc(h, &h->sp_pts, sizeof(T) * 3 * (size_t)P));
     T *d_pts = (T *)h->sp_pts;
     NWX(nw_h2d(h, d_pts, pts_host, sizeof(T) * 3 * (size_t)P));
@@ -278,7 +277,6 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
     if (h->weights_mode == 0) nw_free(&h->pmask);
     // per-point outputs
     NWX(nw_alloc(h, &h->slot, (size_t)P));
-    NWX(nw_alloc(h, &h->lbd, (size_t)P));
     NWX(nw_alloc(h, &h->w0, (size_t)P)); NWX(nw_alloc(h, &h->w1, (size_t)P)); NWX(nw_alloc(h, &h->w2, (size_t)P));
     NWX(nw_alloc(h, &h->rx, (size_t)P)); NWX(nw_alloc(h, &h->ry, (size_t)P)); NWX(nw_alloc(h, &h->rz, (size_t)P));
     NWX(nw_alloc(h, &h->fx, (size_t)P)); NWX(nw_alloc(h, &h->fy, (size_t)P)); NWX(nw_alloc(h, &h->fz, (size_t)P));   // foot points (seeds across uploads)

@@ -10,7 +10,6 @@
 // Determinism: the adjoint accumulates in 64-bit fixed point (integer atomics are order-independent,
 // float atomics are not); the Gram sums use a fixed thread->point assignment and a fixed two-stage tree.
 #include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
@@ -68,17 +67,10 @@ struct QueryF64 {
 struct Nearest {
     double d2;
     float ub;      // d2 rounded up to float: prune bound for the float32 lower bounds
-    float lb2;     // lower bound (float32, rounded down) of the SQUARED fp64 distance to every centroid other than `slot`
-                   // that the search has accounted for: pruned nodes, pruned or losing centroids (see k_sweep1_fast)
     int slot, face;
-    __device__ __forceinline__ void lose(float v) { lb2 = fminf(lb2, v); }
     __device__ __forceinline__ void offer(double v, int s, int f) {
-        if (s == slot) return;                 // the current best seen again (its leaf is searched like any other)
         // strict minimum; exact fp64 ties -> lowest face index (contract of SURVEY 7.3)
-        if (v < d2 || (v == d2 && f < face)) {
-            lose(__double2float_rd(d2));       // the previous best is now one of the others (+inf when there was none)
-            d2 = v; slot = s; face = f; ub = __double2float_ru(v);
-        } else lose(__double2float_rd(v));
+        if (v < d2 || (v == d2 && f < face)) { d2 = v; slot = s; face = f; ub = __double2float_ru(v); }
     }
 };
 
@@ -207,9 +199,8 @@ struct Traversal {
         const unsigned m = (d | (d >> 10) | (d >> 20)) & 1023u;       // highest differing bit over the three axes
         return m ? __clz(m) - 22 : 10;
     }
-    // true if nothing outside the query's level-`level` cube can beat the current best; *out2 = the squared distance
-    // everything outside that cube is at least away
-    __device__ __forceinline__ bool cube_clear(int level, float *out2) const {
+    // true if nothing outside the query's level-`level` cube can beat the current best
+    __device__ __forceinline__ bool cube_clear(int level) const {
         const int s = 10 - level;
         const float w = (float)(1u << s);
         const float gx = grid(q.fx(), tv.grid_lo.x), gy = grid(q.fy(), tv.grid_lo.y), gz = grid(q.fz(), tv.grid_lo.z);
@@ -218,8 +209,7 @@ struct Traversal {
         const float cl = fminf(fminf(fminf(fx, w - fx), fminf(fy, w - fy)), fminf(fz, w - fz));
         // slack: rounding of g for the query and for the centroids (a few ulp of 1024 each), of the coordinates (eps)
         const float m = (cl - escape - 1e-3f) * tv.grid_cellw - 2.f * eps;
-        *out2 = __fmul_rd(__fmul_rd(m, m), 0.99999f);
-        return m > 0.f && *out2 > best.ub;
+        return m > 0.f && __fmul_rd(__fmul_rd(m, m), 0.99999f) > best.ub;
     }
 
     __device__ __forceinline__ void leaf(int node) {
@@ -227,9 +217,7 @@ struct Traversal {
         if constexpr (COUNT) ++n_leaves;
         for (int s = k.x; s < k.x + k.y; ++s) {
             const float4 c = __ldg(&tv.cent[s]);
-            const float l = q.lb_box(c, c);
-            if (l <= best.ub) { if constexpr (COUNT) ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
-            else best.lose(l);
+            if (q.lb_box(c, c) <= best.ub) { if constexpr (COUNT) ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
         }
     }
 #ifdef NW_LEVEL_STATS
@@ -249,12 +237,10 @@ struct Traversal {
         while (true) {
             int link;                                      // first child | (node is a last child) << 31, stored in the node itself
             if (tick()) return;
-            const float lb = node_lb(q, &tv.boxes[node], eps, &link);
-            const bool pass = any(lb <= best.ub);
+            const bool pass = any(node_lb(q, &tv.boxes[node], eps, &link) <= best.ub);
 #ifdef NW_LEVEL_STATS
             count_test(node, pass);
 #endif
-            if (!pass) best.lose(lb);                      // skipped for every lane: this lane's bound covers the whole subtree
             if (pass) {
                 if (node >= tv.leaf0) leaf(node);
                 else { node = link & 0x7fffffff; continue; }
@@ -284,16 +270,8 @@ struct Traversal {
         const QueryF32 pk_c = packet_centre();
         const int j = (int)(threadIdx.x & 31);
         bool hit = false;
-        float gone = __int_as_float(0x7f800000);              // distance bound of a sibling this lane prunes for the packet
-        if (j < n && c0 + j != skip) {
-            const float dc = __fsqrt_rd(node_lb(pk_c, &tv.boxes[c0 + j], eps));
-            hit = !(dc > reach);
-            if (!hit) gone = dc;
-        }
+        if (j < n && c0 + j != skip) hit = !(__fsqrt_rd(node_lb(pk_c, &tv.boxes[c0 + j], eps)) > reach);
         if constexpr (COUNT) ++n_tests;
-        // a sibling at distance dc from the packet centre is at least dc - pk_r from every lane (dc > reach >= pk_r)
-        const float g = __fsub_rd(__uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(gone))), pk_r);
-        best.lose(__fmul_rd(g, g));
         return __ballot_sync(0xffffffffu, hit);
     }
     // climb from a leaf (one of whose centroids was keyed into `cell`): at every level only the sibling subtrees are searched
@@ -301,9 +279,7 @@ struct Traversal {
         leaf(node);
         const int shared = shared_levels(cell);
         for (int level = tv.leaf_level; level >= 1; --level) {
-            float out2 = 0.f;
-            const bool clear = level <= shared && cube_clear(level, &out2);
-            if (all(!active || clear)) { if (clear) best.lose(out2); return; }
+            if (all(!active || (level <= shared && cube_clear(level)))) return;
             const int p = __ldg(&tv.parent[node]) & 0x7fffffff;
             const int2 k = __ldg(&tv.kids[p]);
             if constexpr (PACKET) {
@@ -379,8 +355,6 @@ struct Sweep1Args {
     const float *wx, *wy, *wz;     // weight arrays (may alias sigma_inv) or NULL
     float sinv_scalar, wmean;
     int *slot;
-    float *lbd;                    // per point: distance every centroid other than slot[] is at least away (k_sweep1_fast)
-    const int *list, *list_n;      // LIST mode of k_sweep1: the points that need the search
     float *w0, *w1, *w2, *rx, *ry, *rz;
     int two_limbs;                 // 1: every fixed-point term is below 2^53 in magnitude (group_sum2)
     const int *order;              // block schedule (see build_block_order) or NULL
@@ -460,7 +434,7 @@ __global__ void __launch_bounds__(128) k_seed_leaders(const __grid_constant__ Sw
     const int64_t i = t * 32;
     if (i >= a.P || a.slot[i] >= 0) return;
     Nearest best;
-    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.lb2 = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
+    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
     const float x = a.px[i], y = a.py[i], z = a.pz[i];
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
@@ -519,7 +493,7 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
         if (__ldg(&fkeys[mid]) < key) lo = mid + 1; else hi = mid;
     }
     Nearest best;
-    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.lb2 = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
+    best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
     QueryF32 q;
     q.x = x; q.y = y; q.z = z;
@@ -532,17 +506,38 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
     a.slot[i] = tr.best.slot;
 }
 
-// Everything that follows the nearest-face decision for one point: inverse-distance weights, A f, residual, and (MODE 1)
-// the deterministic adjoint scatter.  All 32 lanes of a warp must call it (the scatter sums inside the warp first);
-// `live` = this lane has a point and its nearest face `slot` at exact squared distance `d2near`.
-// MODE 0: weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
-template <bool F64, int MODE>
-__device__ __forceinline__ void point_tail(const Sweep1Args &a, int64_t i, bool live, int slot, double d2near, float x, float y, float z,
-                                           double xd, double yd, double zd) {
+// MODE 0: nearest face + weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
+#ifndef NW_S1_MINB
+#define NW_S1_MINB 16     // 32 registers, 64 warps per SM.  Measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 before the global-id tables; after them 48 regs 2.47, 40 regs 2.51, 32 regs 2.33 -- the packet walk is a dependent chain, occupancy hides it
+#endif
+template <bool F64, int MODE, bool STATS>
+__global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB) : NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
+    if (MODE == 1 && a.st->stop) return;
+
+    const int64_t i = (a.order ? __ldg(&a.order[blockIdx.x]) : (int)blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
+    const bool active = i < a.P;
+    float x = 0.f, y = 0.f, z = 0.f;
+    double xd = 0.0, yd = 0.0, zd = 0.0;
+    if (active) {
+        x = a.px[i]; y = a.py[i]; z = a.pz[i];
+        xd = x; yd = y; zd = z;
+        if (F64) { xd = a.px64[i]; yd = a.py64[i]; zd = a.pz64[i]; }
+    }
+    Nearest best;
+    best.d2 = DBL_MAX * 2.0;   // +inf
+    best.ub = FLT_MAX * 2.0f;
+    best.slot = -1;
+    best.face = 0x7fffffff;
+    best = find_nearest<F64, STATS>(a, i, active, x, y, z, xd, yd, zd, best);
+    if (active && best.slot < 0) {      // non-finite query: nothing compares; flag it (the reference asserts on NaN) and stay in bounds
+        a.st->nan_flag = 1;
+        best.slot = 0;
+    }
     float u0 = 0.f, u1 = 0.f, u2 = 0.f, r_x = 0.f, r_y = 0.f, r_z = 0.f;
     int4 sf = make_int4(0, 0, 0, 0);
-    if (live) {
-    sf = a.sfaces[slot];
+    if (active) {
+    a.slot[i] = best.slot;
+    sf = a.sfaces[best.slot];
     const float4 v0 = __ldg(&a.posq[sf.x]), v1 = __ldg(&a.posq[sf.y]), v2 = __ldg(&a.posq[sf.z]);
     // corner distances, mesh_conj_grad.py:491-495 (float32 points: all float32; float64 points: float64 then stored float32)
     float d0, d1, d2;
@@ -580,7 +575,7 @@ __device__ __forceinline__ void point_tail(const Sweep1Args &a, int64_t i, bool 
         wny = __fdiv_rn(a.wy == a.sy ? s_y : a.wy[i], a.wmean);
         wnz = __fdiv_rn(a.wz == a.sz ? s_z : a.wz[i], a.wmean);
     } else wnx = wny = wnz = a.sinv_scalar;
-    const double D = sqrt(d2near);
+    const double D = sqrt(best.d2);
     if (F64) {
         r_x = (float)((double)wnx * (xd - (double)afx)); r_y = (float)((double)wny * (yd - (double)afy)); r_z = (float)((double)wnz * (zd - (double)afz));
     } else {
@@ -598,15 +593,14 @@ __device__ __forceinline__ void point_tail(const Sweep1Args &a, int64_t i, bool 
     // Lanes whose point landed on the same face are summed inside the warp first (exact integer sums), so a face
     // costs 12 global RED.64 per warp instead of 12 per point and the lanes of a warp never collide on an address.
     const double sc = pow2d(a.st->acc_shift), sci = pow2d(a.st->infl_shift);
-    // lanes without a point share ONE group (they add zeros and never lead): REDUX runs once per distinct member mask
-    const int key = live ? slot : -1;
+    const int key = active ? best.slot : -1 - (int)(threadIdx.x & 31);
     const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const bool lead = live && ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1));
+    const bool lead = active && ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1));
     const float uw[3] = {u0, u1, u2};
     const int vid[3] = {sf.x, sf.y, sf.z};
-    const bool two = a.two_limbs != 0 && a.st->acc_shift > -60;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
+        const bool two = a.two_limbs != 0 && a.st->acc_shift > -60;
         const unsigned long long gx = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
         const unsigned long long gy = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
         const unsigned long long gz = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
@@ -616,141 +610,6 @@ __device__ __forceinline__ void point_tail(const Sweep1Args &a, int64_t i, bool 
             atomicAdd(dst + 0, gx); atomicAdd(dst + 1, gy); atomicAdd(dst + 2, gz); atomicAdd(dst + 3, gi);
         }
     }
-}
-
-// safety factor between the recorded float32 bounds and the comparison of fp64-evaluated distances (see k_sweep1_fast)
-#define NW_LBD_SAFE 0.999999f
-
-// Full search.  LIST = false: every point, blocks in the longest-first order (build_block_order);
-// LIST = true: only the points k_sweep1_fast could not settle (a.list[0 .. *a.list_n), in Hilbert order).
-#ifndef NW_S1_MINB
-#define NW_S1_MINB 16     // 32 registers, 64 warps per SM.  Measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 before the global-id tables; after them 48 regs 2.47, 40 regs 2.51, 32 regs 2.33 -- the packet walk is a dependent chain, occupancy hides it
-#endif
-template <bool F64, int MODE, bool STATS, bool LIST>
-__global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB) : NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
-    if (MODE == 1 && a.st->stop) return;
-    int64_t i;
-    bool active;
-    if constexpr (LIST) {
-        const int n = *a.list_n;
-        if (blockIdx.x == 0 && threadIdx.x == 0) a.st->n_listed = n;
-        const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        if ((int64_t)blockIdx.x * blockDim.x >= n) return;
-        active = t < n;
-        i = active ? a.list[t] : 0;
-    } else {
-        i = (a.order ? __ldg(&a.order[blockIdx.x]) : (int)blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
-        active = i < a.P;
-        if (MODE == 1 && blockIdx.x == 0 && threadIdx.x == 0) a.st->n_listed = -1;
-    }
-    float x = 0.f, y = 0.f, z = 0.f;
-    double xd = 0.0, yd = 0.0, zd = 0.0;
-    if (active) {
-        x = a.px[i]; y = a.py[i]; z = a.pz[i];
-        xd = x; yd = y; zd = z;
-        if (F64) { xd = a.px64[i]; yd = a.py64[i]; zd = a.pz64[i]; }
-    }
-    Nearest best;
-    best.d2 = DBL_MAX * 2.0;   // +inf
-    best.ub = FLT_MAX * 2.0f;
-    best.lb2 = FLT_MAX * 2.0f;
-    best.slot = -1;
-    best.face = 0x7fffffff;
-    best = find_nearest<F64, STATS>(a, i, active, x, y, z, xd, yd, zd, best);
-    if (active && best.slot < 0) {      // non-finite query: nothing compares; flag it (the reference asserts on NaN) and stay in bounds
-        a.st->nan_flag = 1;
-        best.slot = 0;
-        best.lb2 = 0.f;
-    }
-    if (active) {
-        a.slot[i] = best.slot;
-        a.lbd[i] = __fsqrt_rd(best.lb2);          // distance every OTHER centroid is at least away (k_sweep1_fast)
-    }
-    point_tail<F64, MODE>(a, i, active, best.slot, best.d2, x, y, z, xd, yd, zd);
-}
-
-// ---- exact skip of the search (k-means style bounds) ---------------------------------------------------------------
-// Points never move and the centroids move a little per iteration, so most nearest faces do not change.  Every full search
-// leaves, per point, lbd = a lower bound of the distance to every centroid OTHER than the winner.  Before the next sweep
-// k_refit_centroids measures how far every centroid has moved (max per cell of a pyramid of grids over the key grid,
-// levels 0 = whole mesh .. NW_DG_TOP = 2^NW_DG_TOP cells per axis; k_dilate_dgrid takes the max over the 3x3x3
-// neighbourhood).  For a point whose winner s is now at exact distance d1, with L the finest level whose cells are wider than
-// d1 (+ slack):
-//   * a centroid keyed inside the 3x3x3 block of level-L cells around the point was at least lbd away and has moved at
-//     most delta_L(block), so it is at least lbd - delta_L away now;
-//   * a centroid keyed outside that block is at least one cell width W_L, minus how far centroids have left their key
-//     cells (cell_escape), away.
-// If d1 is strictly below both, s is still THE nearest centroid (strictly: no tie to resolve) and the tree is not
-// touched; min(both) is the new lbd.  Otherwise the point goes on the list for the packet search (LIST = true above).
-// Level 0 is one cell = the whole mesh: no "outside", delta_0 = the largest displacement anywhere.
-
-struct FastArgs {
-    const float *dgrid;            // dilated displacement pyramid
-    unsigned char *flag;           // 1 = needs the search
-};
-
-template <bool F64>
-__global__ void __launch_bounds__(256) k_sweep1_fast(const __grid_constant__ Sweep1Args a, const FastArgs fa) {
-    if (a.st->stop) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < a.P;
-    float x = 0.f, y = 0.f, z = 0.f;
-    double xd = 0.0, yd = 0.0, zd = 0.0, d2 = 0.0;
-    int s = -1;
-    bool keep = false;
-    if (active) {
-        x = a.px[i]; y = a.py[i]; z = a.pz[i];
-        xd = x; yd = y; zd = z;
-        if (F64) { xd = a.px64[i]; yd = a.py64[i]; zd = a.pz64[i]; }
-        s = a.slot[i];
-        if (s >= 0) {
-            const float4 c = __ldg(&a.tv.cent[s]);
-            if (F64) { QueryF64 q; q.set(xd, yd, zd); d2 = q.d2(c); }
-            else { QueryF32 q; q.x = x; q.y = y; q.z = z; d2 = q.d2(c); }
-            const float d1 = __fsqrt_ru(__double2float_ru(d2));
-            const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;
-            // finest level whose cell width exceeds d1 + what the centroids may have left their key cells by
-            const float gx = (x - a.tv.grid_lo.x) * a.tv.grid_inv, gy = (y - a.tv.grid_lo.y) * a.tv.grid_inv, gz = (z - a.tv.grid_lo.z) * a.tv.grid_inv;
-            const bool inside = gx >= 0.f && gx < 1024.f && gy >= 0.f && gy < 1024.f && gz >= 0.f && gz < 1024.f && a.tv.grid_inv > 0.f;
-            int L = 0;
-            float wall = __int_as_float(0x7f800000);
-            if (inside) {
-                const float lost = (a.st->cell_escape + 1e-3f) * a.tv.grid_cellw + 2.f * eps;
-#pragma unroll
-                for (int l = NW_DG_TOP; l >= 1; --l) {
-                    const float w = __fsub_rd((float)(1024 >> l) * a.tv.grid_cellw, lost);
-                    if (L == 0 && d1 < w) { L = l; wall = w; }
-                }
-            }
-            const int sh = 10 - L;
-            const int cell = L ? (int)(((unsigned)gx >> sh) | (((unsigned)gy >> sh) << L) | (((unsigned)gz >> sh) << (2 * L))) : 0;
-            const float moved = __ldg(&fa.dgrid[nw_dg_off(L) + cell]);
-            const float nb = __fmul_rd(fminf(__fsub_rd(a.lbd[i], moved), wall), NW_LBD_SAFE);
-            keep = d1 < nb;                                  // false for NaN anywhere
-            if (keep) a.lbd[i] = nb;
-        }
-        fa.flag[i] = keep ? 0 : 1;
-    }
-    point_tail<F64, 1>(a, i, keep, s, d2, x, y, z, xd, yd, zd);
-}
-
-// 3x3x3 maximum of every level of the displacement pyramid
-__global__ void __launch_bounds__(256) k_dilate_dgrid(const float *__restrict__ raw, float *__restrict__ out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= NW_DG_CELLS) return;
-    int L = 0;
-    while (L < NW_DG_TOP && t >= nw_dg_off(L + 1)) ++L;
-    const int c = t - nw_dg_off(L), n = 1 << L, m = n - 1;
-    const int cx = c & m, cy = (c >> L) & m, cz = c >> (2 * L);
-    float v = 0.f;
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int X = cx + dx, Y = cy + dy, Z = cz + dz;
-                if (X < 0 || Y < 0 || Z < 0 || X >= n || Y >= n || Z >= n) continue;
-                v = fmaxf(v, raw[nw_dg_off(L) + (X | (Y << L) | (Z << (2 * L)))]);   // +inf (NaN displacement) propagates
-            }
-    out[t] = v;
 }
 
 // ---- single-operator forms ------------------------------------------------------------------------
@@ -981,7 +840,6 @@ static Sweep1Args make_args(nw_ctx *h) {
     else { a.wx = a.wy = a.wz = nullptr; }
     a.sinv_scalar = h->sinv_scalar; a.wmean = h->wmean;
     a.slot = h->slot;
-    a.lbd = h->lbd; a.list = h->slist; a.list_n = h->slist_n;
     a.w0 = h->w0; a.w1 = h->w1; a.w2 = h->w2; a.rx = h->rx; a.ry = h->ry; a.rz = h->rz;
     a.posq = h->posq; a.sfaces = h->sfaces; a.tl = h->tl; a.F = h->F;
     a.tv.cent = h->cent; a.tv.boxes = h->boxes; a.tv.parent = h->parent_g; a.tv.kids = h->kids; a.tv.leaf_of_slot = h->leaf_of_slot;
@@ -1086,63 +944,13 @@ int nw_launch_sweep1(nw_ctx *h, bool scatter) {
     const bool stats = (h->profile & 2) != 0;
 #endif
     if (h->px64) {
-        if (stats) { if (scatter) k_sweep1<true, 1, true, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, true, false><<<G, B, 0, h->stream>>>(a); }
-        else { if (scatter) k_sweep1<true, 1, false, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, false, false><<<G, B, 0, h->stream>>>(a); }
+        if (stats) { if (scatter) k_sweep1<true, 1, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, true><<<G, B, 0, h->stream>>>(a); }
+        else { if (scatter) k_sweep1<true, 1, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, false><<<G, B, 0, h->stream>>>(a); }
     } else {
-        if (stats) { if (scatter) k_sweep1<false, 1, true, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, true, false><<<G, B, 0, h->stream>>>(a); }
-        else { if (scatter) k_sweep1<false, 1, false, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false, false><<<G, B, 0, h->stream>>>(a); }
+        if (stats) { if (scatter) k_sweep1<false, 1, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, true><<<G, B, 0, h->stream>>>(a); }
+        else { if (scatter) k_sweep1<false, 1, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false><<<G, B, 0, h->stream>>>(a); }
     }
     NW_LAUNCH_CHECK();
-    h->bounds_valid = true;             // every point now carries the bound of a complete search at the current centroids
-    return NW_OK;
-}
-
-int nw_dilate_dgrid(nw_ctx *h) {
-    k_dilate_dgrid<<<nw_grid(NW_DG_CELLS, 256), 256, 0, h->stream>>>(h->dg_raw, h->dg);
-    NW_LAUNCH_CHECK();
-    return NW_OK;
-}
-
-// buffers of the fast path; called outside stream capture (nw_search, before the first iteration)
-int nw_sweep1_prepare(nw_ctx *h) {
-    if (h->P == 0) return NW_OK;
-    NW_CHECK(nw_alloc(h, &h->sflag, (size_t)h->P)); NW_CHECK(nw_alloc(h, &h->slist, (size_t)h->P));
-    NW_CHECK(nw_alloc(h, &h->slist_n, 4));
-    size_t tmp = 0;
-    cub::DeviceSelect::Flagged(nullptr, tmp, thrust::counting_iterator<int>(0), h->sflag, h->slist, h->slist_n, (int)h->P, h->stream);
-    if (tmp > h->cub_tmp_bytes) { NW_CHECK(nw_alloc(h, (char **)&h->cub_tmp, tmp)); h->cub_tmp_bytes = tmp; }
-    return NW_OK;
-}
-
-// Sweep with the search skipped wherever the bounds of the previous sweep still prove the nearest face (k_sweep1_fast);
-// the remaining points are compacted in Hilbert order and searched as packets.  Three stages so that they can be timed.
-int nw_launch_sweep1_fast(nw_ctx *h) {
-    if (h->P == 0) return NW_OK;
-    NW_ARG(h->bounds_valid && h->sflag && h->dg, "sweep1_fast: no bounds from a previous sweep");
-    Sweep1Args a = make_args(h);
-    FastArgs fa;
-    fa.dgrid = h->dg; fa.flag = h->sflag;
-    NW_CHECK(nw_stage_begin(h, 10));
-    if (h->px64) k_sweep1_fast<true><<<nw_grid(h->P, 256), 256, 0, h->stream>>>(a, fa);
-    else k_sweep1_fast<false><<<nw_grid(h->P, 256), 256, 0, h->stream>>>(a, fa);
-    NW_LAUNCH_CHECK();
-    NW_CHECK(nw_stage_end(h, 10));
-    NW_CHECK(nw_stage_begin(h, 11));
-    size_t tmp = h->cub_tmp_bytes;
-    NW_CUDA(cub::DeviceSelect::Flagged(h->cub_tmp, tmp, thrust::counting_iterator<int>(0), h->sflag, h->slist, h->slist_n, (int)h->P, h->stream));
-    h->launches += 2;
-    NW_CHECK(nw_stage_end(h, 11));
-    NW_CHECK(nw_stage_begin(h, 12));
-#ifdef NW_LEVEL_STATS
-    const bool stats = true;
-#else
-    const bool stats = (h->profile & 2) != 0;
-#endif
-    const int G = nw_grid(h->P, 128);
-    if (h->px64) { if (stats) k_sweep1<true, 1, true, true><<<G, 128, 0, h->stream>>>(a); else k_sweep1<true, 1, false, true><<<G, 128, 0, h->stream>>>(a); }
-    else { if (stats) k_sweep1<false, 1, true, true><<<G, 128, 0, h->stream>>>(a); else k_sweep1<false, 1, false, true><<<G, 128, 0, h->stream>>>(a); }
-    NW_LAUNCH_CHECK();
-    NW_CHECK(nw_stage_end(h, 12));
     return NW_OK;
 }
 
@@ -1362,7 +1170,6 @@ int nw_bench_launch(nw_ctx *h, const char *name) {
     } else if (n == "mesh_prior") {
         return nw_launch_mesh_prior(h, true);
     } else if (n == "refit") {
-        h->bounds_valid = false;                 // a refit without a sweep: the measured displacements are not consumed
         return nw_tree_refit(h);
     } else if (n == "allreduce_acc") {
         return nw_allreduce_acc(h);              // N > 1: the per-iteration collective alone, all ranks in lockstep

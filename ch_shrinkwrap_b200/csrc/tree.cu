@@ -204,23 +204,14 @@ __global__ void k_copy_minus1(const int *__restrict__ id, int F, int *__restrict
 // Also measures how far (L-infinity, grid units, evaluated with the operations of k_face_keys) any centroid now lies
 // outside the grid cell it was keyed into at upload: the slack of the cell-clearance early-out of the search (sweep.cu).
 __global__ void k_refit_centroids(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F, float4 *__restrict__ cent,
-                                  const unsigned *__restrict__ fcells, float3 lo, float inv, SolverState *st, float *__restrict__ dg_raw) {
+                                  const unsigned *__restrict__ fcells, float3 lo, float inv, SolverState *st) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float esc = 0.f, moved = 0.f;
-    unsigned cell = 0u;
+    float esc = 0.f;
     if (i < F) {
         const int4 sf = sfaces[i];
         const float3 cc = centroid_f32(pos[sf.x], pos[sf.y], pos[sf.z]);
-        cell = fcells[i];
-        if (dg_raw) {
-            // how far this centroid has moved since the last sweep (rounded up); folded below into every level of the
-            // displacement pyramid at the cell the centroid was KEYED into (static membership): sweep.cu, k_sweep1_fast
-            const float4 old = cent[i];
-            const double dx = (double)cc.x - (double)old.x, dy = (double)cc.y - (double)old.y, dz = (double)cc.z - (double)old.z;
-            moved = __fmul_ru(__double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)), 1.000001f);
-            if (!(moved >= 0.f)) moved = __int_as_float(0x7f800000);   // NaN positions: nobody skips
-        }
         cent[i] = make_float4(cc.x, cc.y, cc.z, __int_as_float(sf.w));
+        const unsigned cell = fcells[i];
         const float gx = (cc.x - lo.x) * inv, gy = (cc.y - lo.y) * inv, gz = (cc.z - lo.z) * inv;
         const float cx = (float)(cell & 1023u), cy = (float)((cell >> 10) & 1023u), cz = (float)(cell >> 20);
         // the last cell of an axis also holds everything that was clamped into it
@@ -230,26 +221,6 @@ __global__ void k_refit_centroids(const int4 *__restrict__ sfaces, const float4 
     }
     const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(esc));    // non-negative floats order like their bits
     if ((threadIdx.x & 31) == 0 && m) atomicMax((unsigned *)&st->cell_escape, m);
-    if (dg_raw) {
-        // the faces of a warp are neighbours on the Hilbert curve: at most levels they share the cell, so the warp's
-        // maximum goes in with one atomic (and most of those change nothing: look first, a stale value only costs a
-        // redundant atomic)
-        const unsigned du = __float_as_uint(moved);                  // non-negative floats order like their bits; 0 for idle lanes
-        const unsigned wmax = __reduce_max_sync(0xffffffffu, du);
-        if (wmax == 0u) return;
-        const unsigned cx = cell & 1023u, cy = (cell >> 10) & 1023u, cz = cell >> 20;
-        const bool live = i < F;
-#pragma unroll
-        for (int L = NW_DG_TOP; L >= 0; --L) {
-            const int sh = 10 - L;
-            const int idx = (int)((cx >> sh) | ((cy >> sh) << L) | ((cz >> sh) << (2 * L)));
-            const int idx0 = __shfl_sync(0xffffffffu, idx, 0);
-            unsigned *p = (unsigned *)dg_raw + nw_dg_off(L);
-            if (__all_sync(0xffffffffu, !live || idx == idx0)) {
-                if ((threadIdx.x & 31) == 0 && wmax > __ldcg(p + idx0)) atomicMax(p + idx0, wmax);
-            } else if (live && du > __ldcg(p + idx)) atomicMax(p + idx, du);
-        }
-    }
 }
 
 // warp-level "sum over lanes with the same key" for floats (build time only): every lane returns its group's sum
@@ -532,8 +503,6 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     if (h->slot && h->P) NW_CUDA(cudaMemsetAsync(h->slot, 0xff, sizeof(int) * h->P, s));
     h->seeds_cold = true;
     h->order_stale = true;
-    h->bounds_valid = false;
-    NW_CHECK(nw_alloc(h, &h->dg_raw, (size_t)NW_DG_CELLS)); NW_CHECK(nw_alloc(h, &h->dg, (size_t)NW_DG_CELLS));
     NW_CHECK(nw_tree_build(h));
     return seg_end(h);
 }
@@ -561,23 +530,15 @@ static int extents_pass(nw_ctx *h) {
     return NW_OK;
 }
 
-static void launch_refit_centroids(nw_ctx *h, bool measure_moves) {
+static void launch_refit_centroids(nw_ctx *h) {
     cudaMemsetAsync(&h->st->cell_escape, 0, sizeof(float), h->stream);
-    if (measure_moves) cudaMemsetAsync(h->dg_raw, 0, sizeof(float) * NW_DG_CELLS, h->stream);
     k_refit_centroids<<<nw_grid(h->F, 256), 256, 0, h->stream>>>(h->sfaces, h->posq, h->F, h->cent, h->fcells,
-                                                                 make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv, h->st,
-                                                                 measure_moves ? h->dg_raw : nullptr);
+                                                                 make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv, h->st);
 }
 
-int nw_dilate_dgrid(nw_ctx *h);    // sweep.cu
-
-// every iteration: centroids + boxes at the current f.  When the previous sweep left bounds (bounds_valid) the
-// displacement of every centroid since then is measured on the way (cent[] still holds that sweep's centroids).
 int nw_tree_refit(nw_ctx *h) {
-    const bool moves = h->bounds_valid && h->dg_raw != nullptr;
-    launch_refit_centroids(h, moves);
+    launch_refit_centroids(h);
     NW_LAUNCH_CHECK();
-    if (moves) NW_CHECK(nw_dilate_dgrid(h));
     return extents_pass(h);
 }
 
@@ -670,7 +631,7 @@ int nw_tree_build(nw_ctx *h) {
     }
     trace.mark("level tables");
     // ---- frames (fixed for the block), then the first extents
-    launch_refit_centroids(h, false);
+    launch_refit_centroids(h);
     NW_LAUNCH_CHECK();
     NW_CUDA(cudaMemsetAsync(h->node_f, 0, sizeof(float) * NW_NMOM * total, s));
     if (kL >= 1) {
@@ -701,7 +662,7 @@ extern "C" int nw_set_positions(nw_ctx *h, const float *pos) {
     NW_CUDA(cudaStreamSynchronize(h->stream));
     h->weights_valid = false;
     h->pin_fresh = false;
-    return NW_OK;          // bounds stay valid: the next refit measures how far the centroids have moved, whatever moved them
+    return NW_OK;
 }
 
 // Current positions (and the valid flags) into the handle's pinned staging buffer.  nw_search enqueues this behind its last

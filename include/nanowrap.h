@@ -151,15 +151,11 @@ int nw_bench_kernel(nw_ctx *h, const char *name, int reps, float *ms_per_launch)
 int nw_sync(nw_ctx *h);
 /* CUDA-event timing on the handle's stream: on & 1 brackets every stage of every iteration inside
  * nw_search and the device-side segments of nw_set_topology*.  nw_get_profile returns accumulated ms and kernel
- * launches per stage (13 stages: refit, shift, sweep1 = full search, allreduce_acc, mesh_prior, sweep2, allreduce_scalars,
+ * launches per stage (10 stages: refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars,
  * solve_update, seed_leaders, topology_build = foot points + record unpack + Hilbert sort + octree tables + frames of
- * every upload, host->device copies excluded; sweep1_fast = bound check + settled points, sweep1_select = compaction
- * of the rest, sweep1_list = their search) and the event-timed duration of the last nw_search call (first kernel to
+ * every upload, host->device copies excluded) and the event-timed duration of the last nw_search call (first kernel to
  * last kernel). */
 int nw_set_profile(nw_ctx *h, int on);
-/* per iteration of the last nw_search call: how many points needed the nearest-face search (-1 = all of them, a full sweep);
- * the others kept their face on the strength of the previous sweep's bounds ("exact skip") */
-int nw_get_search_counts(nw_ctx *h, double *listed, int n);
 int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms);
 /* the stage intervals of the last profiled nw_search call in launch order: stage[k] (index into the list above), ms[k];
  * at most cap entries are written, *n = how many there are */
@@ -170,9 +166,6 @@ int nw_get_stage_trace(nw_ctx *h, int32_t *stage, float *ms, int cap, int *n);
 int nw_get_traversal_stats(nw_ctx *h, uint64_t out[4]);
 /* diagnosis: boxes of one level of the centroid pyramid (16 floats per node, layout of csrc/common.cuh: Box) */
 int nw_debug_tree(nw_ctx *h, int level, float *boxes16, int *counts, int *n_levels);
-/* diagnosis: the centroid-displacement pyramid of the last refit (levels 0..6 back to back, *n_cells floats each array):
- * per-cell maxima and their 3x3x3-dilated maxima (what k_sweep1_fast subtracts from the stored bounds) */
-int nw_debug_dgrid(nw_ctx *h, float *raw, float *dilated, int *n_cells);
 /* kernels launched by this handle since creation (for bench.py's gpu_launches) */
 int64_t nw_launch_count(nw_ctx *h);
 

@@ -1,5 +1,5 @@
-"""Bench window (first N iterations of a fit at C3, blocks of 5) with the per-iteration cost of the three sweep1 stages and the
-number of points the bound check could not settle.  argv: workload blocks"""
+"""Bench window (first N iterations of a fit, blocks as bench.py runs them) with the per-iteration cost of every stage
+(nw_get_stage_trace).  argv: workload blocks"""
 import sys, os, ctypes, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
@@ -19,7 +19,6 @@ for blk in range(nblk):
     n = ctypes.c_int(0)
     st = (ctypes.c_int32 * 4096)(); ms = (ctypes.c_float * 4096)()
     cg._h.call('nw_get_stage_trace', st, ms, 4096, ctypes.byref(n))
-    listed = np.zeros(cfg['block']); cg._h.call('nw_get_search_counts', listed.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), cfg['block'])
     sm = ctypes.c_double(); cg._h.call('nw_get_profile', None, None, ctypes.byref(sm))
     tot += sm.value
     rows, cur = [], {}
@@ -30,8 +29,6 @@ for blk in range(nblk):
     rows.append(cur)
     print('block %d: search %.2f ms' % (blk, sm.value))
     for it, r in enumerate(rows):
-        s1 = sum(r.get(k, 0.0) for k in (2, 10, 11, 12))
-        print('   it %d: sweep1 %.3f (full %.3f fast %.3f select %.3f list %.3f) refit %.3f sweep2 %.3f prior %.3f solve %.3f seeds %.3f | searched %s' % (
-            it, s1, r.get(2, 0), r.get(10, 0), r.get(11, 0), r.get(12, 0), r.get(0, 0), r.get(5, 0), r.get(4, 0), r.get(7, 0), r.get(8, 0),
-            'all' if listed[it] < 0 else '%.2f %%' % (100.0 * listed[it] / P)))
+        print('   it %d: sweep1 %.3f refit %.3f sweep2 %.3f prior %.3f solve %.3f seeds %.3f shift %.3f' % (
+            it, r.get(2, 0), r.get(0, 0), r.get(5, 0), r.get(4, 0), r.get(7, 0), r.get(8, 0), r.get(1, 0)))
 print('total search ms %.2f over %d iterations: %.3f ms/iter' % (tot, nblk * cfg['block'], tot / (nblk * cfg['block'])))
