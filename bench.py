@@ -36,15 +36,19 @@ WORKLOADS = {
     'c4': dict(points=12_500_000, geo=316, curvature_weight=10.0, block=5, desc='config3: 100M localisations over 8 GPUs (12.5M per GPU), 998 562-vertex replicated mesh'),
     'c5': dict(points=2_000_000, geo=632, curvature_weight=50.0, block=5, desc='config4: curvature stress, 3 994 242-vertex mesh, sparse 2M-localisation cloud'),
 }
-REFERENCE_SAMPLE = 'c2'   # bounded CPU sample: same shape, same 20 localisations per vertex, 1/10 of c3
+CPU_SAMPLE = 'c2'         # bounded CPU sample of the cpu_baseline leg: same shape, same 20 localisations per vertex, 1/10 of c3
 STAGES = ['refit', 'shift', 'sweep1', 'allreduce_acc', 'mesh_prior', 'sweep2', 'allreduce_scalars', 'solve_update', 'seed_leaders',
           'topology_build']
 
 
-def build_workload(name, seed):
+def build_workload(name, seed, points=None):
+    """(mesh, points, sigma, cfg) of a BASELINE config; `points` overrides the number of localisations (parity tests draw a
+    subset-sized cloud over the full-size mesh)."""
     from ch_shrinkwrap_b200 import minimesh, synth
     from ch_shrinkwrap_b200.membrane_mesh import MembraneMesh
-    cfg = WORKLOADS[name]
+    cfg = dict(WORKLOADS[name])
+    if points is not None:
+        cfg['points'] = int(points)
     shape = synth.two_lobed()
     v, f = minimesh.geodesic_sphere(cfg['geo'])
     v, f = minimesh.spatially_sorted(v, f)       # arbitrary generator order -> spatially coherent vertex / face order
@@ -123,25 +127,56 @@ def run_blocks(mesh, pts, s_inv, lam, n_iters, block, handle_profile=True):
     return dev_ms, wall, cg
 
 
-def cpu_reference_run(steps, warmup, seed):
-    """The reference's CPU path (oracle port: numpy + scipy cKDTree(workers=-1) + the C scatter) on the bounded
-    sample.  Returns dict(value, seconds, P, M, cores)."""
-    from oracle import build as obuild
-    from oracle import nanowrap_oracle as orc
-    obuild.build_oracle_c()
-    mesh, pts, sig, cfg = build_workload(REFERENCE_SAMPLE, seed)
+def cpu_reference_run(workload, steps, warmup, seed):
+    """The reference's own CPU path on `workload`: the UNMODIFIED ``ShrinkwrapMeshConjGrad.search``
+    (mesh_conj_grad.py:150-292: scipy cKDTree(workers=-1), numpy, the C scatter) imported through oracle/refharness.py from
+    the build product oracle/_ref/ (kind "reference"); only if that is missing, the oracle's numpy/scipy restatement
+    (kind "port").  One solver object, `warmup` untimed iterations, then `steps` timed ones.
+    Returns dict(value, seconds, P, M, cores, kind, sample)."""
+    from oracle import refharness
+    mesh, pts, sig, cfg = build_workload(workload, seed)
     s_inv = (1.0 / sig.ravel()).astype(np.float32)
     lam = cfg['curvature_weight'] * 1.0 / 2.0
-    oc = orc.OracleConjGrad(mesh, pts)
-    mesh.cg = oc
+    if refharness.available():
+        kind, how = 'reference', 'unmodified reference (%s)' % refharness.kind()
+        oc = refharness.reference_solver(mesh, pts)
+    else:
+        from oracle import build as obuild
+        from oracle import nanowrap_oracle as orc
+        obuild.build_oracle_c()
+        kind, how = 'port', 'oracle port (reference not staged under oracle/_ref/)'
+        oc = orc.OracleConjGrad(mesh, pts)
+        mesh.cg = oc
     if warmup > 0:
         oc.search(pts, lams=[lam], num_iters=warmup, sigma_inv=s_inv)
     t0 = time.perf_counter()
     oc.search(pts, lams=[lam], num_iters=steps, sigma_inv=s_inv)
     dt = time.perf_counter() - t0
     P = len(pts)
-    return dict(value=P * steps / dt, seconds=dt, P=P, M=len(mesh._vertices), cores=os.cpu_count(),
-                sample='%s, %d CG iterations after %d warm-up' % (cfg['desc'], steps, warmup))
+    return dict(value=P * steps / dt, seconds=dt, P=P, M=len(mesh._vertices), cores=os.cpu_count(), kind=kind,
+                sample='%s: %d CG iterations after %d warm-up, %s' % (cfg['desc'], steps, warmup, how), mesh=mesh)
+
+
+def cpu_curvature_run(mesh):
+    """The reference's c_curvature_grad (membrane_mesh_utils.c:915-1250, compiled from the reference's own source into
+    oracle/_ref/libref_curvature.so) on the whole mesh: vertices/s on one host core (the reference loop is serial)."""
+    from oracle import refharness
+    mesh.update_geometry()
+    try:
+        t0 = time.perf_counter()
+        refharness.reference_curvature(mesh, kc=1.0, seed=1)
+        dt = time.perf_counter() - t0
+        kind = 'reference'
+    except Exception:
+        from oracle import build as obuild
+        from oracle import nanowrap_oracle as orc
+        obuild.build_oracle_c()
+        t0 = time.perf_counter()
+        orc.curvature_grad(mesh)
+        dt = time.perf_counter() - t0
+        kind = 'port'
+    M = len(mesh._vertices)
+    return {'value': M / dt, 'unit': 'vertices/s', 'seconds': dt, 'vertices': M, 'cores': 1, 'kind': kind}
 
 
 def main():
@@ -153,7 +188,9 @@ def main():
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--seed', type=int, default=1234)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-steps', type=int, default=2)
+    ap.add_argument('--cpu-steps', type=int, default=5, help='timed iterations of the cpu_baseline sample (our arm)')
+    ap.add_argument('--ref-steps', type=int, default=0, help='reference arm: timed full-size iterations (default min(steps, 2))')
+    ap.add_argument('--ref-warmup', type=int, default=-1, help='reference arm: untimed full-size iterations (default 0)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -165,16 +202,24 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        W = max(args.warmup, 1)
-        r = cpu_reference_run(args.steps, W, args.seed)
+        # The SAME workload as our arm (default c3: 10 M localisations, 501 762 vertices).  One reference iteration at this
+        # size takes minutes of host time, so the arm times a bounded number of full-size steps (default: the FIRST 2 iterations of the fit,
+        # no warm-up -- our arm's window is the first K iterations from the same start mesh; --ref-steps / --ref-warmup) whatever --steps / --warmup ask for, and says so in the line.
+        K = args.ref_steps if args.ref_steps > 0 else min(args.steps, 2)
+        W = args.ref_warmup if args.ref_warmup >= 0 else 0
+        r = cpu_reference_run(args.workload, K, W, args.seed)
         cfg = WORKLOADS[args.workload]
+        curv = cpu_curvature_run(r['mesh'])
         line = {
-            'impl': 'reference', 'metric': metric, 'value': r['value'], 'unit': unit, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': W, 'ms_per_step': 1e3 * r['seconds'] / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'impl': 'reference', 'metric': metric, 'value': r['value'], 'unit': unit, 'n_gpus': args.gpus, 'steps': K,
+            'warmup': W, 'ms_per_step': 1e3 * r['seconds'] / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32 (fp64 nearest-face compare and Gram sums)', 'data': 'synthetic',
-            'config': {'workload': cfg['desc'] + ' per GPU', 'reference_sample': r['sample'], 'points_timed': r['P'], 'vertices_timed': r['M']},
-            'cg_iters_per_s_on_sample': args.steps / r['seconds'],
-            'cpu_baseline': {'value': r['value'], 'unit': unit, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
+            'config': {'workload': cfg['desc'] + ' per GPU', 'points_timed': r['P'], 'vertices_timed': r['M'],
+                       'same_config_as_gpu_arm': True, 'requested_steps': args.steps, 'requested_warmup': args.warmup,
+                       'timed': 'full-size steps of the same workload; bounded to %d timed + %d warm-up iterations' % (K, W)},
+            'cg_iters_per_s': K / r['seconds'],
+            'cpu_baseline': {'value': r['value'], 'unit': unit, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample'],
+                             'curvature': curv},
             'e2e': {'value': r['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0,
         }
@@ -253,6 +298,7 @@ def main():
     run_blocks(mesh, pts, s_inv, lam, W, block)
     mesh._vertices['position'][:] = start_pos
     mesh.update_geometry()
+    h.call('nw_reset_seeds')              # the timed run starts cold like a fit does: no faces / foot points left over from the warm-up
     h.call('nw_set_profile', 1)
     launches0 = h.lib.nw_launch_count(h.h)
     clocks = ClockSampler(local_rank)
@@ -327,16 +373,28 @@ def main():
                                 'vertices_per_s': M / (ms.value * 1e-3)}
     except Exception as e:      # noqa
         kernels['curvature'] = {'error': str(e)}
+    # every rank holds the whole mesh and must end the timed run with the very same vertices: the adjoint accumulates in
+    # integers (order-free) and the mesh-side kernels are replicated, so anything but bit identity is a bug
+    ranks_identical = None
     if dist is not None:
+        import zlib
+        import torch
+        crc = zlib.crc32(np.ascontiguousarray(mesh._vertices['position']).tobytes())
+        t = torch.tensor([crc], dtype=torch.int64, device='cuda')
+        allc = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allc, t)
+        ranks_identical = bool(all(int(c.item()) == crc for c in allc))
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(args.cpu_steps, 1, args.seed)
-        cpu = {'value': r['value'], 'unit': unit, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample'],
-               'cg_iters_per_s_on_sample': args.cpu_steps / r['seconds']}
+        # bounded sample (config 1 is the same shape at 1/10 the size); the full-size CPU number is the reference arm's
+        r = cpu_reference_run(CPU_SAMPLE if args.workload in ('c3', 'c4', 'c5') else args.workload, args.cpu_steps, 1, args.seed)
+        cpu = {'value': r['value'], 'unit': unit, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample'],
+               'cg_iters_per_s_on_sample': args.cpu_steps / r['seconds'],
+               'curvature': cpu_curvature_run(mesh)}      # the bench mesh itself (full size), one host core
     line = {
         'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': dev_ms / K,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -348,6 +406,8 @@ def main():
         'e2e': e2e, 'gpu_launches': launches, 'clocks': {k: clk[k] for k in ('sm_mhz', 'sm_max_mhz', 'reasons')},
         'roofline': roofline, 'cpu_baseline': cpu, 'stages': stage, 'kernels': kernels,
     }
+    if ranks_identical is not None:
+        line['ranks_bit_identical'] = ranks_identical
     print(json.dumps(line))
 
 

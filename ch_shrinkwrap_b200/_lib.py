@@ -49,6 +49,7 @@ SIGNATURES = {
     'nw_neck_candidates': (c_int, [c_void_p, c_float, c_float, _i, POINTER(c_int)]),
     'nw_bench_kernel': (c_int, [c_void_p, c_char_p, c_int, _f]),
     'nw_sync': (c_int, [c_void_p]),
+    'nw_reset_seeds': (c_int, [c_void_p]),
     'nw_set_profile': (c_int, [c_void_p, c_int]),
     'nw_get_stage_trace': (c_int, [c_void_p, _i, _f, c_int, POINTER(c_int)]),
     'nw_get_profile': (c_int, [c_void_p, _d, POINTER(c_int64), _d]),

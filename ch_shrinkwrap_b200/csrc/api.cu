@@ -122,6 +122,19 @@ static int enqueue_iteration(nw_ctx *h, int it, int last_step) {
     return NW_OK;
 }
 
+// Forget every nearest-face seed (previous sweep's slots and the foot points kept across topology uploads): the next sweep
+// starts as the first sweep of a fit does.  For measurements that must include the cold start; results never depend on seeds.
+extern "C" int nw_reset_seeds(nw_ctx *h) {
+    if (!h) return NW_ERR_ARG;
+    NW_CUDA(cudaSetDevice(h->device));
+    if (h->slot && h->P) NW_CUDA(cudaMemsetAsync(h->slot, 0xff, sizeof(int) * h->P, h->stream));
+    h->seeds_cold = true;
+    h->feet_valid = false;
+    h->order_stale = true;
+    h->weights_valid = false;
+    return NW_OK;
+}
+
 extern "C" int nw_set_profile(nw_ctx *h, int on) {
     if (!h) return NW_ERR_ARG;
     h->profile = on;
@@ -165,6 +178,12 @@ extern "C" int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launch
     }
     if (search_ms) *search_ms = h->last_search_ms;
     return NW_OK;
+}
+
+static void release_graph(cudaGraph_t &graph, cudaGraphExec_t &graph_exec) {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (graph) cudaGraphDestroy(graph);
+    graph = nullptr; graph_exec = nullptr;
 }
 
 extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, const double *prev_tests, int n_prev,
@@ -221,10 +240,13 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
                 }
             } else {
                 cudaGetLastError();                              // capture refused: the loop below runs the iterations eagerly
-                if (rc != NW_OK) return rc;
+                if (rc != NW_OK) { release_graph(graph, graph_exec); return rc; }
             }
         }
-        for (; it < num_iters; ++it) NW_CHECK(enqueue_iteration(h, it, last_step));
+        for (; it < num_iters; ++it) {
+            const int rc = enqueue_iteration(h, it, last_step);
+            if (rc != NW_OK) { release_graph(graph, graph_exec); return rc; }
+        }
     }
     NW_CUDA(cudaEventRecord(h->ev_search1, h->stream));
     h->pin_fresh = false;
@@ -232,8 +254,7 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     SolverState r;
     NW_CUDA(cudaMemcpyAsync(&r, h->st, sizeof(SolverState), cudaMemcpyDeviceToHost, h->stream));
     NW_CUDA(cudaStreamSynchronize(h->stream));
-    if (graph_exec) cudaGraphExecDestroy(graph_exec);
-    if (graph) cudaGraphDestroy(graph);
+    release_graph(graph, graph_exec);
     {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_search0, h->ev_search1);

@@ -97,6 +97,8 @@ int nw_comm_destroy(nw_ctx *h) {
     return NW_OK;
 }
 
+int nw_comm_allreduce_host_doubles(nw_ctx *h, double *vals, int n);
+
 int nw_allreduce_acc(nw_ctx *h) {
     if (h->nranks <= 1) return NW_OK;
     NW_ARG(h->nccl, "communicator not initialised");
@@ -111,9 +113,30 @@ int nw_allreduce_acc(nw_ctx *h) {
 int nw_upload_replicated(nw_ctx *h, void *dst, const void *src, size_t bytes, size_t stride) {
     if (h->nranks <= 1) return nw_h2d_strided32(h, dst, src, bytes, stride);
     NW_ARG(h->nccl, "communicator not initialised");
-    if (h->rank == 0) NW_CHECK(nw_h2d_strided32(h, dst, src, bytes, stride));
+    // rank 0 enters the collective even if its own copy failed (the others are already waiting in it); the failure is
+    // agreed on by nw_comm_agree at the end of the upload, so every rank returns an error instead of some hanging
+    int rc = NW_OK;
+    if (h->rank == 0) rc = nw_h2d_strided32(h, dst, src, bytes, stride);
     NW_NCCL(g_nccl.Broadcast(dst, dst, bytes, ncclUint8, 0, (ncclComm_t)h->nccl, h->stream));
+    if (rc != NW_OK) h->comm_status = rc;
     return NW_OK;
+}
+
+// Largest error code any rank has latched since the last call (0 = all fine), with a host synchronisation.  Ranks that
+// were fine themselves get NW_ERR_COMM and a message saying a peer failed.
+int nw_comm_agree(nw_ctx *h) {
+    if (h->nranks <= 1) { const int rc = h->comm_status; h->comm_status = NW_OK; return rc; }
+    NW_ARG(h->nccl, "communicator not initialised");
+    double v[8] = {0};
+    v[h->comm_status < 8 ? h->comm_status : 7] = 1.0;
+    const int mine = h->comm_status;
+    h->comm_status = NW_OK;
+    NW_CHECK(nw_comm_allreduce_host_doubles(h, v, 8));
+    int worst = 0;
+    for (int k = 1; k < 8; ++k) if (v[k] > 0.0) worst = k;
+    if (worst == 0) return NW_OK;
+    if (mine == NW_OK) { h->err = "a peer rank failed during a collective call (see its error)"; return NW_ERR_COMM; }
+    return mine;
 }
 // every rank must be talking about the same mesh: compares a few integers with rank 0's
 int nw_check_replicated(nw_ctx *h, const long long *vals, int n, const char *what) {

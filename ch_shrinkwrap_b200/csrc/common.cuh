@@ -161,6 +161,7 @@ struct nw_ctx {
     // ---- comm ----
     void *nccl = nullptr;                        // ncclComm_t
     int rank = 0, nranks = 1;
+    int comm_status = 0;                         // error latched inside a collective sequence (nw_comm_agree)
 };
 
 #define NW_CUDA(call)                                                                      \
@@ -261,5 +262,6 @@ int nw_allreduce_acc(nw_ctx *h);
 int nw_upload_replicated(nw_ctx *h, void *dst, const void *src, size_t bytes, size_t stride = 4);   // comm.cu
 int nw_check_replicated(nw_ctx *h, const long long *vals, int n, const char *what);
 int nw_allreduce_scalars(nw_ctx *h);
+int nw_comm_agree(nw_ctx *h);
 int nw_set_acc_shifts(nw_ctx *h);
 int nw_curvature_relaunch(nw_ctx *h);

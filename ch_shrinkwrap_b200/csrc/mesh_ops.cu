@@ -245,7 +245,13 @@ __global__ void k_solve(const double *__restrict__ mesh_partials, int n_mesh_blo
         cGw += c[i] * st->gw[i];
     }
     const double prefs2 = Hw[1][1];   // |prefs|^2 == |S1|^2
-    const double test = 1.0 - fabs(Hw[0][1] / (sqrt(Hw[0][0]) * sqrt(Hw[1][1])));       // mesh_conj_grad.py:262-265
+    // mesh_conj_grad.py:262-265.  The reference forms the ratio from float32 sums and subtracts it from 1 in float32, so
+    // its statistic moves in steps of 2^-24 near convergence, and the stop rule ("strictly decreasing three times",
+    // :1009-1016) sees those steps.  Here the ratio comes from float64 sums (more accurate than the reference's own) and
+    // is rounded to float32 ONCE, then subtracted in float32: the history and the rule work on the same kind of number as
+    // the reference's, and what the caller gets back (float32 in self.tests) is exactly what the device compared.
+    const float ratio32 = (float)fabs(Hw[0][1] / (sqrt(Hw[0][0]) * sqrt(Hw[1][1])));
+    const double test = (double)(1.0f - ratio32);
     hist[0 * NW_MAX_ITERS + iter_index] = test;
     hist[1 * NW_MAX_ITERS + iter_index] = sqrt(st->res2);
     hist[2 * NW_MAX_ITERS + iter_index] = sqrt(prefs2);

@@ -504,7 +504,8 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     h->seeds_cold = true;
     h->order_stale = true;
     NW_CHECK(nw_tree_build(h));
-    return seg_end(h);
+    NW_CHECK(seg_end(h));
+    return nw_comm_agree(h);        // N > 1: a rank whose upload failed makes EVERY rank return an error (no one is left waiting)
 }
 
 static int scan_inclusive(nw_ctx *h, const int *in, int *out, int n) {

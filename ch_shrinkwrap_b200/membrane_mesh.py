@@ -13,6 +13,7 @@ combines it with the harness mini-mesh so tests and bench.py can run the whole d
 from __future__ import annotations
 
 import ctypes
+import logging
 import math
 
 import numpy as np
@@ -20,6 +21,8 @@ import numpy as np
 from . import _lib
 from .mesh_conj_grad import ShrinkwrapMeshConjGrad, _session_for
 from .minimesh import MiniMesh
+
+logger = logging.getLogger(__name__)
 
 KBT = 0.0257   # membrane_mesh_utils.h:16
 
@@ -118,11 +121,20 @@ class ShrinkwrapMeshMixin:
 
     def _populate_curvature_grad(self):
         self.curvature_grad_c()
-        if self.smooth_curvature and hasattr(self, 'smooth_per_vertex_data'):      # PYME-side smoothing (:182-186)
+        if not getattr(self, 'smooth_curvature', False):
+            return
+        if hasattr(self, 'smooth_per_vertex_data'):      # PYME-side smoothing (:182-186), host code of the mesh class
             self._H = self.smooth_per_vertex_data(self._H)
             self._K = self.smooth_per_vertex_data(self._K)
             self._k_0 = self.smooth_per_vertex_data(self._k_0)
             self._k_1 = self.smooth_per_vertex_data(self._k_1)
+            self._curvature_smoothing = 'host smooth_per_vertex_data'
+        else:
+            # PYME's TriangleMesh.smooth_per_vertex_data is not part of the reference repository (unpinned);
+            # without it the curvatures stay unsmoothed -- say so instead of skipping silently
+            self._curvature_smoothing = 'skipped: the host mesh class has no smooth_per_vertex_data'
+            logger.warning('smooth_curvature=True but %s has no smooth_per_vertex_data (PYME TriangleMesh method): '
+                           'curvatures are left unsmoothed', type(self).__name__)
 
     def _lazy(self, name):
         if not np.any(getattr(self, name)):
@@ -167,7 +179,12 @@ class ShrinkwrapMeshMixin:
 
     @property
     def point_influence(self):
-        return self.cg.point_influence()
+        fn = getattr(self.cg, 'point_influence', None)
+        if callable(fn):                  # GPU solver: one fused pass on the device
+            return fn()
+        # any other solver object (the reference's, the oracle's): _membrane_mesh.pyx:1625-1634 as written
+        s = self.cg.Ahfunc(np.ones_like(self.cg.res)).reshape(self.vertices.shape)
+        return np.sqrt((s * s).sum(1))
 
     # -- neck removal: criterion on the GPU, topology on the host (_membrane_mesh.pyx:1201-1219) -------------
     def remove_necks(self, neck_curvature_threshold_low=-1e-4, neck_curvature_threshold_high=1e-2):

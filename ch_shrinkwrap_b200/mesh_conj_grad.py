@@ -70,18 +70,63 @@ class _Session:
         self.P = P
 
 
+def _is_vertex_t(dt):
+    """True if the structured dtype is laid out like vertex_t (membrane_mesh_utils.h:57-65): the device unpacks the raw
+    records by byte offset, so the fast path is only taken for exactly this layout."""
+    f = dt.fields
+    if dt.itemsize != 120 or f is None:
+        return False
+    want = {'position': (0, np.dtype(('<f4', (3,)))), 'normal': (12, np.dtype(('<f4', (3,)))), 'halfedge': (24, np.dtype('<i4')),
+            'valence': (28, np.dtype('<i4')), 'neighbors': (32, np.dtype(('<i4', (20,))))}
+    for name, (off, typ) in want.items():
+        if name not in f or f[name][1] != off or f[name][0] != typ:
+            return False
+    return True
+
+
 def _session_for(mesh, device=0, comm=None):
+    """The device session of `mesh` (created on first use).  Normally an attribute of the mesh object; mesh classes that
+    cannot take attributes (cdef classes without ``__dict__``, like the reference's ``MembraneMesh`` when it is not
+    subclassed, _membrane_mesh.pyx:78) are looked up in a small module-level table instead -- the same session must come
+    back for every remesh block, or each block would re-upload and re-sort all the points and leak a handle."""
     s = getattr(mesh, '_nw_session', None)
+    if s is None:
+        ent = _FALLBACK_SESSIONS.get(id(mesh))
+        if ent is not None and ent[0] is mesh:
+            s = ent[1]
+            _FALLBACK_SESSIONS[id(mesh)] = _FALLBACK_SESSIONS.pop(id(mesh))      # most recently used last
     if s is None or s.handle.h is None:
         s = _Session(device, comm)
         try:
             mesh._nw_session = s
-        except AttributeError:      # cdef classes without __dict__: keep a module-level cache
-            _FALLBACK_SESSIONS[id(mesh)] = s
+        except AttributeError:
+            # the entry holds the mesh itself, so its id() cannot be recycled while the entry lives; the table is a
+            # small LRU and closes what it evicts, so device memory does not pile up across many meshes
+            _FALLBACK_SESSIONS.pop(id(mesh), None)
+            _FALLBACK_SESSIONS[id(mesh)] = (mesh, s)
+            while len(_FALLBACK_SESSIONS) > _FALLBACK_LIMIT:
+                _, (_, old) = next(iter(_FALLBACK_SESSIONS.items()))
+                _FALLBACK_SESSIONS.pop(next(iter(_FALLBACK_SESSIONS)))
+                old.handle.close()
     return s
 
 
-_FALLBACK_SESSIONS = {}
+def release_session(mesh):
+    """Free the device state of `mesh` now (otherwise it goes with the mesh object, or when the fallback table evicts it)."""
+    s = getattr(mesh, '_nw_session', None)
+    ent = _FALLBACK_SESSIONS.pop(id(mesh), None)
+    if s is None and ent is not None and ent[0] is mesh:
+        s = ent[1]
+    if s is not None:
+        s.handle.close()
+        try:
+            mesh._nw_session = None
+        except AttributeError:
+            pass
+
+
+_FALLBACK_SESSIONS = {}      # id(mesh) -> (mesh, session), insertion order = least recently used first
+_FALLBACK_LIMIT = 4
 
 
 class ShrinkwrapMeshConjGrad(object):
@@ -92,6 +137,8 @@ class ShrinkwrapMeshConjGrad(object):
     def __init__(self, mesh, points, sigma=None, search_k=200, search_rad=100, shield_sigma=None, use_octree=False,
                  device=0, comm=None):
         self.tests, self.ress, self.prefs = [], [], []             # conj_grad.py:37-39
+        self._tests64 = []                                          # the same history as the device computed it (float64): what
+                                                                    # the stop rule sees, so search(10) == search(5); search(5)
         self.Lfuncs, self.Lhfuncs = ["I"], ["I"]                    # mesh_conj_grad.py:38
         self.mesh = mesh
         self._points = points
@@ -147,7 +194,7 @@ class ShrinkwrapMeshConjGrad(object):
         he_field = mesh._halfedges['vertex']
         verts = mesh._vertices
         nrm = mesh.vertex_normals
-        if (verts.dtype.itemsize == 120 and verts.flags.c_contiguous and isinstance(nrm, np.ndarray)
+        if (_is_vertex_t(verts.dtype) and verts.flags.c_contiguous and isinstance(nrm, np.ndarray)
                 and np.shares_memory(nrm, verts) and nrm.shape == (len(verts), 3)):
             # fast path: the records go up as they lie in memory (position, normal, halfedge, neighbors all inside); the
             # half-edge 'vertex' field is gathered out of its records by the library's upload threads
@@ -198,13 +245,14 @@ class ShrinkwrapMeshConjGrad(object):
         n = int(num_iters)
         out = np.empty((self.M, 3), np.float32)
         hist = [np.zeros(max(n, 1), np.float64) for _ in range(5)]
-        prev = np.asarray(self.tests[-3:], dtype=np.float64)
+        prev = np.asarray(self._tests64[-3:], dtype=np.float64)
         n_done = ctypes.c_int(0)
         lam = float(lams[0]) if len(lams) > 0 else 0.0
         self._h.call('nw_search', lam, n, int(bool(last_step)), _lib.dptr(prev) if len(prev) else None, int(len(prev)),
                      _lib.fptr(out), *[_lib.dptr(a) for a in hist], ctypes.byref(n_done))
         k = n_done.value
         self.loopcount = k
+        self._tests64.extend(float(t) for t in hist[0][:k])
         self.tests.extend(np.float32(t) for t in hist[0][:k])
         self.ress.extend(hist[1][:k].tolist())
         self.prefs.extend(np.array([p], np.float32) for p in hist[2][:k])
@@ -213,7 +261,8 @@ class ShrinkwrapMeshConjGrad(object):
         self.fs = out
         self.f = out.ravel()
         dst = self.mesh._vertices['position']
-        if isinstance(dst, np.ndarray) and dst.dtype == np.float32 and dst.ndim == 2 and dst.shape == out.shape and dst.strides[1] == 4:
+        if (isinstance(dst, np.ndarray) and dst.dtype == np.float32 and dst.ndim == 2 and dst.shape == out.shape
+                and dst.strides[1] == 4 and dst.strides[0] >= 12):
             # :289, written by the library row by row into the records (valid rows only)
             self._h.call('nw_get_positions_strided', ctypes.c_void_p(dst.ctypes.data), int(dst.strides[0]), 1)
         else:

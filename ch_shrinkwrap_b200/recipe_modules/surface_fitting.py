@@ -43,14 +43,36 @@ except Exception:                                          # noqa: BLE001
         return lambda cls: cls
 
 
+_GPU_MESH_CLASS = {}
+
+
+def gpu_mesh_class(host_cls):
+    """The host mesh class with the GPU NanoWrap path mixed in FRONT of it: ``opt_conjugate_gradient``, ``shrink_wrap``,
+    the curvature properties and ``remove_necks`` resolve to ``ShrinkwrapMeshMixin`` (libnanowrap.so), everything
+    topological (remesh, repair, punch_holes, ...) to the host class.  Without this, ``_membrane_mesh.MembraneMesh`` would
+    run its own ``opt_conjugate_gradient``, which builds the reference's CPU ``ShrinkwrapMeshConjGrad``
+    (_membrane_mesh.pyx:1428,1510) -- a silent CPU path."""
+    cls = _GPU_MESH_CLASS.get(host_cls)
+    if cls is None:
+        from ..membrane_mesh import ShrinkwrapMeshMixin
+        cls = type('GpuMembraneMesh', (ShrinkwrapMeshMixin, host_cls), {'__doc__': gpu_mesh_class.__doc__})
+        _GPU_MESH_CLASS[host_cls] = cls
+    return cls
+
+
 def _mesh_factory(inp, **kw):
-    """MembraneMesh(mesh=inp, ...) as at surface_fitting.py:56: PYME's class when available, else the harness mesh."""
-    try:                                                   # pragma: no cover
+    """MembraneMesh(mesh=inp, ...) as at surface_fitting.py:56: the reference's (PYME-backed) mesh class with the GPU path
+    mixed in when it is importable, else the harness mesh.  Either way the solver that runs is the GPU one."""
+    try:
         from ch_shrinkwrap import _membrane_mesh
-        return _membrane_mesh.MembraneMesh(mesh=inp, **kw)
-    except Exception:                                      # noqa: BLE001
+        host_cls = _membrane_mesh.MembraneMesh
+    except Exception:                                      # noqa: BLE001  (no PYME / reference extension in this environment)
         from ..membrane_mesh import MembraneMesh
         return MembraneMesh(mesh=inp, **kw)
+    mesh = gpu_mesh_class(host_cls)(mesh=inp, **kw)
+    if not hasattr(mesh, 'cg'):
+        mesh.cg = None
+    return mesh
 
 
 @register_module('ShrinkwrapMembrane')

@@ -148,6 +148,9 @@ int nw_neck_candidates(nw_ctx *h, float low, float high, int32_t *idx, int *n);
 /* ---- measurement hooks (bench.py / profiling; not part of the reference surface) ------------------ */
 /* device-resident single-kernel launches on the handle's stream, for CUDA-event timing */
 int nw_bench_kernel(nw_ctx *h, const char *name, int reps, float *ms_per_launch);
+/* forget every nearest-face seed (the previous sweep's faces and the foot points kept across topology uploads), so that the
+ * next sweep starts cold like the first sweep of a fit; results never depend on the seeds, only the time does */
+int nw_reset_seeds(nw_ctx *h);
 int nw_sync(nw_ctx *h);
 /* CUDA-event timing on the handle's stream: on & 1 brackets every stage of every iteration inside
  * nw_search and the device-side segments of nw_set_topology*.  nw_get_profile returns accumulated ms and kernel

@@ -1,9 +1,10 @@
-"""Run the UNMODIFIED reference (test infrastructure; this container only).
+"""Run the UNMODIFIED reference (test infrastructure).
 
-Imports ``mesh_conj_grad.py`` / ``conj_grad.py`` straight from /root/reference (nothing is
-copied) and the reference's C compiled by ``oracle/build.py`` into oracle/_ref/.  Used by
-``oracle/make_golden.py`` to write tests/golden/ and by tests marked ``needs_reference``.
-/root/reference does not exist on the GPU box, so nothing under ``-m gpu`` may import this.
+Imports ``mesh_conj_grad.py`` / ``conj_grad.py`` straight from /root/reference when it exists (this
+container), else from the byte-for-byte build product ``oracle/build.py`` staged under
+oracle/_ref/ch_shrinkwrap/ (the GPU box), together with the reference's C compiled into oracle/_ref/.
+Used by ``oracle/make_golden.py`` to write tests/golden/, by tests marked ``needs_reference`` and by
+``bench.py``'s reference arm / CPU-baseline leg -- never by the product path.
 
 Import recipe: empty ``sys.modules`` stubs for
 ``numpy.compat.py3k`` (removed in numpy 2; imported but unused, mesh_conj_grad.py:7),
@@ -23,11 +24,19 @@ import numpy as np
 
 from . import build as _build
 
-REF_PKG_DIR = '/root/reference/ch_shrinkwrap'
+def ref_pkg_dir():
+    return _build.ref_python_dir()
 
 
 def available():
-    return os.path.isdir(REF_PKG_DIR)
+    """True if the unmodified reference can be imported here (live tree or staged build product + its compiled C)."""
+    if ref_pkg_dir() is None:
+        return False
+    return os.path.isdir(_build.REF_SRC) or all(os.path.exists(p) for p in _build.ref_paths())
+
+
+def kind():
+    return 'live tree /root/reference' if os.path.isdir(_build.REF_SRC) else 'staged copy oracle/_ref/ch_shrinkwrap'
 
 
 _mods = {}
@@ -38,8 +47,8 @@ def load_reference():
     if 'mcg' in _mods:
         return _mods['mcg'], _mods['cgu']
     if not available():
-        raise RuntimeError('/root/reference is not present on this machine')
-    cg_so, _ = _build.build_ref()
+        raise RuntimeError('the reference is neither at /root/reference nor staged under oracle/_ref/ (run oracle/build.py where it is)')
+    cg_so = (_build.build_ref() or _build.ref_paths())[0]
 
     def stub(name, **attrs):
         if name not in sys.modules:
@@ -56,7 +65,7 @@ def load_reference():
     sys.modules['PYME.experimental'].isosurface = sys.modules['PYME.experimental.isosurface']
 
     pkg = types.ModuleType('ch_shrinkwrap')
-    pkg.__path__ = [REF_PKG_DIR]
+    pkg.__path__ = [ref_pkg_dir()]
     sys.modules['ch_shrinkwrap'] = pkg
     loader = importlib.machinery.ExtensionFileLoader('ch_shrinkwrap.conj_grad_utils', cg_so)
     spec = importlib.util.spec_from_file_location('ch_shrinkwrap.conj_grad_utils', cg_so, loader=loader)
@@ -91,7 +100,7 @@ def libc_uniforms(seed, n):
 def reference_curvature(mesh, dN=0.1, skip_prob=0.0, kc=1.0, kg=-20.0 * 0.0257, c0=0.0, seed=None):
     """Reference ``c_curvature_grad`` (membrane_mesh_utils.c:915) on the mesh's structured arrays.
     ``seed``: call libc ``srand(seed)`` first so the jitter draws are reproducible."""
-    _, so = _build.build_ref()
+    so = (_build.build_ref() or _build.ref_paths())[1]
     lib = ctypes.PyDLL(so)
     from .nanowrap_oracle import CURV_SCALARS, CURV_VECTORS
     M = len(mesh._vertices)

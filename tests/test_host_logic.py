@@ -178,3 +178,110 @@ def test_solver_shim_chooses_the_record_upload_and_passes_the_half_edge_stride()
     calls.clear()
     cg.search(pts, lams=[5.0], num_iters=2, sigma_inv=0.1)
     assert [c[0] for c in calls] == ['set_points', 'nw_set_positions', 'nw_search', 'nw_get_positions_strided']
+
+
+# ---- sessions and the recipe's mesh factory (no GPU: the library handle is stubbed) -------------------------------------
+class _FakeHandle:
+    created = 0
+
+    def __init__(self, device=0):
+        type(self).created += 1
+        self.h = object()
+        self.calls = []
+
+    def call(self, name, *args):
+        self.calls.append(name)
+
+    def close(self):
+        self.h = None
+
+
+def test_session_is_reused_for_a_mesh_without_dict(monkeypatch):
+    """a cdef-style mesh (no __dict__) must get the SAME session for every remesh block: one handle, one
+    nw_set_points."""
+    from ch_shrinkwrap_b200 import _lib, mesh_conj_grad as mcg
+    monkeypatch.setattr(_lib, 'Handle', _FakeHandle)
+    monkeypatch.setattr(mcg, '_FALLBACK_SESSIONS', {})
+    _FakeHandle.created = 0
+
+    class Slotted:
+        __slots__ = ('x',)
+
+    m = Slotted()
+    s1 = mcg._session_for(m)
+    s2 = mcg._session_for(m)
+    assert s1 is s2 and _FakeHandle.created == 1
+    pts = np.zeros((5, 3), np.float32)
+    for _ in range(3):                      # three "blocks"
+        mcg._session_for(m).set_points(pts, 1.0, None)
+    assert s1.handle.calls.count('nw_set_points') == 1
+    # the table is bounded and closes what it evicts
+    others = [Slotted() for _ in range(mcg._FALLBACK_LIMIT)]
+    for o in others:
+        mcg._session_for(o)
+    assert len(mcg._FALLBACK_SESSIONS) == mcg._FALLBACK_LIMIT and s1.handle.h is None
+    mcg.release_session(others[-1])
+    assert id(others[-1]) not in mcg._FALLBACK_SESSIONS
+
+
+def test_mesh_factory_mixes_the_gpu_path_into_the_host_mesh_class(monkeypatch):
+    """when the reference's ``ch_shrinkwrap._membrane_mesh`` imports, the recipe must still run the GPU
+    solver -- not MembraneMesh.opt_conjugate_gradient's own CPU ShrinkwrapMeshConjGrad (_membrane_mesh.pyx:1428)."""
+    import sys
+    import types
+    from ch_shrinkwrap_b200 import membrane_mesh as mm
+    from ch_shrinkwrap_b200 import minimesh
+    from ch_shrinkwrap_b200.recipe_modules import surface_fitting as sf
+
+    ran = []
+
+    class HostMembraneMesh(minimesh.MiniMesh):          # stands in for the PYME-backed class
+        def __init__(self, mesh=None, **kw):
+            minimesh.MiniMesh.__init__(self, mesh.vertices, mesh.faces)
+            self.kc, self.step_size, self.max_iter, self.remesh_frequency, self.delaunay_remesh_frequency = 1.0, 1.0, 4, 2, 0
+            self.shrink_weight, self.search_k, self.search_rad, self.smooth_curvature = 0, 200, 100, False
+            for k, v in kw.items():
+                setattr(self, k, v)
+
+        def opt_conjugate_gradient(self, *a, **k):      # the CPU path that must NOT run
+            ran.append('cpu')
+
+        def remesh(self, n, target_length, l, n_relax=0):
+            ran.append('host remesh')
+
+    pkg = types.ModuleType('ch_shrinkwrap')
+    mod = types.ModuleType('ch_shrinkwrap._membrane_mesh')
+    mod.MembraneMesh = HostMembraneMesh
+    pkg._membrane_mesh = mod
+    monkeypatch.setitem(sys.modules, 'ch_shrinkwrap', pkg)
+    monkeypatch.setitem(sys.modules, 'ch_shrinkwrap._membrane_mesh', mod)
+    monkeypatch.setattr(sf, '_GPU_MESH_CLASS', {})
+
+    class SolverSpy:
+        def __init__(self, mesh, points, **kw):
+            ran.append('gpu solver built')
+
+        def search(self, points, lams, num_iters=10, sigma_inv=1.0, weights=None):
+            ran.append('gpu search %d' % num_iters)
+
+    monkeypatch.setattr(mm, 'ShrinkwrapMeshConjGrad', SolverSpy)
+    base = minimesh.sphere_mesh(100.0, 3)
+    mesh = sf._mesh_factory(base, kc=1.0, max_iter=4, step_size=10.0, remesh_frequency=2, delaunay_remesh_frequency=0)
+    assert isinstance(mesh, HostMembraneMesh) and isinstance(mesh, mm.ShrinkwrapMeshMixin)
+    assert type(mesh).opt_conjugate_gradient is mm.ShrinkwrapMeshMixin.opt_conjugate_gradient
+    pts = np.zeros((10, 3), np.float32)
+    mesh.shrink_wrap(pts, np.ones((10, 3), np.float32), method='conjugate_gradient')
+    assert 'cpu' not in ran
+    assert ran.count('gpu solver built') == 2 and ran.count('gpu search 2') == 2      # 4 iterations in blocks of 2
+    assert 'host remesh' in ran                                                            # topology stays with the host class
+
+
+def test_smoothing_skip_is_reported(caplog):
+    from ch_shrinkwrap_b200 import membrane_mesh as mm
+    m = mm.MembraneMesh.__new__(mm.MembraneMesh)
+    m.smooth_curvature = True
+    m.curvature_grad_c = lambda *a, **k: None
+    import logging
+    with caplog.at_level(logging.WARNING):
+        m._populate_curvature_grad()
+    assert 'unsmoothed' in caplog.text and m._curvature_smoothing.startswith('skipped')
