@@ -47,6 +47,9 @@ SIGNATURES = {
     'nw_curvature_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                                   _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, c_float, c_float, c_float, _f, _d, c_uint64]),
     'nw_neck_candidates': (c_int, [c_void_p, c_float, c_float, _i, POINTER(c_int)]),
+    'nw_set_point_targets': (c_int, [c_void_p, c_void_p, c_int, c_int64]),
+    'nw_points_from_mesh': (c_int, [c_void_p, _f, _i, c_int, c_int, c_double, _d, c_int64, POINTER(c_int64)]),
+    'nw_holepunch_pair_candidate_faces': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, _i, c_int, _i]),
     'nw_bench_kernel': (c_int, [c_void_p, c_char_p, c_int, _f]),
     'nw_sync': (c_int, [c_void_p]),
     'nw_reset_seeds': (c_int, [c_void_p]),

@@ -116,6 +116,8 @@ struct nw_ctx {
     float key_lo[3] = {0, 0, 0}, key_inv = 0.f;  // quantisation used for those keys
     int *parent_g = nullptr; int2 *kids = nullptr;  // the same tree addressed by global node ids (what the search walks)
     unsigned *fcells = nullptr;                  // per sorted slot: grid cell of the centroid at upload time, x | y << 10 | z << 20
+    bool points_mode = false;                    // the "faces" are raw target points (nw_set_point_targets): centroid = the point itself
+    double *cent64 = nullptr;                    // points mode with float64 targets: exact coordinates per sorted slot (3 doubles)
     // ---- solver vectors ----
     unsigned long long *acc = nullptr;           // (M,4) int64 fixed point: AH res xyz, AH 1
     float4 *Sq = nullptr;                        // search directions, interleaved: S_k of vertex v at Sq[3v + k] (48 B per vertex)

@@ -8,6 +8,10 @@
 // (dH, dK, pE, dEdN) are within the CUDA math library's 1-2 ulp.
 #include <cub/cub.cuh>
 #include <cmath>
+#include <cstddef>
+#include <cstring>
+#include <thread>
+#include <vector>
 #include "common.cuh"
 
 namespace {
@@ -110,16 +114,20 @@ __global__ void k_valid_flags(const VertRec *__restrict__ V, int M, int *__restr
     if (i < M) flag[i] = V[i].halfedge != -1;
 }
 
-struct CurvOut { float *k0, *k1, *e0, *e1, *H, *K, *dH, *dK, *E, *pE, *dEnb, *dEdN; };
+struct CurvOut { float *k0, *k1, *e0, *e1, *H, *K, *dH, *dK, *E, *pE, *dEnb, *dEdN; int *n_deleted; };
 
-__global__ void __launch_bounds__(128) k_curvature(const VertRec *__restrict__ V, const FaceRec *__restrict__ F,
+#ifndef NW_CURV_MINB
+#define NW_CURV_MINB 4      // 128 registers, 16 warps per SM: measured at C3 0.285 ms (3 blocks, 152 registers) -> 0.242 ms; 5 blocks (96 registers, spills) 0.248 ms
+#endif
+__global__ void __launch_bounds__(128, NW_CURV_MINB) k_curvature(const VertRec *__restrict__ V, const FaceRec *__restrict__ F,
                                                    const HeRec *__restrict__ HE, int M, float dN, float kc, float kg, float c0,
                                                    const double *__restrict__ jitter_u, const int *__restrict__ jitter_off,
                                                    unsigned long long seed, CurvOut o) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     const VertRec *cv = &V[i];
-    if (cv->halfedge == -1) {                        // membrane_mesh_utils.c:962-973 (k0,k1,e0,e1 untouched)
+    if (cv->halfedge == -1) {                        // membrane_mesh_utils.c:962-973 (k0,k1,e0,e1 untouched: the copy-out skips these rows)
+        atomicAdd(o.n_deleted, 1);
         o.H[i] = o.K[i] = o.dH[i] = o.dK[i] = o.dEnb[i] = o.E[i] = o.pE[i] = 0.0f;
         o.dEdN[3 * i] = o.dEdN[3 * i + 1] = o.dEdN[3 * i + 2] = 0.0f;
         return;
@@ -278,6 +286,7 @@ static void curv_outputs(nw_ctx *h, CurvOut &co, size_t *offs) {
     co.k0 = out + offs[0]; co.k1 = out + offs[1]; co.H = out + offs[2]; co.K = out + offs[3]; co.dH = out + offs[4];
     co.dK = out + offs[5]; co.E = out + offs[6]; co.pE = out + offs[7]; co.dEnb = out + offs[8];
     co.e0 = out + offs[9]; co.e1 = out + offs[10]; co.dEdN = out + offs[11];
+    co.n_deleted = (int *)(out + 18 * M);              // one counter behind the 18 M floats: comes back with the same copy
 }
 
 int nw_curvature_relaunch(nw_ctx *h) {
@@ -292,6 +301,16 @@ int nw_curvature_relaunch(nw_ctx *h) {
     return NW_OK;
 }
 
+// rows [a, b) of one output array: plain copy, or (masked) only the rows of live vertices
+static void copy_rows(float *dst, const float *src, size_t a, size_t b, int width, const char *vertex_records) {
+    if (!vertex_records) { memcpy(dst + a * width, src + a * width, (b - a) * width * sizeof(float)); return; }
+    for (size_t i = a; i < b; ++i) {
+        int he;
+        memcpy(&he, vertex_records + i * sizeof(VertRec) + offsetof(VertRec, halfedge), sizeof(int));
+        if (he != -1) memcpy(dst + i * width, src + i * width, width * sizeof(float));
+    }
+}
+
 extern "C" int nw_curvature_grad(nw_ctx *h, const void *vertices, const void *faces, const void *halfedges, int n_vertices,
                                  int n_faces, int n_halfedges, float dN, float skip_prob, float *k_0, float *k_1, float *e_0,
                                  float *e_1, float *H, float *K, float *dH, float *dK, float *E, float *pE, float *dE_neighbors,
@@ -304,22 +323,19 @@ extern "C" int nw_curvature_grad(nw_ctx *h, const void *vertices, const void *fa
     cudaStream_t s = h->stream;
     const int M = n_vertices;
     int *flag = nullptr;
+    // device copies are grow-only members: remove_necks calls this once per remesh block (_membrane_mesh.pyx:1212)
     NW_CHECK(nw_alloc(h, (VertRec **)&h->cvV, (size_t)M)); NW_CHECK(nw_alloc(h, (FaceRec **)&h->cvF, (size_t)n_faces));
-    NW_CHECK(nw_alloc(h, (HeRec **)&h->cvH, (size_t)n_halfedges)); NW_CHECK(nw_alloc(h, &h->cvOut, (size_t)18 * M));
+    NW_CHECK(nw_alloc(h, (HeRec **)&h->cvH, (size_t)n_halfedges)); NW_CHECK(nw_alloc(h, &h->cvOut, (size_t)18 * M + 4));
     nw_free(&h->cvJ); nw_free(&h->cvOff);
     h->curvM = M; h->cv_dN = dN; h->cv_kc = kc; h->cv_kg = kg; h->cv_c0 = c0; h->cv_seed = (unsigned long long)jitter_seed;
+    // the three record arrays go up through the pinned multi-lane path (xfer.cu), back to back on the handle's stream
     NW_CHECK(nw_h2d(h, h->cvV, vertices, sizeof(VertRec) * (size_t)M));
     NW_CHECK(nw_h2d(h, h->cvF, faces, sizeof(FaceRec) * (size_t)n_faces));
     NW_CHECK(nw_h2d(h, h->cvH, halfedges, sizeof(HeRec) * (size_t)n_halfedges));
     CurvOut co;
     size_t offs[12];
     curv_outputs(h, co, offs);
-    // k0,k1,e0,e1 rows of deleted vertices are left untouched by the reference: seed them with the caller's values
-    float *host_out[12] = {k_0, k_1, H, K, dH, dK, E, pE, dE_neighbors, e_0, e_1, dEdN};
-    NW_CUDA(cudaMemcpyAsync(co.k0, k_0, sizeof(float) * M, cudaMemcpyHostToDevice, s));
-    NW_CUDA(cudaMemcpyAsync(co.k1, k_1, sizeof(float) * M, cudaMemcpyHostToDevice, s));
-    NW_CUDA(cudaMemcpyAsync(co.e0, e_0, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
-    NW_CUDA(cudaMemcpyAsync(co.e1, e_1, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, s));
+    NW_CUDA(cudaMemsetAsync(co.n_deleted, 0, sizeof(int), s));
     if (jitter_u) {
         NW_CHECK(nw_alloc(h, &flag, (size_t)M)); NW_CHECK(nw_alloc(h, &h->cvOff, (size_t)M));
         k_valid_flags<<<nw_grid(M, 256), 256, 0, s>>>((const VertRec *)h->cvV, M, flag);
@@ -338,9 +354,36 @@ extern "C" int nw_curvature_grad(nw_ctx *h, const void *vertices, const void *fa
         NW_CUDA(cudaMemcpyAsync(h->cvJ, jitter_u, sizeof(double) * nj, cudaMemcpyHostToDevice, s));
     }
     NW_CHECK(nw_curvature_relaunch(h));
-    for (int k = 0; k < 12; ++k)
-        NW_CUDA(cudaMemcpyAsync(host_out[k], h->cvOut + offs[k], sizeof(float) * (k < 9 ? 1 : 3) * M, cudaMemcpyDeviceToHost, s));
+    // ONE device->host copy of all 18 M output floats (+ the deleted-row counter) into the handle's pinned buffer, then
+    // a threaded scatter into the caller's twelve arrays.  k0, k1, e0, e1 of deleted vertices keep the caller's values
+    // (the reference leaves them untouched, membrane_mesh_utils.c:962-973): those four arrays are copied row by row,
+    // skipping rows whose record has halfedge == -1, only when the kernel met such a row at all.
+    const size_t out_bytes = sizeof(float) * 18 * (size_t)M + sizeof(int);
+    if (h->pin_bytes < out_bytes) {
+        if (h->pin_host) cudaFreeHost(h->pin_host);
+        h->pin_host = nullptr; h->pin_bytes = 0;
+        NW_CUDA(cudaHostAlloc((void **)&h->pin_host, out_bytes + out_bytes / 4, cudaHostAllocDefault));
+        h->pin_bytes = out_bytes + out_bytes / 4;
+    }
+    h->pin_fresh = false;                       // the buffer no longer holds the positions
+    NW_CUDA(cudaMemcpyAsync(h->pin_host, h->cvOut, out_bytes, cudaMemcpyDeviceToHost, s));
     NW_CUDA(cudaStreamSynchronize(s));
+    const float *src = (const float *)h->pin_host;
+    int n_deleted = 0;
+    memcpy(&n_deleted, src + 18 * (size_t)M, sizeof(int));
+    float *host_out[12] = {k_0, k_1, H, K, dH, dK, E, pE, dE_neighbors, e_0, e_1, dEdN};
+    const char *recs = n_deleted > 0 ? (const char *)vertices : nullptr;
+    auto part = [&](size_t a, size_t b) {
+        for (int k = 0; k < 12; ++k) {
+            const bool keep_deleted = (k == 0 || k == 1 || k == 9 || k == 10);
+            copy_rows(host_out[k], src + offs[k], a, b, k < 9 ? 1 : 3, keep_deleted ? recs : nullptr);
+        }
+    };
+    const size_t nt = (size_t)M < 65536 ? 1 : std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency() / 2));
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(part, (size_t)M * t / nt, (size_t)M * (t + 1) / nt);
+    part(0, (size_t)M / nt);
+    for (auto &t : th) t.join();
     h->curvK = co.K;       // stays on the device for the neck criterion
     return NW_OK;
 }

@@ -37,6 +37,11 @@ struct QueryF32 {
         double dx = (double)x - (double)c.x, dy = (double)y - (double)c.y, dz = (double)z - (double)c.z;
         return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     }
+    // the same against a float64 target (points mode, nw_set_point_targets)
+    __device__ __forceinline__ double d2(const double *c) const {
+        double dx = (double)x - c[0], dy = (double)y - c[1], dz = (double)z - c[2];
+        return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    }
 };
 
 struct QueryF64 {
@@ -61,7 +66,15 @@ struct QueryF64 {
         double dx = x - (double)c.x, dy = y - (double)c.y, dz = z - (double)c.z;
         return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     }
+    __device__ __forceinline__ double d2(const double *c) const {
+        double dx = x - c[0], dy = y - c[1], dz = z - c[2];
+        return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    }
 };
+
+// float32 box that certainly contains the float64 value a float32 was rounded from (one ulp either side)
+__device__ __forceinline__ float4 ulp_below(const float4 c) { return make_float4(nextafterf(c.x, -FLT_MAX), nextafterf(c.y, -FLT_MAX), nextafterf(c.z, -FLT_MAX), c.w); }
+__device__ __forceinline__ float4 ulp_above(const float4 c) { return make_float4(nextafterf(c.x, FLT_MAX), nextafterf(c.y, FLT_MAX), nextafterf(c.z, FLT_MAX), c.w); }
 
 
 struct Nearest {
@@ -121,6 +134,7 @@ __device__ __forceinline__ float node_score(const Q &q, const Box *__restrict__ 
 // back to back, root = 0, leaves = [leaf0, n_nodes)), so a step needs no per-level offset lookups.
 struct TreeView {
     const float4 *__restrict__ cent;
+    const double *__restrict__ cent64;  // NULL, or (points mode, float64 targets) the exact coordinates per slot: cent[] only prunes
     const Box *__restrict__ boxes;
     const int *__restrict__ parent;     // global id of the parent | (the parent is the last child of its parent) << 31
     const int2 *__restrict__ kids;      // inner node: {global id of the first child, children}; leaf: {first slot, centroids}
@@ -139,7 +153,7 @@ struct TreeView {
 // broadcast loads) and pays for the union of the lanes' node sets instead of 32 interleaved private walks.
 // All 32 lanes must call the methods; lanes past the end of the array are constructed with active_ = false, which
 // gives them a bound no node can satisfy (no branch on `active` inside the walk).
-template <typename Q, bool PACKET = false, bool COUNT = true>
+template <typename Q, bool PACKET = false, bool COUNT = true, bool T64 = false>
 struct Traversal {
     Q q;
     Nearest best;
@@ -217,7 +231,9 @@ struct Traversal {
         if constexpr (COUNT) ++n_leaves;
         for (int s = k.x; s < k.x + k.y; ++s) {
             const float4 c = __ldg(&tv.cent[s]);
-            if (q.lb_box(c, c) <= best.ub) { if constexpr (COUNT) ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
+            if constexpr (T64) {             // points mode with float64 targets: the float32 copy (widened by an ulp) only prunes
+                if (q.lb_box(ulp_below(c), ulp_above(c)) <= best.ub) { if constexpr (COUNT) ++n_exact; best.offer(q.d2(tv.cent64 + 3 * (size_t)s), s, __float_as_int(c.w)); }
+            } else if (q.lb_box(c, c) <= best.ub) { if constexpr (COUNT) ++n_exact; best.offer(q.d2(c), s, __float_as_int(c.w)); }
         }
     }
 #ifdef NW_LEVEL_STATS
@@ -370,14 +386,14 @@ struct Sweep1Args {
 #ifndef NW_FN_INLINE
 #define NW_FN_INLINE __noinline__
 #endif
-template <bool F64, bool STATS>
+template <bool F64, bool STATS, bool T64>
 __device__ NW_FN_INLINE Nearest find_nearest(const Sweep1Args &a, int64_t i, bool active, float x, float y, float z,
                                              double xd, double yd, double zd, Nearest best) {
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;   // 2^-20 * L1 magnitude
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
     if constexpr (F64) q.set(xd, yd, zd);
     else { q.x = x; q.y = y; q.z = z; }
-    Traversal<decltype(q), true, STATS> tr(q, best, a.tv, eps, a.st->cell_escape, active);
+    Traversal<decltype(q), true, STATS, T64> tr(q, best, a.tv, eps, a.st->cell_escape, active);
 #ifdef NW_LEVEL_STATS
     tr.dbg = a.st; tr.dbg_tl = &a.tl;
 #endif
@@ -397,7 +413,7 @@ __device__ NW_FN_INLINE Nearest find_nearest(const Sweep1Args &a, int64_t i, boo
         if (active && tr.best.slot < 0) {
             if (seed < 0) seed = start;
             const float4 c = __ldg(&a.tv.cent[seed]);
-            tr.best.offer(tr.q.d2(c), seed, __float_as_int(c.w));
+            tr.best.offer(T64 ? tr.q.d2(a.tv.cent64 + 3 * (size_t)seed) : tr.q.d2(c), seed, __float_as_int(c.w));
         }
         tr.set_packet_centre(__ffs(alive) - 1);
         tr.from_seed(start);
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
 #ifndef NW_S1_MINB
 #define NW_S1_MINB 16     // 32 registers, 64 warps per SM.  Measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 before the global-id tables; after them 48 regs 2.47, 40 regs 2.51, 32 regs 2.33 -- the packet walk is a dependent chain, occupancy hides it
 #endif
-template <bool F64, int MODE, bool STATS>
+template <bool F64, int MODE, bool STATS, bool T64 = false>
 __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB) : NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
     if (MODE == 1 && a.st->stop) return;
 
@@ -528,7 +544,7 @@ __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB)
     best.ub = FLT_MAX * 2.0f;
     best.slot = -1;
     best.face = 0x7fffffff;
-    best = find_nearest<F64, STATS>(a, i, active, x, y, z, xd, yd, zd, best);
+    best = find_nearest<F64, STATS, T64>(a, i, active, x, y, z, xd, yd, zd, best);
     if (active && best.slot < 0) {      // non-finite query: nothing compares; flag it (the reference asserts on NaN) and stay in bounds
         a.st->nan_flag = 1;
         best.slot = 0;
@@ -799,16 +815,18 @@ __global__ void k_scatter_vidx(const int *__restrict__ slot, const int4 *__restr
     if (face) face[s] = sf.w;
 }
 template <bool F64>
-__global__ void k_scatter_dist(const int *__restrict__ slot, const float4 *__restrict__ cent, const int *__restrict__ perm, int64_t P,
+__global__ void k_scatter_dist(const int *__restrict__ slot, const float4 *__restrict__ cent, const double *__restrict__ cent64,
+                               const int *__restrict__ perm, int64_t P,
                                const float *__restrict__ px, const float *__restrict__ py, const float *__restrict__ pz,
                                const double *__restrict__ px64, const double *__restrict__ py64, const double *__restrict__ pz64,
                                double *__restrict__ dist) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= P) return;
-    const float4 c = cent[slot[i]];
+    const int s = slot[i];
+    const float4 c = cent[s];
     double d2;
-    if (F64) { QueryF64 q; q.set(px64[i], py64[i], pz64[i]); d2 = q.d2(c); }
-    else { QueryF32 q{px[i], py[i], pz[i]}; d2 = q.d2(c); }
+    if (F64) { QueryF64 q; q.set(px64[i], py64[i], pz64[i]); d2 = cent64 ? q.d2(cent64 + 3 * (size_t)s) : q.d2(c); }
+    else { QueryF32 q{px[i], py[i], pz[i]}; d2 = cent64 ? q.d2(cent64 + 3 * (size_t)s) : q.d2(c); }
     dist[perm[i]] = sqrt(d2);
 }
 __global__ void k_pack3(const float *__restrict__ src, int M, float4 *__restrict__ dst) {
@@ -842,7 +860,7 @@ static Sweep1Args make_args(nw_ctx *h) {
     a.slot = h->slot;
     a.w0 = h->w0; a.w1 = h->w1; a.w2 = h->w2; a.rx = h->rx; a.ry = h->ry; a.rz = h->rz;
     a.posq = h->posq; a.sfaces = h->sfaces; a.tl = h->tl; a.F = h->F;
-    a.tv.cent = h->cent; a.tv.boxes = h->boxes; a.tv.parent = h->parent_g; a.tv.kids = h->kids; a.tv.leaf_of_slot = h->leaf_of_slot;
+    a.tv.cent = h->cent; a.tv.cent64 = h->points_mode ? h->cent64 : nullptr; a.tv.boxes = h->boxes; a.tv.parent = h->parent_g; a.tv.kids = h->kids; a.tv.leaf_of_slot = h->leaf_of_slot;
     a.tv.leaf_level = h->tl.n_levels - 1; a.tv.leaf0 = h->tl.n_levels > 0 ? h->tl.off[h->tl.n_levels - 1] : 0;
     a.tv.fcells = h->fcells; a.tv.grid_lo = make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]); a.tv.grid_inv = h->key_inv;
     a.tv.grid_cellw = h->key_inv > 0.f ? 1.f / h->key_inv : 0.f;
@@ -943,7 +961,11 @@ int nw_launch_sweep1(nw_ctx *h, bool scatter) {
 #else
     const bool stats = (h->profile & 2) != 0;
 #endif
-    if (h->px64) {
+    if (a.tv.cent64) {
+        // points mode with float64 targets (nw_set_point_targets): only the nearest-target query exists, no statistics
+        NW_ARG(!scatter, "sweep1: float64 point targets support nearest-point queries only");
+        if (h->px64) k_sweep1<true, 0, false, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false, true><<<G, B, 0, h->stream>>>(a);
+    } else if (h->px64) {
         if (stats) { if (scatter) k_sweep1<true, 1, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, true><<<G, B, 0, h->stream>>>(a); }
         else { if (scatter) k_sweep1<true, 1, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, false><<<G, B, 0, h->stream>>>(a); }
     } else {
@@ -1032,8 +1054,8 @@ extern "C" int nw_get_weights(nw_ctx *h, int32_t *v_idx, float *w, double *dist,
     }
     if (dist) {
         double *dd = (double *)h->scratchP;
-        if (h->px64) k_scatter_dist<true><<<nw_grid(P, B), B, 0, s>>>(h->slot, h->cent, h->perm, P, h->px, h->py, h->pz, h->px64, h->py64, h->pz64, dd);
-        else k_scatter_dist<false><<<nw_grid(P, B), B, 0, s>>>(h->slot, h->cent, h->perm, P, h->px, h->py, h->pz, nullptr, nullptr, nullptr, dd);
+        if (h->px64) k_scatter_dist<true><<<nw_grid(P, B), B, 0, s>>>(h->slot, h->cent, h->points_mode ? h->cent64 : nullptr, h->perm, P, h->px, h->py, h->pz, h->px64, h->py64, h->pz64, dd);
+        else k_scatter_dist<false><<<nw_grid(P, B), B, 0, s>>>(h->slot, h->cent, h->points_mode ? h->cent64 : nullptr, h->perm, P, h->px, h->py, h->pz, nullptr, nullptr, nullptr, dd);
         NW_LAUNCH_CHECK();
         NW_CUDA(cudaMemcpyAsync(dist, dd, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
         NW_CUDA(cudaStreamSynchronize(s));

@@ -74,10 +74,15 @@ __global__ void k_unpack_vertex_records(const int *__restrict__ rec, int M, cons
     valence[v] = n;
 }
 
-__global__ void k_face_bbox(const int *__restrict__ faces, const float4 *__restrict__ pos, int F, int *__restrict__ out6) {
+// `points`: the "faces" are single target points (nw_set_point_targets): the centroid IS the point, no arithmetic
+__device__ __forceinline__ float3 centroid_of(bool points, const float4 a, const float4 b, const float4 c) {
+    return points ? make_float3(a.x, a.y, a.z) : centroid_f32(a, b, c);
+}
+
+__global__ void k_face_bbox(const int *__restrict__ faces, const float4 *__restrict__ pos, int F, int *__restrict__ out6, bool points) {
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
-        float3 c = centroid_f32(pos[faces[3 * f]], pos[faces[3 * f + 1]], pos[faces[3 * f + 2]]);
+        float3 c = centroid_of(points, pos[faces[3 * f]], pos[faces[3 * f + 1]], pos[faces[3 * f + 2]]);
         float v[3] = {c.x, c.y, c.z};
         for (int a = 0; a < 3; ++a) if (v[a] == v[a]) { lo[a] = fminf(lo[a], v[a]); hi[a] = fmaxf(hi[a], v[a]); }
     }
@@ -105,10 +110,10 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {
 }
 
 __global__ void k_face_keys(const int *__restrict__ faces, const float4 *__restrict__ pos, int F, float3 lo, float inv,
-                            unsigned *__restrict__ keys, int *__restrict__ idx, unsigned *__restrict__ cells) {
+                            unsigned *__restrict__ keys, int *__restrict__ idx, unsigned *__restrict__ cells, bool points) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
-    float3 c = centroid_f32(pos[faces[3 * f]], pos[faces[3 * f + 1]], pos[faces[3 * f + 2]]);
+    float3 c = centroid_of(points, pos[faces[3 * f]], pos[faces[3 * f + 1]], pos[faces[3 * f + 2]]);
     unsigned qx = (unsigned)fminf(fmaxf((c.x - lo.x) * inv, 0.f), 1023.f);
     unsigned qy = (unsigned)fminf(fmaxf((c.y - lo.y) * inv, 0.f), 1023.f);
     unsigned qz = (unsigned)fminf(fmaxf((c.z - lo.z) * inv, 0.f), 1023.f);
@@ -204,12 +209,12 @@ __global__ void k_copy_minus1(const int *__restrict__ id, int F, int *__restrict
 // Also measures how far (L-infinity, grid units, evaluated with the operations of k_face_keys) any centroid now lies
 // outside the grid cell it was keyed into at upload: the slack of the cell-clearance early-out of the search (sweep.cu).
 __global__ void k_refit_centroids(const int4 *__restrict__ sfaces, const float4 *__restrict__ pos, int F, float4 *__restrict__ cent,
-                                  const unsigned *__restrict__ fcells, float3 lo, float inv, SolverState *st) {
+                                  const unsigned *__restrict__ fcells, float3 lo, float inv, SolverState *st, bool points) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float esc = 0.f;
     if (i < F) {
         const int4 sf = sfaces[i];
-        const float3 cc = centroid_f32(pos[sf.x], pos[sf.y], pos[sf.z]);
+        const float3 cc = centroid_of(points, pos[sf.x], pos[sf.y], pos[sf.z]);
         cent[i] = make_float4(cc.x, cc.y, cc.z, __int_as_float(sf.w));
         const unsigned cell = fcells[i];
         const float gx = (cc.x - lo.x) * inv, gy = (cc.y - lo.y) * inv, gz = (cc.z - lo.z) * inv;
@@ -450,6 +455,8 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     h->M = M; h->F = F;
     h->weights_valid = false;
     h->pin_fresh = false;
+    h->points_mode = false;
+    nw_free(&h->cent64);
     NW_CHECK(nw_alloc(h, &h->posq, (size_t)M)); NW_CHECK(nw_alloc(h, &h->nrmq, (size_t)M));
     NW_CHECK(nw_alloc(h, &h->faces, (size_t)3 * F));
     NW_CHECK(nw_alloc(h, &h->nbrT, (size_t)NW_NEIGHBORSIZE * M)); NW_CHECK(nw_alloc(h, &h->valence, (size_t)M));
@@ -534,7 +541,8 @@ static int extents_pass(nw_ctx *h) {
 static void launch_refit_centroids(nw_ctx *h) {
     cudaMemsetAsync(&h->st->cell_escape, 0, sizeof(float), h->stream);
     k_refit_centroids<<<nw_grid(h->F, 256), 256, 0, h->stream>>>(h->sfaces, h->posq, h->F, h->cent, h->fcells,
-                                                                 make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv, h->st);
+                                                                 make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv, h->st,
+                                                                 h->points_mode);
 }
 
 int nw_tree_refit(nw_ctx *h) {
@@ -553,7 +561,7 @@ int nw_tree_build(nw_ctx *h) {
     NW_CHECK(nw_alloc(h, &d_bbox, 16));
     int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
     NW_CUDA(cudaMemcpyAsync(d_bbox, init, sizeof(init), cudaMemcpyHostToDevice, s));
-    k_face_bbox<<<std::min(nw_grid(F, B), 148 * 4), B, 0, s>>>(h->faces, h->posq, F, d_bbox);
+    k_face_bbox<<<std::min(nw_grid(F, B), 148 * 4), B, 0, s>>>(h->faces, h->posq, F, d_bbox, h->points_mode);
     int bb[6];
     NW_CUDA(cudaMemcpyAsync(bb, d_bbox, sizeof(bb), cudaMemcpyDeviceToHost, s));
     NW_CUDA(cudaStreamSynchronize(s));
@@ -566,7 +574,7 @@ int nw_tree_build(nw_ctx *h) {
     NW_CHECK(nw_alloc(h, &idx, (size_t)F)); NW_CHECK(nw_alloc(h, &order, (size_t)F));
     unsigned *&cells = h->tb_u2;
     NW_CHECK(nw_alloc(h, &cells, (size_t)F)); NW_CHECK(nw_alloc(h, &h->fcells, (size_t)F));
-    k_face_keys<<<nw_grid(F, B), B, 0, s>>>(h->faces, h->posq, F, make_float3(lo[0], lo[1], lo[2]), inv, keys, idx, cells);
+    k_face_keys<<<nw_grid(F, B), B, 0, s>>>(h->faces, h->posq, F, make_float3(lo[0], lo[1], lo[2]), inv, keys, idx, cells, h->points_mode);
     size_t tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, keys2, idx, order, F, 0, 30, s);
     if (tmp > h->cub_tmp_bytes) { NW_CHECK(nw_alloc(h, (char **)&h->cub_tmp, tmp)); h->cub_tmp_bytes = tmp; }
@@ -650,6 +658,70 @@ int nw_tree_build(nw_ctx *h) {
     trace.mark("normals + frames");
     NW_CHECK(extents_pass(h));
     trace.mark("extents");
+    return NW_OK;
+}
+
+// ---- a raw point set as the search target (quality metrics, hole-punch candidate search) -----------------------------
+namespace {
+template <typename T>
+__global__ void k_targets_unpack(const T *__restrict__ xyz, int N, float4 *__restrict__ posq, int *__restrict__ faces) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    posq[i] = make_float4((float)xyz[3 * (size_t)i], (float)xyz[3 * (size_t)i + 1], (float)xyz[3 * (size_t)i + 2], 0.f);
+    faces[3 * (size_t)i] = faces[3 * (size_t)i + 1] = faces[3 * (size_t)i + 2] = i;
+}
+// float64 targets in sorted-slot order, for the exact distance evaluation (the float32 copies only prune)
+__global__ void k_targets_sorted64(const double *__restrict__ xyz, const int4 *__restrict__ sfaces, int N, double *__restrict__ cent64) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const size_t i = (size_t)sfaces[s].w;
+    cent64[3 * (size_t)s] = xyz[3 * i]; cent64[3 * (size_t)s + 1] = xyz[3 * i + 1]; cent64[3 * (size_t)s + 2] = xyz[3 * i + 2];
+}
+}  // namespace
+
+// The search hierarchy over N arbitrary points instead of face centroids: what scipy.spatial.cKDTree(points) is to the
+// reference's quality metrics (evaluation_utils.py:172-180) and hole-punch candidate search (_membrane_mesh.pyx:882-883).
+// Queries go through nw_set_points + nw_compute_weights + nw_get_weights(dist, face): `face` is then the index of the
+// nearest target point and `dist` its float64 distance, exactly as cKDTree.query(k=1) returns them (float64 targets are
+// compared in float64; their float32 roundings only prune).
+extern "C" int nw_set_point_targets(nw_ctx *h, const void *xyz, int is_f64, int64_t N) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(xyz && N > 0 && N < 2147483647LL / 3, "nw_set_point_targets: need 1 <= N < 2^31 / 3 points");
+    NW_ARG(h->nranks == 1, "nw_set_point_targets: single-rank handles only");
+    NW_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int n = (int)N, B = 256;
+    h->M = n; h->F = n;
+    h->weights_valid = false; h->pin_fresh = false; h->feet_valid = false;
+    h->points_mode = true;
+    NW_CHECK(nw_alloc(h, &h->posq, (size_t)n)); NW_CHECK(nw_alloc(h, &h->nrmq, (size_t)n));
+    NW_CHECK(nw_alloc(h, &h->faces, (size_t)3 * n));
+    NW_CHECK(nw_alloc(h, &h->nbrT, (size_t)NW_NEIGHBORSIZE * n)); NW_CHECK(nw_alloc(h, &h->valence, (size_t)n));
+    NW_CHECK(nw_alloc(h, &h->valid, (size_t)n));
+    NW_CHECK(nw_alloc(h, &h->acc, (size_t)4 * n)); NW_CHECK(nw_alloc(h, &h->Sq, (size_t)3 * n));
+    NW_CHECK(nw_alloc(h, &h->fdef, (size_t)3 * n)); NW_CHECK(nw_alloc(h, &h->scratchM, (size_t)3 * n));
+    NW_CHECK(nw_alloc(h, &h->sfaces, (size_t)n)); NW_CHECK(nw_alloc(h, &h->cent, (size_t)n));
+    const size_t raw = (is_f64 ? 8 : 4) * 3 * (size_t)n;
+    NW_CHECK(nw_alloc(h, &h->sp_pts, raw));                      // staging shared with nw_set_points (queries come later)
+    NW_CHECK(nw_h2d(h, h->sp_pts, xyz, raw));
+    if (is_f64) k_targets_unpack<double><<<nw_grid(n, B), B, 0, s>>>((const double *)h->sp_pts, n, h->posq, h->faces);
+    else k_targets_unpack<float><<<nw_grid(n, B), B, 0, s>>>((const float *)h->sp_pts, n, h->posq, h->faces);
+    NW_LAUNCH_CHECK();
+    NW_CUDA(cudaMemsetAsync(h->nrmq, 0, sizeof(float4) * n, s));
+    NW_CUDA(cudaMemsetAsync(h->valence, 0, sizeof(int) * n, s));
+    NW_CUDA(cudaMemsetAsync(h->valid, 1, n, s));
+    NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * n, s));
+    NW_CUDA(cudaMemsetAsync(h->Sq, 0, sizeof(float4) * 3 * n, s));
+    if (h->slot && h->P) NW_CUDA(cudaMemsetAsync(h->slot, 0xff, sizeof(int) * h->P, s));
+    h->seeds_cold = true;
+    h->order_stale = true;
+    NW_CHECK(nw_tree_build(h));
+    if (is_f64) {
+        NW_CHECK(nw_alloc(h, &h->cent64, (size_t)3 * n));
+        k_targets_sorted64<<<nw_grid(n, B), B, 0, s>>>((const double *)h->sp_pts, h->sfaces, n, h->cent64);
+        NW_LAUNCH_CHECK();
+    } else nw_free(&h->cent64);
+    NW_CUDA(cudaStreamSynchronize(s));
     return NW_OK;
 }
 

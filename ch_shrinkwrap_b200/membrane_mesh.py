@@ -201,6 +201,30 @@ class ShrinkwrapMeshMixin:
             self.remove_inner_surfaces()
         return verts
 
+    # -- hole punching: the two searches on the GPU, the topology surgery on the host (_membrane_mesh.pyx:877-907) ---------
+    def _holepunch_find_candidate_faces(self, points, eps=10.0):
+        """Faces with no localisation within eps of their centre (:877-887)."""
+        from .evaluation_utils import nearest_point_distance
+        centres = self._vertices['position'][self.faces].mean(1)
+        dist = nearest_point_distance(points, centres, _session_for(self, getattr(self, '_nw_device', 0)).aux())
+        inds = np.flatnonzero(self._faces['halfedge'] != -1).astype('i4')
+        return inds[dist > eps]
+
+    def _holepunch_pair_candidate_faces(self, candidates):
+        """For each candidate the opposing candidate nearest in the mean-normal plane (:898-907, the USE_C branch)."""
+        candidates = np.ascontiguousarray(candidates, dtype=np.int32)
+        pairs = -1 * np.ones(candidates.shape[0], dtype='i4')
+        verts, faces, hes = (np.ascontiguousarray(a) for a in (self._vertices, self._faces, self._halfedges))
+        if verts.dtype.itemsize != 120 or faces.dtype.itemsize != 24 or hes.dtype.itemsize != 28:
+            raise RuntimeError('mesh record layouts differ from membrane_mesh_utils.h:31-65')
+        if len(candidates):
+            _session_for(self, getattr(self, '_nw_device', 0)).handle.call(
+                'nw_holepunch_pair_candidate_faces', ctypes.c_void_p(verts.ctypes.data), ctypes.c_void_p(faces.ctypes.data),
+                ctypes.c_void_p(hes.ctypes.data), len(verts), len(faces), len(hes), _lib.iptr(candidates), len(candidates), _lib.iptr(pairs))
+        pair_inds = pairs != -1
+        new_inds = np.cumsum(pair_inds) - 1
+        return candidates[pair_inds], new_inds[pairs[pair_inds]]
+
     # -- block driver (_membrane_mesh.pyx:1427-1560) ---------------------------------------------------------
     def opt_conjugate_gradient(self, points, sigma, max_iter=10, step_size=1.0, weights=None, **kwargs):
         r = (self.remesh_frequency != 0) and (self.remesh_frequency <= max_iter)

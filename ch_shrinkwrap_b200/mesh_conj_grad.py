@@ -26,6 +26,13 @@ class _Session:
             rank, nranks, uid = comm
             self.handle.call('nw_comm_init', int(rank), int(nranks), uid)
 
+    def aux(self):
+        """A second handle on the same GPU for searches that need their own points / targets (hole-punch candidate search,
+        quality metrics), so that the fit's resident localisations and topology stay untouched."""
+        if getattr(self, '_aux', None) is None or self._aux.h is None:
+            self._aux = _lib.Handle(self.handle.device)
+        return self._aux
+
     def __deepcopy__(self, memo):
         return None            # device state is not copyable; a copied mesh opens its own session on first use
 
@@ -137,8 +144,6 @@ class ShrinkwrapMeshConjGrad(object):
     def __init__(self, mesh, points, sigma=None, search_k=200, search_rad=100, shield_sigma=None, use_octree=False,
                  device=0, comm=None):
         self.tests, self.ress, self.prefs = [], [], []             # conj_grad.py:37-39
-        self._tests64 = []                                          # the same history as the device computed it (float64): what
-                                                                    # the stop rule sees, so search(10) == search(5); search(5)
         self.Lfuncs, self.Lhfuncs = ["I"], ["I"]                    # mesh_conj_grad.py:38
         self.mesh = mesh
         self._points = points
@@ -245,14 +250,15 @@ class ShrinkwrapMeshConjGrad(object):
         n = int(num_iters)
         out = np.empty((self.M, 3), np.float32)
         hist = [np.zeros(max(n, 1), np.float64) for _ in range(5)]
-        prev = np.asarray(self._tests64[-3:], dtype=np.float64)
+        # the device forms the statistic in float32 like the reference, so the float32 history IS what it compared:
+        # search(10) stops exactly where search(5); search(5) does
+        prev = np.asarray(self.tests[-3:], dtype=np.float64)
         n_done = ctypes.c_int(0)
         lam = float(lams[0]) if len(lams) > 0 else 0.0
         self._h.call('nw_search', lam, n, int(bool(last_step)), _lib.dptr(prev) if len(prev) else None, int(len(prev)),
                      _lib.fptr(out), *[_lib.dptr(a) for a in hist], ctypes.byref(n_done))
         k = n_done.value
         self.loopcount = k
-        self._tests64.extend(float(t) for t in hist[0][:k])
         self.tests.extend(np.float32(t) for t in hist[0][:k])
         self.ress.extend(hist[1][:k].tolist())
         self.prefs.extend(np.array([p], np.float32) for p in hist[2][:k])

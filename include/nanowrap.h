@@ -145,6 +145,26 @@ int nw_curvature_grad(nw_ctx *h, const void *vertices, const void *faces, const 
  * nw_curvature_grad call; returns the count in *n (idx may be NULL to query the count) */
 int nw_neck_candidates(nw_ctx *h, float low, float high, int32_t *idx, int *n);
 
+/* ---- either side of the solver: quality metrics and the hole-punch candidate search ---------
+ * A raw point set as the search target, replacing scipy.spatial.cKDTree(points) at evaluation_utils.py:172-173
+ * (average_squared_distance) and _membrane_mesh.pyx:882 (_holepunch_find_candidate_faces).  xyz: (N,3) float32
+ * (is_f64 = 0) or float64 (= 1).  Afterwards nw_set_points(queries) + nw_compute_weights + nw_get_weights(NULL,
+ * NULL, dist, face) give, per query, the float64 distance to and the index of its nearest target point exactly as
+ * cKDTree.query(k=1) does (float64 compare; ties -> lowest index).  Replaces any topology set on the handle. */
+int nw_set_point_targets(nw_ctx *h, const void *xyz, int is_f64, int64_t N);
+/* points_from_mesh, evaluation_utils.py:35-145: every triangle sampled on a dx_min grid in its own plane.  pos (M,3)
+ * float32 = mesh._vertices['position'], faces (F,3) int32 = mesh.faces.  Call with out = NULL to get the number of
+ * samples in *n_out, then with out (n,3) float64 and capacity >= n.  Samples come in the reference's generation order
+ * and are bit-identical to its `d` array; the random permutation / subsampling of :137 stays with the caller. */
+int nw_points_from_mesh(nw_ctx *h, const float *pos, const int32_t *faces, int M, int F, double dx_min, double *out,
+                        int64_t capacity, int64_t *n_out);
+/* c_holepunch_pair_candidate_faces, membrane_mesh_utils.c:1301-1379 (binding _membrane_mesh.pyx:890-896): same
+ * arguments plus the array lengths; pairs[i] = index into candidates of the opposing face nearest to candidates[i] in
+ * the mean-normal plane, or -1.  pairs is overwritten (the reference expects it initialised to -1 by the caller). */
+int nw_holepunch_pair_candidate_faces(nw_ctx *h, const void *vertices, const void *faces, const void *halfedges,
+                                      int n_vertices, int n_faces, int n_halfedges, const int32_t *candidates,
+                                      int n_candidates, int32_t *pairs);
+
 /* ---- measurement hooks (bench.py / profiling; not part of the reference surface) ------------------ */
 /* device-resident single-kernel launches on the handle's stream, for CUDA-event timing */
 int nw_bench_kernel(nw_ctx *h, const char *name, int reps, float *ms_per_launch);

@@ -89,6 +89,28 @@ def main():
     out['area_w'] = w
     np.savez_compressed(os.path.join(OUT, 'ring_ops.npz'), f=f, seed=103, **out)
     print('ring_ops ok')
+    quality_fixture()
+
+
+def quality_fixture():
+    """Quality metrics and hole-punch searches from the unmodified reference:
+    evaluation_utils.points_from_mesh / average_squared_distance (imported), c_holepunch_pair_candidate_faces (compiled
+    from the reference's source through oracle/ref_curvature_wrapper.c)."""
+    from ch_shrinkwrap_b200 import synth
+    evu = refharness.load_evaluation_utils()
+    shape = synth.two_lobed()
+    m = synth.star_mesh(shape, 4, scale=1.0)
+    np.random.seed(5)
+    d = evu.points_from_mesh(m, dx_min=25)                      # random order (np.random.choice, :137)
+    order = np.lexsort((d[:, 2], d[:, 1], d[:, 0]))
+    pts, _ = synth.smlm_cloud(shape, 4000, seed=104)
+    msd = evu.average_squared_distance(d, pts.astype(np.float64))
+    msd32 = evu.average_squared_distance(d.astype(np.float32), pts)
+    cand = np.arange(len(m._faces), dtype=np.int32)[::2].copy()
+    pairs = refharness.reference_holepunch_pairs(m, cand)
+    np.savez_compressed(os.path.join(OUT, 'quality.npz'), n_geo=4, dx_min=25, samples_sorted=d[order], cloud_seed=104, cloud_n=4000,
+                        msd=np.array(msd), msd32=np.array(msd32), candidates=cand, pairs=pairs)
+    print('quality ok', d.shape, msd, int((pairs != -1).sum()))
 
 
 if __name__ == '__main__':

@@ -312,3 +312,76 @@ def curvature_grad(mesh, dN=0.1, skip_prob=0.0, kc=1.0, kg=-20.0 * 0.0257, c0=0.
         ctypes.c_float(kc), ctypes.c_float(kg), ctypes.c_float(c0), out['dEdN'].ctypes.data_as(fp),
         None if ju is None else ju.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
     return out
+
+
+# ---- quality metrics and hole-punch searches -----------------------------------------------
+def points_from_mesh_samples(mesh, dx_min=5):
+    """The ``d`` array of ``points_from_mesh`` (evaluation_utils.py:59-135) BEFORE the random permutation of :137,
+    restated statement by statement (same dtypes: float32 frame, float64 grid)."""
+    tris = mesh._vertices['position'][mesh.faces]                                   # :59
+    norms = np.cross((tris[:, 2, :] - tris[:, 1, :]), (tris[:, 0, :] - tris[:, 1, :]))   # :61
+    nn = np.linalg.norm(norms, axis=1)
+    nan_mask = nn != 0                                                              # :67
+    norms = norms[nan_mask] / nn[nan_mask, None]
+    tris = tris[nan_mask, :, :]
+    v0 = tris[:, 1, :] - tris[:, 0, :]                                              # :78-81
+    e0n = np.linalg.norm(v0, axis=1)
+    e0 = v0 / e0n[:, None]
+    e1 = np.cross(norms, e0, axis=1)
+    x0 = (tris[:, 0, :] * e0).sum(1); y0 = (tris[:, 0, :] * e1).sum(1)              # :84-89
+    x1 = (tris[:, 1, :] * e0).sum(1); y1 = (tris[:, 1, :] * e1).sum(1)
+    x2 = (tris[:, 2, :] * e0).sum(1); y2 = (tris[:, 2, :] * e1).sum(1)
+    x0x1x2 = np.vstack([x0, x1, x2]).T; y0y1y2 = np.vstack([y0, y1, y2]).T          # :92-97
+    xl, xu = np.min(x0x1x2, axis=1), np.max(x0x1x2, axis=1)
+    yl, yu = np.min(y0y1y2, axis=1), np.max(y0y1y2, axis=1)
+    x1x0, x2x1, x0x2 = x1 - x0, x2 - x1, x0 - x2                                    # :100-110
+    with np.errstate(divide='ignore', invalid='ignore'):
+        m0 = (y1 - y0) / x1x0; m0[x1x0 == 0] = 0
+        m1 = (y2 - y1) / x2x1; m1[x2x1 == 0] = 0
+        m2 = (y0 - y2) / x0x2; m2[x0x2 == 0] = 0
+    s1, s2 = np.sign(m1), np.sign(m2)
+    d = []
+    for i in range(tris.shape[0]):                                                  # :117-133
+        x = np.arange(xl[i] - x0[i] - dx_min / 2, xu[i] - x0[i], dx_min)
+        y = np.arange(yl[i] - y0[i] - dx_min / 2, yu[i] - y0[i], dx_min)
+        X, Y = np.meshgrid(x, y)
+        X_mask = (Y > X * m0[i]) & (s1[i] * Y > s1[i] * (y1[i] - y0[i] + (X - x1[i] + x0[i]) * m1[i])) & \
+                 (s2[i] * Y < s2[i] * (y2[i] - y0[i] + (X - x2[i] + x0[i]) * m2[i]))
+        pos = X[X_mask].ravel()[:, None] * e0[i, None, :] + Y[X_mask].ravel()[:, None] * e1[i, None, :] + tris[i, 0, :]
+        d.append(pos)
+    return np.vstack(d) if d else np.zeros((0, 3))
+
+
+def average_squared_distance(points0, points1):
+    """evaluation_utils.py:147-180."""
+    t0, t1 = scipy.spatial.cKDTree(points0), scipy.spatial.cKDTree(points1)
+    e0, _ = t0.query(points1, k=1)
+    e1, _ = t1.query(points0, k=1)
+    return np.nansum(e0 ** 2) / len(e0), np.nansum(e1 ** 2) / len(e1)
+
+
+def holepunch_find_candidate_faces(mesh, points, eps=10.0):
+    """_membrane_mesh.pyx:877-887."""
+    tree = scipy.spatial.cKDTree(points)
+    dist, _ = tree.query(mesh._vertices['position'][mesh.faces].mean(1))
+    inds = np.flatnonzero(mesh._faces['halfedge'] != -1).astype('i4')
+    return inds[dist > eps]
+
+
+def holepunch_pairs(mesh, candidates):
+    """Raw ``pairs`` of c_holepunch_pair_candidate_faces (membrane_mesh_utils.c:1301-1379, restated in oracle_c.c)."""
+    verts, faces, hes = (np.ascontiguousarray(a) for a in (mesh._vertices, mesh._faces, mesh._halfedges))
+    cand = np.ascontiguousarray(candidates, dtype=np.int32)
+    pairs = -1 * np.ones(len(cand), np.int32)
+    _clib().orc_holepunch_pair(ctypes.c_void_p(verts.ctypes.data), ctypes.c_void_p(faces.ctypes.data), ctypes.c_void_p(hes.ctypes.data),
+                               _p(cand, ctypes.c_int32), ctypes.c_int(len(cand)), _p(pairs, ctypes.c_int32))
+    return pairs
+
+
+def holepunch_pair_candidate_faces(mesh, candidates):
+    """_membrane_mesh.pyx:898-907 (the USE_C branch)."""
+    candidates = np.asarray(candidates)
+    pairs = holepunch_pairs(mesh, candidates)
+    pair_inds = pairs != -1
+    new_inds = np.cumsum(pair_inds) - 1
+    return candidates[pair_inds], new_inds[pairs[pair_inds]]

@@ -335,3 +335,54 @@ void orc_curvature_grad(const void *vertices_, const void *faces_, const void *h
         for (int a = 0; a < 3; ++a) dEdN[3 * i + a] = g * dir[a];
     }
 }
+
+/* ---- hole-punch candidate pairing: membrane_mesh_utils.c:1261-1285 (face centroid) and :1301-1379 ---------------- */
+typedef struct { int32_t vertex, face, twin, next, prev; float length; int32_t component; } orc_he_t;        /* membrane_mesh_utils.h:31-39 */
+typedef struct { int32_t halfedge; float normal[3]; float area; int32_t component; } orc_face_t;             /* :41-46 */
+typedef struct { float position[3]; float normal[3]; int32_t halfedge, valence; int32_t neighbors[20];
+                 int32_t component, locally_manifold; } orc_vert_t;                                          /* :57-65 */
+
+static float orc_fdot(const float *a, const float *b) { float c = 0.0; int i; for (i = 0; i < 3; ++i) c += a[i] * b[i]; return c; }
+static float orc_fnorm(const float *p) { float n = 0.0; int i; for (i = 0; i < 3; ++i) n += p[i] * p[i]; return sqrt(n); }
+static void orc_centroid(const orc_face_t *f, const orc_vert_t *V, const orc_he_t *HE, float *c)
+{
+    const int32_t he = f->halfedge;
+    const float *p0 = V[HE[HE[he].prev].vertex].position, *p1 = V[HE[he].vertex].position, *p2 = V[HE[HE[he].next].vertex].position;
+    const float third = 0.3333333333333333;
+    int k;
+    for (k = 0; k < 3; ++k) { float s = p0[k] + p1[k]; s = s + p2[k]; c[k] = s * third; }
+}
+
+void orc_holepunch_pair(const void *vertices, const void *faces, const void *halfedges, const int32_t *candidates,
+                        int n_candidates, int32_t *pairs)
+{
+    const orc_vert_t *V = (const orc_vert_t *)vertices;
+    const orc_face_t *F = (const orc_face_t *)faces;
+    const orc_he_t *HE = (const orc_he_t *)halfedges;
+    int i, j, k;
+    for (i = 0; i < n_candidates; ++i) {
+        const orc_face_t *fi = &F[candidates[i]];
+        float ci[3], cj[3], n_hat[3], sh[3], s[3];
+        float min_shift = 1e6;
+        orc_centroid(fi, V, HE, ci);
+        for (j = i + 1; j < n_candidates; ++j) {
+            const orc_face_t *fj = &F[candidates[j]];
+            float nd, ndi, ndj, shn, dotn, b, a;
+            if (pairs[j] != -1) continue;                              /* :1334 */
+            nd = orc_fdot(fi->normal, fj->normal);
+            if (nd > -0.6) continue;                                   /* :1342 */
+            orc_centroid(fj, V, HE, cj);
+            for (k = 0; k < 3; ++k) n_hat[k] = (fi->normal[k] + fj->normal[k]) * 0.5f;    /* :1348-1349 */
+            for (k = 0; k < 3; ++k) sh[k] = ci[k] - cj[k];                                /* :1352 */
+            ndi = orc_fdot(fi->normal, sh);
+            ndj = orc_fdot(fj->normal, sh);
+            if ((ndi < 0) && (ndj > 0)) continue;                      /* :1359 */
+            shn = orc_fnorm(sh);
+            dotn = orc_fdot(n_hat, sh);
+            b = dotn * shn;                                            /* :1364 */
+            for (k = 0; k < 3; ++k) s[k] = sh[k] - n_hat[k] * b;
+            a = orc_fdot(s, s);
+            if (a < min_shift) { min_shift = a; pairs[i] = j; }        /* :1370-1374 */
+        }
+    }
+}

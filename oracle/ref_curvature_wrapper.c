@@ -12,3 +12,10 @@ void ref_curvature_grad(void *vertices, void *faces, void *halfedges, float dN, 
     c_curvature_grad(vertices, faces, (halfedge_t *)halfedges, dN, skip_prob, n_vertices, k_0, k_1,
                      e_0, e_1, H, K, dH, dK, E, pE, dE_neighbors, kc, kg, c0, (points_t *)dEdN);
 }
+
+/* c_holepunch_pair_candidate_faces is `static` too (membrane_mesh_utils.c:1301) */
+void ref_holepunch_pair_candidate_faces(void *vertices, void *faces, void *halfedges, int *candidates,
+                                        int n_candidates, int *pairs)
+{
+    c_holepunch_pair_candidate_faces(vertices, faces, (halfedge_t *)halfedges, candidates, n_candidates, pairs);
+}

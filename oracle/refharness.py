@@ -118,3 +118,42 @@ def reference_curvature(mesh, dN=0.1, skip_prob=0.0, kc=1.0, kg=-20.0 * 0.0257, 
         *[out[k].ctypes.data_as(fp) for k in ('k0', 'k1', 'e0', 'e1', 'H', 'K', 'dH', 'dK', 'E', 'pE', 'dE_neighbors')],
         ctypes.c_float(kc), ctypes.c_float(kg), ctypes.c_float(c0), out['dEdN'].ctypes.data_as(fp))
     return out
+
+
+def reference_holepunch_pairs(mesh, candidates):
+    """Reference ``c_holepunch_pair_candidate_faces`` (membrane_mesh_utils.c:1301-1379) on the mesh's structured arrays:
+    returns the raw ``pairs`` array (index into candidates, -1 = none), initialised to -1 like _membrane_mesh.pyx:899."""
+    so = (_build.build_ref() or _build.ref_paths())[1]
+    lib = ctypes.PyDLL(so)
+    verts = np.ascontiguousarray(mesh._vertices)
+    faces = np.ascontiguousarray(mesh._faces)
+    hes = np.ascontiguousarray(mesh._halfedges)
+    cand = np.ascontiguousarray(candidates, dtype=np.int32)
+    pairs = -1 * np.ones(len(cand), np.int32)
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.ref_holepunch_pair_candidate_faces(ctypes.c_void_p(verts.ctypes.data), ctypes.c_void_p(faces.ctypes.data),
+                                           ctypes.c_void_p(hes.ctypes.data), cand.ctypes.data_as(ip), ctypes.c_int(len(cand)),
+                                           pairs.ctypes.data_as(ip))
+    return pairs
+
+
+def load_evaluation_utils():
+    """The reference's ``evaluation_utils`` module, unmodified (points_from_mesh, average_squared_distance are pure
+    numpy/scipy; the module-level imports of the compiled mesh class and of PYME's simulator are stubbed)."""
+    if 'evu' in _mods:
+        return _mods['evu']
+    load_reference()
+
+    def stub(name):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+        return sys.modules[name]
+
+    stub('ch_shrinkwrap._membrane_mesh')
+    sys.modules['ch_shrinkwrap']._membrane_mesh = sys.modules['ch_shrinkwrap._membrane_mesh']
+    stub('PYME.simulation'); stub('PYME.simulation.locify').points_from_sdf = None
+    sys.modules['PYME'].simulation = sys.modules['PYME.simulation']
+    sys.modules['PYME.simulation'].locify = sys.modules['PYME.simulation.locify']
+    import ch_shrinkwrap.evaluation_utils as evu  # noqa: E402  (the reference file, unmodified)
+    _mods['evu'] = evu
+    return evu

@@ -101,3 +101,34 @@ def test_oracle_adjointness_and_stop_rule():
     assert oc._stop_cond()
     oc.tests = [5e-7, 4e-7, 4.5e-7]
     assert not oc._stop_cond()
+
+
+def _quality_case():
+    from ch_shrinkwrap_b200 import synth
+    g = np.load(os.path.join(GOLD, 'quality.npz'))
+    shape = synth.two_lobed()
+    mesh = synth.star_mesh(shape, int(g['n_geo']), scale=1.0)
+    pts, _ = synth.smlm_cloud(shape, int(g['cloud_n']), seed=int(g['cloud_seed']))
+    return g, mesh, pts
+
+
+def _lexsorted(a):
+    return a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+
+
+def test_oracle_quality_metrics_match_reference_fixture():
+    """points_from_mesh / average_squared_distance of the unmodified reference (evaluation_utils.py:35-180): bit-exact."""
+    from oracle import nanowrap_oracle as orc
+    g, mesh, pts = _quality_case()
+    d = orc.points_from_mesh_samples(mesh, int(g['dx_min']))
+    assert np.array_equal(_lexsorted(d), g['samples_sorted'])
+    assert np.array_equal(np.array(orc.average_squared_distance(d, pts.astype(np.float64))), g['msd'])
+    assert np.array_equal(np.array(orc.average_squared_distance(d.astype(np.float32), pts)), g['msd32'])
+
+
+def test_oracle_holepunch_pairs_match_reference_fixture():
+    """c_holepunch_pair_candidate_faces of the unmodified reference (membrane_mesh_utils.c:1301-1379): index-exact."""
+    from oracle import nanowrap_oracle as orc
+    g, mesh, pts = _quality_case()
+    assert np.array_equal(orc.holepunch_pairs(mesh, g['candidates']), g['pairs'])
+    assert (g['pairs'] != -1).sum() > 50

@@ -64,3 +64,23 @@ def test_c_helpers_bitwise_vs_reference():
     cgu.c_shrinkwrap_ah_helper(v_idx, w, fv, a)
     orc.ah_scatter(v_idx, w, fv, b)
     assert np.array_equal(a, b)
+
+
+def test_quality_metrics_and_holepunch_vs_reference():
+    from ch_shrinkwrap_b200 import synth
+    from oracle import nanowrap_oracle as orc
+    from oracle import refharness
+    evu = refharness.load_evaluation_utils()
+    m = synth.star_mesh(synth.two_lobed(), 5, scale=1.0)
+    np.random.seed(3)
+    d_ref = evu.points_from_mesh(m, dx_min=12)
+    d_orc = orc.points_from_mesh_samples(m, 12)
+    np.random.seed(3)
+    perm = np.random.choice(np.arange(len(d_orc)), size=len(d_orc), replace=False)
+    assert np.array_equal(d_orc[perm], d_ref)                       # same samples, same permutation for the same seed
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((4000, 3)) * 100
+    b = a[:2500] + rng.standard_normal((2500, 3))
+    assert evu.average_squared_distance(a, b) == orc.average_squared_distance(a, b)
+    cand = np.arange(len(m._faces), dtype=np.int32)
+    assert np.array_equal(refharness.reference_holepunch_pairs(m, cand), orc.holepunch_pairs(m, cand))

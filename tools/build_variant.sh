@@ -8,6 +8,7 @@ mkdir -p build/var_$1
 for f in sweep tree api; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr $2 -c csrc/$f.cu -o build/var_$1/$f.cu.o &
 done
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -fmad=false $2 -c csrc/curvature.cu -o build/var_$1/curvature.cu.o &
 wait
 objs=""
 for o in build/*.cu.o; do b=$(basename $o); if [ -f build/var_$1/$b ]; then objs="$objs build/var_$1/$b"; else objs="$objs $o"; fi; done
