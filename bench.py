@@ -34,6 +34,8 @@ WORKLOADS = {
     'c2': dict(points=1_000_000, geo=71, curvature_weight=10.0, block=5, desc='config1: 1M localisations, 50 412-vertex mesh'),
     'c3': dict(points=10_000_000, geo=224, curvature_weight=10.0, block=5, desc='config2: 10M localisations, 501 762-vertex two-lobed mesh'),
     'c4': dict(points=12_500_000, geo=316, curvature_weight=10.0, block=5, desc='config3: 100M localisations over 8 GPUs (12.5M per GPU), 998 562-vertex replicated mesh'),
+    'c4s': dict(points=100_000_000, geo=316, curvature_weight=10.0, block=5, strong=True,
+                desc='config3 as BASELINE states it: 100M localisations IN TOTAL sharded over the ranks (strong scaling), 998 562-vertex replicated mesh'),
     'c5': dict(points=2_000_000, geo=632, curvature_weight=50.0, block=5, desc='config4: curvature stress, 3 994 242-vertex mesh, sparse 2M-localisation cloud'),
 }
 CPU_SAMPLE = 'c2'         # bounded CPU sample of the cpu_baseline leg: same shape, same 20 localisations per vertex, 1/10 of c3
@@ -41,19 +43,30 @@ STAGES = ['refit', 'shift', 'sweep1', 'allreduce_acc', 'mesh_prior', 'sweep2', '
           'topology_build']
 
 
-def build_workload(name, seed, points=None):
+def build_workload(name, seed, points=None, rank=0, world=1):
     """(mesh, points, sigma, cfg) of a BASELINE config; `points` overrides the number of localisations (parity tests draw a
     subset-sized cloud over the full-size mesh)."""
     from ch_shrinkwrap_b200 import minimesh, synth
     from ch_shrinkwrap_b200.membrane_mesh import MembraneMesh
     cfg = dict(WORKLOADS[name])
+    cfg['rank'], cfg['world'] = rank, world
     if points is not None:
         cfg['points'] = int(points)
     shape = synth.two_lobed()
     v, f = minimesh.geodesic_sphere(cfg['geo'])
     v, f = minimesh.spatially_sorted(v, f)       # arbitrary generator order -> spatially coherent vertex / face order
     r = synth.radial_surface(shape, v, n_bisect=32)
-    pts, sig = synth.mesh_surface_cloud(v * r[:, None], f, cfg['points'], seed=seed)
+    if cfg.get('strong'):
+        # strong scaling: the SAME global cloud whatever the number of ranks -- 8 seeded chunks, rank r of N holds chunks
+        # [8 r / N, 8 (r + 1) / N).  Every chunk covers the whole surface, so every rank sees the same mix of queries.
+        rank, world = cfg.get('rank', 0), cfg.get('world', 1)
+        assert 8 % world == 0, 'strong-scaling workload needs 1, 2, 4 or 8 ranks'
+        per = cfg['points'] // 8
+        parts = [synth.mesh_surface_cloud(v * r[:, None], f, per, seed=seed + 1000 * c) for c in range(8 * rank // world, 8 * (rank + 1) // world)]
+        pts = np.concatenate([p for p, _ in parts]); sig = np.concatenate([q for _, q in parts])
+        del parts
+    else:
+        pts, sig = synth.mesh_surface_cloud(v * r[:, None], f, cfg['points'], seed=seed)
     mesh = MembraneMesh(v * (1.2 * r)[:, None], f, kc=1.0, step_size=cfg['curvature_weight'],
                         remesh_frequency=cfg['block'], delaunay_remesh_frequency=0)
     return mesh, pts, sig, cfg
@@ -256,7 +269,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    mesh, pts, sig, cfg = build_workload(args.workload, args.seed + 1000 * rank)
+    strong = bool(WORKLOADS[args.workload].get('strong'))
+    mesh, pts, sig, cfg = build_workload(args.workload, args.seed if strong else args.seed + 1000 * rank, rank=rank, world=world)
     mesh._nw_device = local_rank
     mesh._nw_comm = comm
     s_inv = (1.0 / sig.ravel()).astype(np.float32)
@@ -397,9 +411,9 @@ def main():
                'curvature': cpu_curvature_run(mesh)}      # the bench mesh itself (full size), one host core
     line = {
         'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': dev_ms / K,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
         'dtype': 'f32 (fp64 nearest-face compare and Gram sums, int64 fixed-point adjoint)', 'data': 'synthetic',
-        'config': {'workload': cfg['desc'] + ' per GPU', 'points_per_gpu': P, 'vertices': M, 'faces': F, 'lam': lam,
+        'config': {'workload': cfg['desc'] + ('' if strong else ' per GPU'), 'points_per_gpu': P, 'points_total': P * world, 'vertices': M, 'faces': F, 'lam': lam,
                    'block_iterations': block, 'parallelism': 'points sharded x%d, mesh replicated' % world,
                    'l2': 'inputs larger than L2: per-point streams %.0f MB vs 126 MB L2' % (52.0 * P / 1e6)},
         'cg_iters_per_s': K / (dev_ms * 1e-3),

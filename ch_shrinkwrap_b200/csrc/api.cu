@@ -54,7 +54,7 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free((char **)&h->cub_tmp); nw_free(&h->scratchM); nw_free(&h->scratchP);
     nw_free((char **)&h->cvV); nw_free((char **)&h->cvF); nw_free((char **)&h->cvH); nw_free(&h->cvOut); nw_free(&h->cvJ); nw_free(&h->cvOff);
     nw_free(&h->sp_pts); nw_free(&h->sp_k0); nw_free(&h->sp_k1); nw_free(&h->sp_idx); nw_free(&h->sp_tmp3);
-    nw_free(&h->blk_order); nw_free(&h->blk_idx); nw_free(&h->blk_key); nw_free(&h->blk_key2);
+    nw_free(&h->blk_order); nw_free(&h->blk_order_cold); nw_free(&h->blk_idx); nw_free(&h->blk_key); nw_free(&h->blk_key2);
     nw_uploader_destroy(h);
     if (h->pin_host) cudaFreeHost(h->pin_host);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -220,9 +220,12 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
         if (num_iters > 0) { NW_CHECK(enqueue_iteration(h, 0, last_step)); it = 1; }
         // every further iteration is the same ~15 launches with the same arguments: capture one, replay it.  For small
         // fits the iteration is launch-bound (C1: 0.25 ms of launches around microseconds of work).  Not under profiling
-        // (per-stage events) and not with a communicator (the collectives stay eager).
+        // (per-stage events).  With a communicator the two ncclAllReduce calls of the iteration are captured with it
+        // (NCCL supports stream capture; the eager first iteration has already run both collectives once, so nothing is
+        // allocated or connected inside the capture); NW_NO_COMM_GRAPH=1 keeps multi-rank runs eager.
         static const bool no_graph = getenv("NW_NO_GRAPH") != nullptr;
-        if (!no_graph && !h->profile && h->nranks == 1 && num_iters - it >= 2) {
+        static const bool no_comm_graph = getenv("NW_NO_COMM_GRAPH") != nullptr;
+        if (!no_graph && !h->profile && (h->nranks == 1 || !no_comm_graph) && num_iters - it >= 2) {
             const int64_t l0 = h->launches;
             bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             int rc = NW_OK;

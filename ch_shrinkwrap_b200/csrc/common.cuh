@@ -156,6 +156,8 @@ struct nw_ctx {
     char *pin_host = nullptr; size_t pin_bytes = 0; bool pin_fresh = false;   // pinned read-back staging (nw_get_positions_strided)
     // k_sweep1 block schedule: blocks in descending order of their largest seed distance (sweep.cu: build_block_order)
     int *blk_order = nullptr, *blk_idx = nullptr; unsigned *blk_key = nullptr, *blk_key2 = nullptr; bool order_stale = true;
+    int *blk_order_cold = nullptr; int cold_grid = 0;   // schedule of the first sweep of a fit: its costliest blocks run as quarter-packets
+    bool leaders_fresh = false;                  // the seeds are the 1-in-32 root searches of a cold start, nothing has swept yet
     struct nw_uploader *uploader = nullptr;       // xfer.cu: pinned staging lanes for large host->device copies
     cudaEvent_t ev_seg0 = nullptr, ev_seg1 = nullptr;   // topology_build segments (profiling only)
     double last_search_ms = 0.0;

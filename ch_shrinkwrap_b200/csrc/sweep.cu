@@ -259,7 +259,13 @@ struct Traversal {
 #endif
             if (pass) {
                 if (node >= tv.leaf0) leaf(node);
-                else { node = link & 0x7fffffff; continue; }
+                else {
+                    node = link & 0x7fffffff;
+                    // (measured at C3 and rejected: an L1 prefetch of all children here, CCTL.PF1 by lanes 0..7 -- the warm
+                    // sweep went from 2.17 to 2.53 ms and the first sweep of a fit, whose longest packet runs 16 k steps at
+                    // ~1000 cycles each while the average SM is done after 60 % of the launch, did not get shorter)
+                    continue;
+                }
             }
             while (true) {
                 if (node == I) return;
@@ -386,9 +392,12 @@ struct Sweep1Args {
 #ifndef NW_FN_INLINE
 #define NW_FN_INLINE __noinline__
 #endif
+#ifndef NW_S1_MINB
+#define NW_S1_MINB 16     // blocks of 128 per SM for the search kernels: 32 registers, 64 warps per SM (see k_sweep1)
+#endif
 template <bool F64, bool STATS, bool T64>
 __device__ NW_FN_INLINE Nearest find_nearest(const Sweep1Args &a, int64_t i, bool active, float x, float y, float z,
-                                             double xd, double yd, double zd, Nearest best) {
+                                             double xd, double yd, double zd, Nearest best, int block_seed = -1) {
     const float eps = (fabsf(x) + fabsf(y) + fabsf(z) + a.st->coord_l1) * 9.5367431640625e-7f;   // 2^-20 * L1 magnitude
     typename std::conditional<F64, QueryF64, QueryF32>::type q;
     if constexpr (F64) q.set(xd, yd, zd);
@@ -406,6 +415,7 @@ __device__ NW_FN_INLINE Nearest find_nearest(const Sweep1Args &a, int64_t i, boo
         const unsigned warm = __ballot_sync(0xffffffffu, active && seed >= 0);
         int start;
         if (warm) start = __shfl_sync(0xffffffffu, seed, __ffs(warm) - 1);
+        else if (block_seed >= 0) start = block_seed;        // cold start: the block's first point carries the root search's result
         else {
             tr.lead = __ffs(alive) - 1;
             start = __ldg(&a.tv.kids[tr.greedy_leaf()]).x;
@@ -445,9 +455,13 @@ __device__ NW_FN_INLINE Nearest find_nearest(const Sweep1Args &a, int64_t i, boo
 // face from a root search that stops refining after a fixed number of node tests (a seed only has to be close, the
 // exact search happens in k_sweep1; bounding the effort removes the long tail of near-equidistant queries).
 template <bool F64>
-__global__ void __launch_bounds__(128) k_seed_leaders(const __grid_constant__ Sweep1Args a) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t i = t * 32;
+__global__ void __launch_bounds__(128) k_seed_leaders(const __grid_constant__ Sweep1Args a, int stride, unsigned budget) {
+    // ONE search per warp, on lane 0: 32 private walks in one warp diverge at every node, and a diverged warp pays the L2
+    // latency of every lane's node in turn (measured at C3: 2.5 ms for 78 k searches, one warp's serial chain); with one
+    // search per warp the latency is hidden by the other 63 warps of the SM
+    if (threadIdx.x & 31) return;
+    const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t i = t * stride;
     if (i >= a.P || a.slot[i] >= 0) return;
     Nearest best;
     best.d2 = DBL_MAX * 2.0; best.ub = FLT_MAX * 2.0f; best.slot = -1; best.face = 0x7fffffff;
@@ -457,7 +471,7 @@ __global__ void __launch_bounds__(128) k_seed_leaders(const __grid_constant__ Sw
     if constexpr (F64) q.set(a.px64[i], a.py64[i], a.pz64[i]);
     else { q.x = x; q.y = y; q.z = z; }
     Traversal<decltype(q)> tr(q, best, a.tv, eps, a.st->cell_escape);
-    tr.budget = 512;
+    tr.budget = budget;
     tr.top_down();
     a.slot[i] = tr.best.slot;     // >= 0: the first descent always reaches a leaf before the budget can run out
 }
@@ -523,15 +537,19 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
 }
 
 // MODE 0: nearest face + weights only (what calc_w triggers);  MODE 1: + residual + adjoint scatter
-#ifndef NW_S1_MINB
-#define NW_S1_MINB 16     // 32 registers, 64 warps per SM.  Measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 before the global-id tables; after them 48 regs 2.47, 40 regs 2.51, 32 regs 2.33 -- the packet walk is a dependent chain, occupancy hides it
-#endif
+// 32 registers, 64 warps per SM (NW_S1_MINB = 16).  Measured at C3 (warm sweep, ms): 56 regs 3.23, 48 regs 3.08, 40 regs 3.00 before the
+// global-id tables; after them 48 regs 2.47, 40 regs 2.51, 32 regs 2.33 -- the packet walk is a dependent chain, occupancy hides it
 template <bool F64, int MODE, bool STATS, bool T64 = false>
 __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB) : NW_S1_MINB) k_sweep1(const __grid_constant__ Sweep1Args a) {
     if (MODE == 1 && a.st->stop) return;
 
-    const int64_t i = (a.order ? __ldg(&a.order[blockIdx.x]) : (int)blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
-    const bool active = i < a.P;
+    // schedule entry: block of points | quarter << 28.  quarter 0: all 32 lanes of every warp are points; 1..4: only lanes
+    // [8 (quarter - 1), 8 quarter) are, the other 24 idle (k_cold_order); negative: nothing to do
+    const int entry = a.order ? __ldg(&a.order[blockIdx.x]) : (int)blockIdx.x;
+    if (entry < 0) return;
+    const int quarter = entry >> 28;
+    const int64_t i = (entry & 0x0fffffff) * (int64_t)blockDim.x + threadIdx.x;
+    const bool active = i < a.P && (quarter == 0 || (int)((threadIdx.x >> 3) & 3u) == quarter - 1);
     float x = 0.f, y = 0.f, z = 0.f;
     double xd = 0.0, yd = 0.0, zd = 0.0;
     if (active) {
@@ -544,7 +562,11 @@ __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB)
     best.ub = FLT_MAX * 2.0f;
     best.slot = -1;
     best.face = 0x7fffffff;
-    best = find_nearest<F64, STATS, T64>(a, i, active, x, y, z, xd, yd, zd, best);
+    // cold start: only the first point of every block of 128 was searched from the root (k_seed_leaders); the warps that
+    // do not hold it climb from its face too (it may already have been replaced by that point's final answer: just as good)
+    const int64_t i0 = (entry & 0x0fffffff) * (int64_t)blockDim.x;
+    const int block_seed = i0 < a.P ? a.slot[i0] : -1;
+    best = find_nearest<F64, STATS, T64>(a, i, active, x, y, z, xd, yd, zd, best, block_seed);
     if (active && best.slot < 0) {      // non-finite query: nothing compares; flag it (the reference asserts on NaN) and stay in bounds
         a.st->nan_flag = 1;
         best.slot = 0;
@@ -897,11 +919,18 @@ int nw_launch_seed_leaders(nw_ctx *h) {
         h->seeds_cold = false;
         return NW_OK;
     }
-    const int GL = nw_grid((h->P + 31) / 32, B);
-    if (h->px64) k_seed_leaders<true><<<GL, B, 0, h->stream>>>(a);
-    else k_seed_leaders<false><<<GL, B, 0, h->stream>>>(a);
+    // (measured at C3 and rejected: root searches for one point in 1024 only, then the exact packet search for every 32nd
+    // point seeded by them -- the sweep gains 0.8 ms from exact seeds, but packets of points that lie 32 apart cost 6 ms)
+    // one bounded root search per block of k_sweep1 (128 points, Hilbert neighbours): measured at C3, seeds + first sweep in
+    // ms -- every 32nd point, budget 512: 3.4 + 5.6; 256: 2.5 + 5.7; 128: 1.8 + 6.3; 64: 0.9 + 42 (seeds too poor)
+    static const unsigned budget = getenv("NW_SEED_BUDGET") ? (unsigned)atoi(getenv("NW_SEED_BUDGET")) : 256u;
+    static const int stride = getenv("NW_SEED_STRIDE") ? std::max(32, atoi(getenv("NW_SEED_STRIDE")) / 32 * 32) : 128;
+    const int GL = nw_grid(((h->P + stride - 1) / stride) * 32, B);
+    if (h->px64) k_seed_leaders<true><<<GL, B, 0, h->stream>>>(a, stride, budget);
+    else k_seed_leaders<false><<<GL, B, 0, h->stream>>>(a, stride, budget);
     NW_LAUNCH_CHECK();
     h->seeds_cold = false;
+    h->leaders_fresh = true;
     return NW_OK;
 }
 
@@ -932,6 +961,21 @@ __global__ void __launch_bounds__(128) k_block_cost(int64_t P, const float *__re
     if (threadIdx.x == 0) { key[blockIdx.x] = max(max(sh[0], sh[1]), max(sh[2], sh[3])); idx[blockIdx.x] = blockIdx.x; }
 }
 
+// Schedule of the FIRST sweep of a fit.  There the seeds are borrowed (one root search per 32 points), and a packet of
+// background localisations deep inside the object -- 32 queries, each nearly equidistant to a large piece of the surface
+// in a different direction -- walks the union of 32 huge candidate sets: measured at C3, one such packet ran 16 k steps
+// (16.7 M cycles) while the average SM was busy for 9.9 M.  The costliest blocks are therefore split FOUR ways: each of the
+// four entries runs the same 128 points with only 8 of every 32 lanes active, so a packet covers 8 queries, its walk
+// shrinks accordingly and four times as many warps share the work.  Every point is still searched exactly once, by the
+// same exact search.  Layout: 4 entries for each of the first `n_far` blocks of the longest-first order, then the rest.
+__global__ void k_cold_order(const int *__restrict__ order, int G, int n_far, int *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= G) return;
+    const int b = order[k];
+    if (k < n_far) { for (int q = 0; q < 4; ++q) out[4 * k + q] = b | ((q + 1) << 28); }
+    else out[4 * n_far + (k - n_far)] = b;
+}
+
 static int build_block_order(nw_ctx *h, int G) {
     NW_CHECK(nw_alloc(h, &h->blk_key, (size_t)G)); NW_CHECK(nw_alloc(h, &h->blk_key2, (size_t)G));
     NW_CHECK(nw_alloc(h, &h->blk_idx, (size_t)G)); NW_CHECK(nw_alloc(h, &h->blk_order, (size_t)G));
@@ -943,6 +987,19 @@ static int build_block_order(nw_ctx *h, int G) {
     NW_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->cub_tmp, tmp, h->blk_key, h->blk_key2, h->blk_idx, h->blk_order, G, 0, 32, h->stream));
     h->launches += 2;
     h->order_stale = false;
+    h->cold_grid = 0;
+    static const bool no_split = getenv("NW_NO_COLD_SPLIT") != nullptr;           // A/B switch for measurements
+    if (h->leaders_fresh && !no_split && G >= 64 && G < (1 << 26)) {
+        // how many: measured at C3 (78 k blocks), first sweep in ms for the costliest 1/4 .. 1/1024 of the blocks split --
+        // 11.6, 8.8, 7.1, 6.5, 6.0, 5.8, 5.7, 5.6, 5.5 (9.5 unsplit): the pathological packets are a handful, and every
+        // other block that is split pays for 24 idle lanes per warp
+        static const int far_div = getenv("NW_COLD_FAR_DIV") ? std::max(1, atoi(getenv("NW_COLD_FAR_DIV"))) : 512;
+        const int n_far = std::min(G, std::max(32, G / far_div));
+        NW_CHECK(nw_alloc(h, &h->blk_order_cold, (size_t)G + 3 * (size_t)n_far));
+        k_cold_order<<<nw_grid(G, 256), 256, 0, h->stream>>>(h->blk_order, G, n_far, h->blk_order_cold);
+        NW_LAUNCH_CHECK();
+        h->cold_grid = G + 3 * n_far;
+    }
     return NW_OK;
 }
 
@@ -955,6 +1012,9 @@ int nw_launch_sweep1(nw_ctx *h, bool scatter) {
     if (h->order_stale && !no_order) NW_CHECK(build_block_order(h, G));
     Sweep1Args a = make_args(h);
     a.order = no_order ? nullptr : h->blk_order;
+    int G1 = G;
+    if (h->leaders_fresh && h->cold_grid > 0 && !no_order) { a.order = h->blk_order_cold; G1 = h->cold_grid; }
+    h->leaders_fresh = false;                       // only the very first sweep after the root searches is scheduled this way
     // traversal statistics (nw_get_traversal_stats) are collected only when asked for: nw_set_profile(h, 3)
 #ifdef NW_LEVEL_STATS
     const bool stats = true;
@@ -964,13 +1024,13 @@ int nw_launch_sweep1(nw_ctx *h, bool scatter) {
     if (a.tv.cent64) {
         // points mode with float64 targets (nw_set_point_targets): only the nearest-target query exists, no statistics
         NW_ARG(!scatter, "sweep1: float64 point targets support nearest-point queries only");
-        if (h->px64) k_sweep1<true, 0, false, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false, true><<<G, B, 0, h->stream>>>(a);
+        if (h->px64) k_sweep1<true, 0, false, true><<<G1, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false, true><<<G1, B, 0, h->stream>>>(a);
     } else if (h->px64) {
-        if (stats) { if (scatter) k_sweep1<true, 1, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, true><<<G, B, 0, h->stream>>>(a); }
-        else { if (scatter) k_sweep1<true, 1, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<true, 0, false><<<G, B, 0, h->stream>>>(a); }
+        if (stats) { if (scatter) k_sweep1<true, 1, true><<<G1, B, 0, h->stream>>>(a); else k_sweep1<true, 0, true><<<G1, B, 0, h->stream>>>(a); }
+        else { if (scatter) k_sweep1<true, 1, false><<<G1, B, 0, h->stream>>>(a); else k_sweep1<true, 0, false><<<G1, B, 0, h->stream>>>(a); }
     } else {
-        if (stats) { if (scatter) k_sweep1<false, 1, true><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, true><<<G, B, 0, h->stream>>>(a); }
-        else { if (scatter) k_sweep1<false, 1, false><<<G, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false><<<G, B, 0, h->stream>>>(a); }
+        if (stats) { if (scatter) k_sweep1<false, 1, true><<<G1, B, 0, h->stream>>>(a); else k_sweep1<false, 0, true><<<G1, B, 0, h->stream>>>(a); }
+        else { if (scatter) k_sweep1<false, 1, false><<<G1, B, 0, h->stream>>>(a); else k_sweep1<false, 0, false><<<G1, B, 0, h->stream>>>(a); }
     }
     NW_LAUNCH_CHECK();
     return NW_OK;
