@@ -31,6 +31,7 @@ SIGNATURES = {
     'nw_get_positions': (c_int, [c_void_p, _f]),
     'nw_get_positions_strided': (c_int, [c_void_p, c_void_p, c_int, c_int]),
     'nw_search': (c_int, [c_void_p, c_float, c_int, c_int, _d, c_int, _f, _d, _d, _d, _d, _d, POINTER(c_int)]),
+    'nw_set_regulariser': (c_int, [c_void_p, c_int]),
     'nw_compute_weights': (c_int, [c_void_p]),
     'nw_get_weights': (c_int, [c_void_p, _i, _f, _d, _i]),
     'nw_apply_A': (c_int, [c_void_p, _f, _f]),

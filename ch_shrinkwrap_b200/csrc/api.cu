@@ -199,6 +199,7 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     SolverState s;
     memset(&s, 0, sizeof(s));
     s.lam = lam;
+    s.reg_mode = h->reg_mode;
     s.n_search = 2;
     int np = n_prev > 3 ? 3 : n_prev;
     for (int k = 0; k < np; ++k) s.last_tests[k] = prev_tests[n_prev - np + k];
@@ -281,6 +282,16 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     if (pos_out) NW_CHECK(nw_get_positions(h, pos_out));
     if (r.nan_flag == 2) { h->err = "nw_search: singular subspace matrix (numpy.linalg.LinAlgError in the reference)"; return NW_ERR_NAN; }
     if (r.nan_flag) { h->err = "nw_search: non-finite value in residual / search directions / update"; return NW_ERR_NAN; }
+    return NW_OK;
+}
+
+// Which operator regularises the fit: L = LH = "I" (0; the reference's setting, mesh_conj_grad.py:38) or "wfunc" (1; :39,
+// :725-736: the prior residual weighted by 1/sqrt(sum of squared edge lengths + 1) of the current mesh).  These are the two
+// settings of Lfuncs / Lhfuncs the reference's search() can actually run with.
+extern "C" int nw_set_regulariser(nw_ctx *h, int mode) {
+    if (!h) return NW_ERR_ARG;
+    NW_ARG(mode == 0 || mode == 1, "nw_set_regulariser: mode must be 0 (I) or 1 (wfunc)");
+    h->reg_mode = mode;
     return NW_OK;
 }
 

@@ -53,6 +53,8 @@ struct SolverState {
     int stop;                     // stop rule fired: remaining kernels become no-ops
     int nan_flag;
     int n_search;                 // 2 on the first iteration of a call, 3 afterwards (last_step)
+    int reg_mode;                 // regulariser L = LH: 0 = "I" (the reference's default, mesh_conj_grad.py:38), 1 = "wfunc" (:725-736)
+    double tst[3], prefs32_2, prefs64_2;   // S0.S1, |S0|^2, |S1|^2 (test statistic); |prefs|^2 as float32 values / as float64 values
     int acc_shift;                // fixed-point fraction bits of the adjoint accumulators
     int infl_shift;               // ditto for the AH*1 accumulator
     int bbox[6];                  // ordered-int bounding box of the vertices (k_shift_partial -> k_shift_final)
@@ -80,6 +82,7 @@ struct nw_ctx {
     float *sx = nullptr, *sy = nullptr, *sz = nullptr;           // sigma_inv (NULL -> scalar)
     float *wx = nullptr, *wy = nullptr, *wz = nullptr;           // weights when distinct from sigma_inv
     float sinv_scalar = 1.f;
+    int reg_mode = 0;            // nw_set_regulariser
     int weights_mode = 0;        // 0: scalar weight = sinv_scalar; 1: weights = sigma_inv array; 2: own array
     float wmean = 1.f;           // mean of the weight array over all ranks (float32 like numpy)
     int has_mask = 0;            // some weight <= 0

@@ -67,7 +67,7 @@ __global__ void k_shift_final(float plo_x, float plo_y, float plo_z, float phi_x
     st->infl_shift = 61 - e;
 }
 
-#define NW_MSUM 9   // hw00 hw01 hw11 hw02 hw12 hw22 gw0 gw1 gw2
+#define NW_MSUM 14  // hw00 hw01 hw11 hw02 hw12 hw22 gw0 gw1 gw2 | s0.s1 s0.s0 s1.s1 | sum prefs32^2 | sum prefs64^2
 
 template <bool WRITE_DIRS>
 __global__ void __launch_bounds__(256, 3) k_mesh_prior(int M, unsigned long long *__restrict__ acc, SolverState *__restrict__ st,
@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256, 3) k_mesh_prior(int M, unsigned long long
         // ---- ncc: mesh_conj_grad.py:777-818 --------------------------------------------------------
         const float4 p = posq[v], N = nrmq[v];
         const int ms = valence[v];
+        const bool reg = st->reg_mode == 1;
+        float ring2 = 0.f;
         double fx = p.x, fy = p.y, fz = p.z;     // ms == 0 -> f_def = vertex (:818)
         if (ms > 0) {
             int nb[NW_NEIGHBORSIZE];
@@ -110,6 +112,12 @@ __global__ void __launch_bounds__(256, 3) k_mesh_prior(int M, unsigned long long
                 if (k < ms) {
                     const float4 q = __ldg(&posq[nb[k]]);
                     cx = __fadd_rn(cx, q.x); cy = __fadd_rn(cy, q.y); cz = __fadd_rn(cz, q.z);   // float32 sum (:782)
+                    if (reg) {          // vertex_area_weights on the current f (conj_grad_utils.c:500-528): sum of squared edge lengths
+                        float dd = __fsub_rn(q.x, p.x), d2 = __fmul_rn(dd, dd);
+                        dd = __fsub_rn(q.y, p.y); d2 = __fadd_rn(d2, __fmul_rn(dd, dd));
+                        dd = __fsub_rn(q.z, p.z); d2 = __fadd_rn(d2, __fmul_rn(dd, dd));
+                        ring2 = __fadd_rn(ring2, d2);
+                    }
                 }
             }
             const double dms = (double)ms;
@@ -146,21 +154,36 @@ __global__ void __launch_bounds__(256, 3) k_mesh_prior(int M, unsigned long long
         }
         if (fdef_out) { fdef_out[3 * (size_t)v] = fx; fdef_out[3 * (size_t)v + 1] = fy; fdef_out[3 * (size_t)v + 2] = fz; }
         if (WRITE_DIRS) {
-            // prefs = f - f_def (float64 in subsearch, float32 in search); S1 = -prefs
-            const double px64 = (double)p.x - fx, py64 = (double)p.y - fy, pz64 = (double)p.z - fz;
-            const float s1x = -(float)px64, s1y = -(float)py64, s1z = -(float)pz64;
+            // prefs = L(f - f_def) (float64 in subsearch, float32 in search); S1 = -LH(prefs); LS_k = L(S_k)
+            //   L = "I"     (mesh_conj_grad.py:38):     prefs = f - f_def,        S1 = -prefs32,        LS_k = S_k
+            //   L = "wfunc" (:725-736, w = area weight): prefs = (f - f_def) w,    S1 = -(prefs32 w),    LS_k = S_k w
+            // (the other 1-ring operators cannot be the regulariser of a fit in the reference either: search() hands them
+            // the float64 array f - f_def and the C helpers read it as float32, conj_grad_utils.c:283 -- they raise
+            // AssertionError on the NaNs that produces)
+            float wv = 1.0f;
+            if (reg) wv = (ms > 0 && ring2 > 0.f) ? (float)(1.0 / (double)__fsqrt_rn(__fadd_rn(ring2, 1.0f))) : 0.f;   // conj_grad_utils.c:530-540
+            double pr[3] = {(double)p.x - fx, (double)p.y - fy, (double)p.z - fz};
+            if (reg) { pr[0] = __dmul_rn(pr[0], (double)wv); pr[1] = __dmul_rn(pr[1], (double)wv); pr[2] = __dmul_rn(pr[2], (double)wv); }
+            const float p32[3] = {(float)pr[0], (float)pr[1], (float)pr[2]};
+            float s1x = -p32[0], s1y = -p32[1], s1z = -p32[2];
+            if (reg) { s1x = -__fmul_rn(p32[0], wv); s1y = -__fmul_rn(p32[1], wv); s1z = -__fmul_rn(p32[2], wv); }
             Sq[3 * (size_t)v] = make_float4(s0x, s0y, s0z, 0.f);
             Sq[3 * (size_t)v + 1] = make_float4(s1x, s1y, s1z, 0.f);
             if (!(fabsf(s0x) <= FLT_MAX && fabsf(s0y) <= FLT_MAX && fabsf(s0z) <= FLT_MAX &&
                   fabsf(s1x) <= FLT_MAX && fabsf(s1y) <= FLT_MAX && fabsf(s1z) <= FLT_MAX)) st->nan_flag = 1;
             const float4 s2 = Sq[3 * (size_t)v + 2];
-            const double a0[3] = {s0x, s0y, s0z}, a1[3] = {s1x, s1y, s1z}, a2[3] = {s2.x, s2.y, s2.z};
-            const double pr[3] = {px64, py64, pz64};
+            const float S0[3] = {s0x, s0y, s0z}, S1[3] = {s1x, s1y, s1z}, S2[3] = {s2.x, s2.y, s2.z};
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                sums[0] += a0[c] * a0[c]; sums[1] += a0[c] * a1[c]; sums[2] += a1[c] * a1[c];
-                sums[3] += a0[c] * a2[c]; sums[4] += a1[c] * a2[c]; sums[5] += a2[c] * a2[c];
-                sums[6] -= a0[c] * pr[c]; sums[7] -= a1[c] * pr[c]; sums[8] -= a2[c] * pr[c];
+                // LS_k: float32 products like wfunc's f * w
+                const double a0 = reg ? (double)__fmul_rn(S0[c], wv) : (double)S0[c], a1 = reg ? (double)__fmul_rn(S1[c], wv) : (double)S1[c],
+                             a2 = reg ? (double)__fmul_rn(S2[c], wv) : (double)S2[c];
+                sums[0] += a0 * a0; sums[1] += a0 * a1; sums[2] += a1 * a1;
+                sums[3] += a0 * a2; sums[4] += a1 * a2; sums[5] += a2 * a2;
+                sums[6] -= a0 * pr[c]; sums[7] -= a1 * pr[c]; sums[8] -= a2 * pr[c];
+                sums[9] += (double)S0[c] * (double)S1[c]; sums[10] += (double)S0[c] * (double)S0[c]; sums[11] += (double)S1[c] * (double)S1[c];
+                sums[12] += (double)p32[c] * (double)p32[c];
+                sums[13] += pr[c] * pr[c];
             }
         }
     }
@@ -204,6 +227,8 @@ __global__ void k_solve(const double *__restrict__ mesh_partials, int n_mesh_blo
                                       // it here leaves the launch without per-iteration arguments, so it can be replayed from a graph
     for (int k = 0; k < 6; ++k) st->hw[k] = red[k];
     for (int k = 0; k < 3; ++k) st->gw[k] = red[6 + k];
+    for (int k = 0; k < 3; ++k) st->tst[k] = red[9 + k];
+    st->prefs32_2 = red[12]; st->prefs64_2 = red[13];
     const int n = st->n_search;
     const double l2 = (double)st->lam * (double)st->lam;
     // symmetric index map (i<=j): 00->0 01->1 11->2 02->3 12->4 22->5
@@ -244,19 +269,19 @@ __global__ void k_solve(const double *__restrict__ mesh_partials, int n_mesh_blo
         cGc += c[i] * (st->gc[i] + l2 * st->gw[i]);
         cGw += c[i] * st->gw[i];
     }
-    const double prefs2 = Hw[1][1];   // |prefs|^2 == |S1|^2
+    const double prefs2 = st->prefs32_2;   // |prefs|^2 of the float32 prefs array (history, mesh_conj_grad.py:271)
     // mesh_conj_grad.py:262-265.  The reference forms the ratio from float32 sums and subtracts it from 1 in float32, so
     // its statistic moves in steps of 2^-24 near convergence, and the stop rule ("strictly decreasing three times",
     // :1009-1016) sees those steps.  Here the ratio comes from float64 sums (more accurate than the reference's own) and
     // is rounded to float32 ONCE, then subtracted in float32: the history and the rule work on the same kind of number as
     // the reference's, and what the caller gets back (float32 in self.tests) is exactly what the device compared.
-    const float ratio32 = (float)fabs(Hw[0][1] / (sqrt(Hw[0][0]) * sqrt(Hw[1][1])));
+    const float ratio32 = (float)fabs(st->tst[0] / (sqrt(st->tst[1]) * sqrt(st->tst[2])));
     const double test = (double)(1.0f - ratio32);
     hist[0 * NW_MAX_ITERS + iter_index] = test;
     hist[1 * NW_MAX_ITERS + iter_index] = sqrt(st->res2);
     hist[2 * NW_MAX_ITERS + iter_index] = sqrt(prefs2);
     hist[3 * NW_MAX_ITERS + iter_index] = st->c0 + cHc - cGc;
-    hist[4 * NW_MAX_ITERS + iter_index] = prefs2 + cHwc - cGw;
+    hist[4 * NW_MAX_ITERS + iter_index] = st->prefs64_2 + cHwc - cGw;      // wpreds[0], conj_grad.py:192,224
     // histories for the stop rule (:1009-1016): evaluated at the top of the NEXT iteration
     if (st->n_tests < 3) st->last_tests[st->n_tests++] = test;
     else { st->last_tests[0] = st->last_tests[1]; st->last_tests[1] = st->last_tests[2]; st->last_tests[2] = test; }

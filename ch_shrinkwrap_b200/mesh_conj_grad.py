@@ -238,6 +238,15 @@ class ShrinkwrapMeshConjGrad(object):
         if data is not self._points:
             if np.shape(data) != np.shape(self._points) or not np.array_equal(data, self._points):
                 self._points = data
+        # the regulariser is read from the object like the reference does (mesh_conj_grad.py:36-39,257-258)
+        reg = (list(self.Lfuncs), list(self.Lhfuncs))
+        if reg == (["I"], ["I"]):
+            reg_mode = 0
+        elif reg == (["wfunc"], ["wfunc"]):
+            reg_mode = 1
+        else:
+            raise NotImplementedError('Lfuncs/Lhfuncs = %r: the reference\'s search() runs with ["I"] or ["wfunc"] only (its other '
+                                      '1-ring operators receive a float64 array they read as float32 and fail its NaN assert)' % (reg,))
         self._sigma_inv, self._weights = sigma_inv, weights
         self._mask_src = (sigma_inv if weights is None else weights, data)   # mask is built lazily (3P bools)
         self._positions_fresh = False
@@ -255,6 +264,7 @@ class ShrinkwrapMeshConjGrad(object):
         prev = np.asarray(self.tests[-3:], dtype=np.float64)
         n_done = ctypes.c_int(0)
         lam = float(lams[0]) if len(lams) > 0 else 0.0
+        self._h.call('nw_set_regulariser', reg_mode)
         self._h.call('nw_search', lam, n, int(bool(last_step)), _lib.dptr(prev) if len(prev) else None, int(len(prev)),
                      _lib.fptr(out), *[_lib.dptr(a) for a in hist], ctypes.byref(n_done))
         k = n_done.value

@@ -100,6 +100,12 @@ int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, const double *
               int n_prev, float *pos_out, double *tests, double *ress, double *prefs,
               double *cpred, double *wpred, int *n_done);
 
+/* Regulariser of the next nw_search calls: the reference reads Lfuncs / Lhfuncs from the solver object
+ * (mesh_conj_grad.py:36-39,257-258; conj_grad.py:191-200).  mode 0 = ["I"], ["I"] (its setting); mode 1 = ["wfunc"],
+ * ["wfunc"] (:39, :725-736).  The remaining 1-ring operators below cannot regularise a fit in the reference either (its
+ * search() passes them a float64 array that the C helpers read as float32), so they stay stand-alone operators. */
+int nw_set_regulariser(nw_ctx *h, int mode);
+
 /* ---- operators (the reference's public methods on the solver object) --------------------------- */
 /* nearest face + weights at the current f: _compute_weight_matrix4, mesh_conj_grad.py:433-516 */
 int nw_compute_weights(nw_ctx *h);

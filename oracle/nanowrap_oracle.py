@@ -79,6 +79,7 @@ class OracleConjGrad:
         self.vertex_neighbors = n
         self.M = self.vertices.shape[0]
         self.tests, self.ress, self.prefs = [], [], []              # conj_grad.py:37-39
+        self.Lfuncs, self.Lhfuncs = ["I"], ["I"]                    # mesh_conj_grad.py:38 (:39 offers ["wfunc"], ["wfunc"])
         self._prev_loopcount = -1
         self.loopcount = 0
         self.w = None
@@ -152,6 +153,13 @@ class OracleConjGrad:
         vc[ms == 0, :] = verts[ms == 0, :]                                    # :818
         return vc
 
+    def I(self, f):
+        return f
+
+    def wfunc(self, f):                                             # :725-736
+        w = vertex_area_weights(np.ascontiguousarray(self.f), self.vertex_neighbors)
+        return f * w
+
     def _stop_cond(self):                                           # :1009-1016
         if len(self.tests) < 3:
             return False
@@ -162,13 +170,13 @@ class OracleConjGrad:
     def subsearch(self, f0, res, fdefs, lams, S):
         n_search = S.shape[1]
         c0 = (res * res).sum()
-        prefs = [f0 - fdefs[0]]                                     # Lfuncs == ["I"]
+        prefs = [getattr(self, self.Lfuncs[0])(f0 - fdefs[0])]      # conj_grad.py:191
         wpreds = [(p * p).sum() for p in prefs]
         AS = np.zeros((np.size(res), n_search), 'f')
         LS = np.zeros((len(prefs[0]), n_search, 1), 'f')
         for k in range(n_search):
             AS[:, k] = self.Afunc(S[:, k])[self.mask]
-            LS[:, k, 0] = S[:, k]
+            LS[:, k, 0] = getattr(self, self.Lfuncs[0])(S[:, k])    # conj_grad.py:200
         Hc = np.dot(AS.T, AS)
         Gc = np.dot(AS.T, res)
         Hw = np.zeros((n_search, n_search, 1))
@@ -214,8 +222,8 @@ class OracleConjGrad:
             w = 1.0 / (self.d.ravel() * sigma_inv / 2.0 + 1)        # :231
             self.res *= w                                           # :248
             S[:, 0] = self.Ahfunc(self.res)                         # :253
-            prefs[:, 0] = self.f - defaults[0]                      # :257
-            S[:, 1] = -1.0 * prefs[:, 0]                            # :258
+            prefs[:, 0] = getattr(self, self.Lfuncs[0])(self.f - defaults[0])       # :257
+            S[:, 1] = -1.0 * getattr(self, self.Lhfuncs[0])(prefs[:, 0])           # :258
             test = 1.0 - abs((S[:, 0] * S[:, 1]).sum()
                              / (np.linalg.norm(S[:, 0]) * np.linalg.norm(S[:, 1])))   # :262-265
             self.tests.append(test)
@@ -241,12 +249,15 @@ class OracleConjGrad64(OracleConjGrad):
 
     def subsearch(self, f0, res, fdefs, lams, S):
         n_search = S.shape[1]
-        prefs = f0 - fdefs[0]
+        L = getattr(self, self.Lfuncs[0])
+        prefs = L(f0 - fdefs[0])
         AS = np.zeros((np.size(res), n_search), 'f')
+        LS = np.zeros((len(prefs), n_search), 'f')
         for k in range(n_search):
             AS[:, k] = self.Afunc(S[:, k])[self.mask]
+            LS[:, k] = L(S[:, k])
         AS = AS.astype(np.float64)
-        S64 = S.astype(np.float64)
+        S64 = LS.astype(np.float64)
         l2 = float(lams[0]) ** 2
         H = AS.T @ AS + l2 * (S64.T @ S64)
         G = AS.T @ np.asarray(res, np.float64) - l2 * (S64.T @ prefs)

@@ -293,3 +293,37 @@ def test_final_mesh_at_moderate_scale():
         mg.update_geometry()
     d = np.sqrt(((vg.astype(np.float64) - vo) ** 2).sum(1))
     assert d.mean() <= 1e-2 and np.percentile(d, 99.9) <= 0.2 and d.max() <= 3.0, (d.mean(), np.percentile(d, 99.9), d.max())
+
+
+def test_search_with_the_wfunc_regulariser():
+    """Lfuncs = Lhfuncs = ["wfunc"] (mesh_conj_grad.py:39,725-736) read from the solver object like the reference does;
+    anything else the reference cannot run with is refused."""
+    mesh, pts, sig = make_case(n_points=10000, n_geo=6, seed=23)
+    from oracle import nanowrap_oracle as orc
+    mo, m64, mg = _clone(mesh), _clone(mesh), _clone(mesh)
+    s = (1.0 / sig.ravel()).astype(np.float32)
+    lam = 10.0       # the area weights are ~1/sqrt(6 edge^2) ~ 1e-2: a weak prior, so the reference's float32 sgemm noise is large here
+    oc = _oracle(mo, pts)
+    oc.Lfuncs, oc.Lhfuncs = ["wfunc"], ["wfunc"]
+    vo = oc.search(pts, lams=[lam], num_iters=5, sigma_inv=s)
+    o64 = orc.OracleConjGrad64(m64, pts)                  # the same algorithm with float64 Gram sums (what the GPU forms)
+    o64.Lfuncs, o64.Lhfuncs = ["wfunc"], ["wfunc"]
+    v64 = o64.search(pts, lams=[lam], num_iters=5, sigma_inv=s)
+    g = _gpu(mg, pts)
+    g.Lfuncs, g.Lhfuncs = ["wfunc"], ["wfunc"]
+    vg = g.search(pts, lams=[lam], num_iters=5, sigma_inv=s)
+    d64 = np.sqrt(((vg.astype(np.float64) - v64) ** 2).sum(1)).max()
+    d32 = np.sqrt(((vg.astype(np.float64) - vo) ** 2).sum(1)).max()
+    noise = np.sqrt(((v64 - vo) ** 2).sum(1)).max()      # the reference's own float32-sgemm noise on this input
+    assert d64 <= 1e-2, (d64, d32, noise)                 # final mesh, nm
+    assert d32 <= max(1e-2, 3 * noise), (d64, d32, noise)
+    assert np.allclose(np.array(g.tests, np.float64), np.array(oc.tests, np.float64), rtol=1e-3, atol=1e-5)
+    assert np.allclose([float(p[0]) for p in g.prefs], [float(p[0]) for p in oc.prefs], rtol=1e-4)
+    # differs from the default regulariser (the selector is live) ...
+    vi = _gpu(_clone(mesh), pts).search(pts, lams=[lam], num_iters=5, sigma_inv=s)
+    assert np.abs(vi - vg).max() > 1e-2
+    # ... and the operators the reference itself cannot run with are refused
+    g2 = _gpu(_clone(mesh), pts)
+    g2.Lfuncs, g2.Lhfuncs = ["Lfunc3"], ["Lhfunc3"]
+    with pytest.raises(NotImplementedError):
+        g2.search(pts, lams=[10.0], num_iters=1, sigma_inv=s)

@@ -166,7 +166,7 @@ def test_solver_shim_chooses_the_record_upload_and_passes_the_half_edge_stride()
     assert cg._vertex_mask is None                            # the valid mask is built lazily
     out = cg.search(pts, lams=[5.0], num_iters=3, sigma_inv=0.1)
     names = [c[0] for c in calls]
-    assert names == ['set_points', 'nw_set_topology_records', 'nw_search', 'nw_get_positions_strided']
+    assert names == ['set_points', 'nw_set_topology_records', 'nw_set_regulariser', 'nw_search', 'nw_get_positions_strided']
     rec = dict(calls)['nw_set_topology_records']
     assert rec[3] == mesh._halfedges.strides[0] == 28         # half-edge 'vertex' field gathered in place
     assert rec[4] == len(mesh._halfedges) and rec[5] == len(mesh._vertices) and rec[6] == len(mesh.faces)
@@ -177,7 +177,7 @@ def test_solver_shim_chooses_the_record_upload_and_passes_the_half_edge_stride()
     # a second search() on the same object re-sends the (possibly edited) positions, not the topology
     calls.clear()
     cg.search(pts, lams=[5.0], num_iters=2, sigma_inv=0.1)
-    assert [c[0] for c in calls] == ['set_points', 'nw_set_positions', 'nw_search', 'nw_get_positions_strided']
+    assert [c[0] for c in calls] == ['set_points', 'nw_set_positions', 'nw_set_regulariser', 'nw_search', 'nw_get_positions_strided']
 
 
 # ---- sessions and the recipe's mesh factory (no GPU: the library handle is stubbed) -------------------------------------

@@ -84,3 +84,24 @@ def test_quality_metrics_and_holepunch_vs_reference():
     assert evu.average_squared_distance(a, b) == orc.average_squared_distance(a, b)
     cand = np.arange(len(m._faces), dtype=np.int32)
     assert np.array_equal(refharness.reference_holepunch_pairs(m, cand), orc.holepunch_pairs(m, cand))
+
+
+def test_search_with_the_wfunc_regulariser_vs_reference():
+    """mesh_conj_grad.py:39 -- the one alternative regulariser the reference's search() can run with: bit-exact too."""
+    from oracle import nanowrap_oracle as orc
+    from oracle import refharness
+    mesh, pts, sig = make_case(n_points=2000, n_geo=4, seed=33)
+    m_ref, m_orc = copy.deepcopy(mesh), copy.deepcopy(mesh)
+    s = (1.0 / sig.ravel()).astype(np.float32)
+    cg = refharness.reference_solver(m_ref, pts)
+    cg.Lfuncs, cg.Lhfuncs = ["wfunc"], ["wfunc"]
+    vr = cg.search(pts, lams=[10.0], num_iters=4, sigma_inv=s)
+    oc = orc.OracleConjGrad(m_orc, pts)
+    oc.Lfuncs, oc.Lhfuncs = ["wfunc"], ["wfunc"]
+    vo = oc.search(pts, lams=[10.0], num_iters=4, sigma_inv=s)
+    assert np.array_equal(vr, vo) and np.array_equal(cg.S, oc.S) and cg.tests == oc.tests
+    # and the operators the reference cannot run with raise there too (float64 argument read as float32 by the C helper)
+    cg2 = refharness.reference_solver(copy.deepcopy(mesh), pts)
+    cg2.Lfuncs, cg2.Lhfuncs = ["Lfunc3"], ["Lhfunc3"]
+    with pytest.raises(AssertionError):
+        cg2.search(pts, lams=[10.0], num_iters=1, sigma_inv=s)

@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 4 --steps 20 --warmup 5 --workload c4s > gpurun_out/r2_bench_c4s_n4_blocks.json 2> gpurun_out/r2_bench_c4s_n4_blocks.err; tail -c 200 gpurun_out/r2_bench_c4s_n4_blocks.json
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 2 --steps 20 --warmup 5 --workload c4s > gpurun_out/r2_bench_c4s_n2_blocks.json 2> gpurun_out/r2_bench_c4s_n2_blocks.err; tail -c 200 gpurun_out/r2_bench_c4s_n2_blocks.json
+timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py > gpurun_out/r2_gputest_7.txt 2>&1; tail -12 gpurun_out/r2_gputest_7.txt
