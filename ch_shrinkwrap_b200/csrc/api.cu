@@ -39,6 +39,7 @@ extern "C" void nw_destroy(nw_ctx *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->iter_graph) { cudaGraphExecDestroy(h->iter_graph); h->iter_graph = nullptr; }
     nw_comm_destroy(h);
     nw_free(&h->px); nw_free(&h->py); nw_free(&h->pz);
     nw_free(&h->px64); nw_free(&h->py64); nw_free(&h->pz64);
@@ -137,6 +138,7 @@ extern "C" int nw_reset_seeds(nw_ctx *h) {
 
 extern "C" int nw_set_profile(nw_ctx *h, int on) {
     if (!h) return NW_ERR_ARG;
+    if (on != h->profile) h->epoch++;            // the traversal-statistics variant of k_sweep1 is a different launch
     h->profile = on;
     for (int k = 0; k < NW_N_STAGES; ++k) { h->stage_ms[k] = 0.0; h->stage_launches[k] = 0; }
     return NW_OK;
@@ -180,12 +182,6 @@ extern "C" int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launch
     return NW_OK;
 }
 
-static void release_graph(cudaGraph_t &graph, cudaGraphExec_t &graph_exec) {
-    if (graph_exec) cudaGraphExecDestroy(graph_exec);
-    if (graph) cudaGraphDestroy(graph);
-    graph = nullptr; graph_exec = nullptr;
-}
-
 extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, const double *prev_tests, int n_prev,
                          float *pos_out, double *tests, double *ress, double *prefs, double *cpred, double *wpred,
                          int *n_done) {
@@ -213,8 +209,6 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     h->ev_used = 0;
     h->ev_stage.clear();
     NW_CUDA(cudaEventRecord(h->ev_search0, h->stream));
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
     if (!s.stop) {
         int it = 0;
         // the first iteration runs eagerly: it may seed, build the launch schedule and touch allocations
@@ -223,34 +217,45 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
         // fits the iteration is launch-bound (C1: 0.25 ms of launches around microseconds of work).  Not under profiling
         // (per-stage events).  With a communicator the two ncclAllReduce calls of the iteration are captured with it
         // (NCCL supports stream capture; the eager first iteration has already run both collectives once, so nothing is
-        // allocated or connected inside the capture); NW_NO_COMM_GRAPH=1 keeps multi-rank runs eager.
+        // allocated or connected inside the capture); NW_NO_COMM_GRAPH=1 keeps multi-rank runs eager.  The instantiated
+        // graph is kept for as long as the points and the topology stay (h->epoch): a fit calls nw_search once per block,
+        // and repeated calls on one block (continue / finishing iterations) replay the same executable.
         static const bool no_graph = getenv("NW_NO_GRAPH") != nullptr;
         static const bool no_comm_graph = getenv("NW_NO_COMM_GRAPH") != nullptr;
         if (!no_graph && !h->profile && (h->nranks == 1 || !no_comm_graph) && num_iters - it >= 2) {
+            if (h->iter_graph && (h->iter_graph_epoch != h->epoch || h->iter_graph_last_step != last_step)) {
+                cudaGraphExecDestroy(h->iter_graph);
+                h->iter_graph = nullptr;
+            }
             const int64_t l0 = h->launches;
-            bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-            int rc = NW_OK;
-            if (ok) {
-                rc = enqueue_iteration(h, it, last_step);
-                ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && rc == NW_OK && graph != nullptr;
-            }
-            const int64_t per_iter = h->launches - l0;
-            h->launches = l0;                                    // nothing has run yet
-            if (ok) ok = cudaGraphInstantiate(&graph_exec, graph, 0) == cudaSuccess;
-            if (ok) {
-                for (; it < num_iters; ++it) {
-                    NW_CUDA(cudaGraphLaunch(graph_exec, h->stream));
-                    h->launches += per_iter;
+            static int64_t per_iter_launches = 15;
+            if (!h->iter_graph) {
+                cudaGraph_t graph = nullptr;
+                bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                int rc = NW_OK;
+                if (ok) {
+                    rc = enqueue_iteration(h, it, last_step);
+                    ok = cudaStreamEndCapture(h->stream, &graph) == cudaSuccess && rc == NW_OK && graph != nullptr;
                 }
-            } else {
-                cudaGetLastError();                              // capture refused: the loop below runs the iterations eagerly
-                if (rc != NW_OK) { release_graph(graph, graph_exec); return rc; }
+                per_iter_launches = h->launches - l0;
+                h->launches = l0;                                    // nothing has run yet
+                if (ok) ok = cudaGraphInstantiate(&h->iter_graph, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+                if (ok) { h->iter_graph_epoch = h->epoch; h->iter_graph_last_step = last_step; }
+                else {
+                    h->iter_graph = nullptr;
+                    cudaGetLastError();                              // capture refused: the loop below runs the iterations eagerly
+                    if (rc != NW_OK) return rc;
+                }
+            }
+            if (h->iter_graph) {
+                for (; it < num_iters; ++it) {
+                    NW_CUDA(cudaGraphLaunch(h->iter_graph, h->stream));
+                    h->launches += per_iter_launches;
+                }
             }
         }
-        for (; it < num_iters; ++it) {
-            const int rc = enqueue_iteration(h, it, last_step);
-            if (rc != NW_OK) { release_graph(graph, graph_exec); return rc; }
-        }
+        for (; it < num_iters; ++it) NW_CHECK(enqueue_iteration(h, it, last_step));
     }
     NW_CUDA(cudaEventRecord(h->ev_search1, h->stream));
     h->pin_fresh = false;
@@ -258,7 +263,6 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
     SolverState r;
     NW_CUDA(cudaMemcpyAsync(&r, h->st, sizeof(SolverState), cudaMemcpyDeviceToHost, h->stream));
     NW_CUDA(cudaStreamSynchronize(h->stream));
-    release_graph(graph, graph_exec);
     {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_search0, h->ev_search1);
@@ -291,7 +295,7 @@ extern "C" int nw_search(nw_ctx *h, float lam, int num_iters, int last_step, con
 extern "C" int nw_set_regulariser(nw_ctx *h, int mode) {
     if (!h) return NW_ERR_ARG;
     NW_ARG(mode == 0 || mode == 1, "nw_set_regulariser: mode must be 0 (I) or 1 (wfunc)");
-    h->reg_mode = mode;
+    h->reg_mode = mode;                          // read from the device state by the kernels: no new graph needed
     return NW_OK;
 }
 

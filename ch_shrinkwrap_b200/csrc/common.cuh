@@ -164,6 +164,10 @@ struct nw_ctx {
     struct nw_uploader *uploader = nullptr;       // xfer.cu: pinned staging lanes for large host->device copies
     cudaEvent_t ev_seg0 = nullptr, ev_seg1 = nullptr;   // topology_build segments (profiling only)
     double last_search_ms = 0.0;
+    // one captured CG iteration, instantiated once per (points, topology) epoch and replayed by every nw_search call on it
+    cudaGraphExec_t iter_graph = nullptr;
+    int64_t iter_graph_epoch = -1; int iter_graph_last_step = -1;
+    int64_t epoch = 0;                           // bumped by everything that can move a device buffer or change a launch shape
 
     // ---- comm ----
     void *nccl = nullptr;                        // ncclComm_t

@@ -148,6 +148,7 @@ static int set_points_impl(nw_ctx *h, const T *pts_host, int64_t P, const float 
     h->seeds_cold = true;
     h->order_stale = true;
     h->feet_valid = false;
+    h->epoch++;
     NWX(nw_alloc(h, &h->sp_pts, sizeof(T) * 3 * (size_t)P));
     T *d_pts = (T *)h->sp_pts;
     NWX(nw_h2d(h, d_pts, pts_host, sizeof(T) * 3 * (size_t)P));

@@ -453,6 +453,7 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     NW_CHECK(nw_save_feet(h));       // seeds for the next block, taken from the mesh that is about to be replaced
     NW_CHECK(seg_end(h));
     h->M = M; h->F = F;
+    h->epoch++;
     h->weights_valid = false;
     h->pin_fresh = false;
     h->points_mode = false;
@@ -692,6 +693,7 @@ extern "C" int nw_set_point_targets(nw_ctx *h, const void *xyz, int is_f64, int6
     cudaStream_t s = h->stream;
     const int n = (int)N, B = 256;
     h->M = n; h->F = n;
+    h->epoch++;
     h->weights_valid = false; h->pin_fresh = false; h->feet_valid = false;
     h->points_mode = true;
     NW_CHECK(nw_alloc(h, &h->posq, (size_t)n)); NW_CHECK(nw_alloc(h, &h->nrmq, (size_t)n));
