@@ -226,6 +226,8 @@ static inline void nw_free(T **p) {
 
 int nw_h2d(nw_ctx *h, void *dst, const void *src, size_t bytes);   // xfer.cu
 int nw_h2d_strided32(nw_ctx *h, void *dst, const void *src, size_t bytes, size_t stride);
+struct nw_h2d_job { void *dst; const void *src; size_t bytes, stride; };    // stride 4 = plain copy, else one int32 per `stride` source bytes
+int nw_h2d_many(nw_ctx *h, const nw_h2d_job *jobs, int n_jobs);               // xfer.cu: one thread team for several arrays
 void nw_uploader_destroy(nw_ctx *h);
 int nw_fetch_positions_async(nw_ctx *h);                            // tree.cu
 

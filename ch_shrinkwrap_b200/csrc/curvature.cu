@@ -329,9 +329,9 @@ extern "C" int nw_curvature_grad(nw_ctx *h, const void *vertices, const void *fa
     nw_free(&h->cvJ); nw_free(&h->cvOff);
     h->curvM = M; h->cv_dN = dN; h->cv_kc = kc; h->cv_kg = kg; h->cv_c0 = c0; h->cv_seed = (unsigned long long)jitter_seed;
     // the three record arrays go up through the pinned multi-lane path (xfer.cu), back to back on the handle's stream
-    NW_CHECK(nw_h2d(h, h->cvV, vertices, sizeof(VertRec) * (size_t)M));
-    NW_CHECK(nw_h2d(h, h->cvF, faces, sizeof(FaceRec) * (size_t)n_faces));
-    NW_CHECK(nw_h2d(h, h->cvH, halfedges, sizeof(HeRec) * (size_t)n_halfedges));
+    const nw_h2d_job up[3] = {{h->cvV, vertices, sizeof(VertRec) * (size_t)M, 4}, {h->cvF, faces, sizeof(FaceRec) * (size_t)n_faces, 4},
+                              {h->cvH, halfedges, sizeof(HeRec) * (size_t)n_halfedges, 4}};
+    NW_CHECK(nw_h2d_many(h, up, 3));
     CurvOut co;
     size_t offs[12];
     curv_outputs(h, co, offs);

