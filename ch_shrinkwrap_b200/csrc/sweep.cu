@@ -92,11 +92,15 @@ struct Nearest {
 // both the query's and the members' evaluation, DESIGN.md "exactness") and the squares by a relative 1e-5 (axes are
 // orthonormal only to float32 accuracy).  A node is skipped only if this bound exceeds the best exact fp64 distance,
 // so skipping can never change the answer.
+// (Measured dead ends for the instruction count of a step, ~38 in SASS: two 256-bit loads per 64-byte node,
+// ld.global.nc.v8.f32 = LDG.E.256 on sm_100a, would save six -- each of the four 128-bit loads also costs two moves of the
+// warp-uniform node address into the vector registers it is about to overwrite -- but ptxas 12.9 segfaults on this file with
+// them at every optimisation level; an opaque per-thread copy of the address does not change the allocation at 32 registers.)
 template <typename Q>
 __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps, int *link = nullptr) {
     const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
-    const float x = q.fx(), y = q.fy(), z = q.fz();
     const float4 d4 = __ldg(&bp->d);                 // the fourth quarter of the node stores t1 ...
+    const float x = q.fx(), y = q.fy(), z = q.fz();
     const float3 t1 = make_float3(d4.x, d4.y, d4.z);
     if (link) *link = __float_as_int(d4.w);          // ... and first child | last-child flag (k_global_tables)
     const float t2x = c.y, t2y = c.z, t2z = c.w;     // t2 = n x t1
