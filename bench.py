@@ -366,13 +366,15 @@ def main():
     dom = max(('sweep1', 'sweep2', 'mesh_prior'), key=lambda k: stage[k]['ms_total'])
     dom_ms = stage[dom]['ms_total'] / K
     achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9
-    traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
-        except Exception:
-            traffic = None
+    try:
+        traffic_tab = json.load(open(tpath)).get(args.workload, {}) if os.path.exists(tpath) else {}
+    except Exception:
+        traffic_tab = {}
+
+    def traffic_of(name):          # DRAM bytes per launch from the committed ncu captures (profiles/traffic.json), or None
+        return traffic_tab.get(name)
+    traffic = traffic_of(dom)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'peak_source': peak_src, 'frac_of_nominal_8000_gbs': achieved / 8000.0, 'ms_per_launch': dom_ms, 'algorithmic_bytes_per_launch': alg_bytes[dom],
                 'share_of_step': stage[dom]['ms_total'] / dev_ms}
@@ -383,7 +385,7 @@ def main():
         try:
             h.call('nw_bench_kernel', name.encode(), 10, ctypes.byref(ms))
             gbs = alg_bytes[name] / (ms.value * 1e-3) / 1e9
-            kernels[name] = {'ms': ms.value, 'achieved_gbs': gbs, 'frac': gbs / peak}
+            kernels[name] = {'ms': ms.value, 'achieved_gbs': gbs, 'frac': gbs / peak, 'traffic': traffic_of(name)}
         except Exception as e:      # noqa
             kernels[name] = {'error': str(e)}
 
@@ -401,7 +403,11 @@ def main():
         curv_wall = time.perf_counter() - t0
         h.call('nw_bench_kernel', b'curvature', 10, ctypes.byref(ms))
         gbs = alg_bytes['curvature'] / (ms.value * 1e-3) / 1e9
-        kernels['curvature'] = {'ms': ms.value, 'achieved_gbs': gbs, 'frac': gbs / peak, 'c_abi_call_ms_host_buffers': 1e3 * curv_wall, 'c_abi_first_call_ms': 1e3 * curv_first,
+        fp64_ms = traffic_of('curvature_fp64_pipe_busy_ms')
+        kernels['curvature'] = {'ms': ms.value, 'achieved_gbs': gbs, 'frac': gbs / peak, 'traffic': traffic_of('curvature'),
+                                # against the fp64 pipe instead of HBM: the time that pipe is busy for this arithmetic (ncu) / the kernel's time
+                                'fp64_bound': None if not fp64_ms else {'bound': 'fp64', 'pipe_busy_ms': fp64_ms, 'frac': fp64_ms / ms.value},
+                                'c_abi_call_ms_host_buffers': 1e3 * curv_wall, 'c_abi_first_call_ms': 1e3 * curv_first,
                                 'vertices_per_s': M / (ms.value * 1e-3)}
     except Exception as e:      # noqa
         kernels['curvature'] = {'error': str(e)}
