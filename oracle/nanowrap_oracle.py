@@ -396,3 +396,62 @@ def holepunch_pair_candidate_faces(mesh, candidates):
     pair_inds = pairs != -1
     new_inds = np.cumsum(pair_inds) - 1
     return candidates[pair_inds], new_inds[pairs[pair_inds]]
+
+
+# ---- block driver (_membrane_mesh.pyx:1427-1560, 1201-1219) -----------------------------------------------------------
+def opt_conjugate_gradient(mesh, points, sigma, max_iter=10, step_size=1.0, weights=None, remesh=None, log=None, **kwargs):
+    """Restates ``MembraneMesh.opt_conjugate_gradient`` for a harness mesh (mini-mesh: structured arrays, ``update_geometry``,
+    ``area``, ``_mean_edge_length``) with the oracle solver.  Topology edits are PYME's (absent): ``remesh(mesh, target_length)``
+    is the caller's stand-in, neck removal stops at the candidate list (:1212-1213).  ``log`` collects what a test compares:
+    per block ('block', j, n_it), ('necks', j, candidates), ('remesh', j, target_length)."""
+    import math
+    log = [] if log is None else log
+    rfq, drf = mesh.remesh_frequency, mesh.delaunay_remesh_frequency
+    r = (rfq != 0) and (rfq <= max_iter)                                           # :1430
+    dr = (drf != 0) and (drf <= max_iter)
+    if r and dr:
+        rf = math.gcd(rfq, drf)                                                    # :1435
+    elif r:
+        rf = rfq
+    elif dr:
+        rf = drf
+    else:
+        rf = max_iter
+    if r:
+        initial_length = mesh._mean_edge_length                                    # :1444
+        if kwargs.get('minimum_edge_length', -1) < 0:
+            final_length = np.clip(np.min(sigma) / 2.5, 1.0, 50.0)
+        else:
+            final_length = kwargs.get('minimum_edge_length')
+        m = (final_length - initial_length) / (rf * np.ceil(max_iter / rf))        # :1455
+    neck_first_iter = getattr(mesh, 'neck_first_iter', -1)
+    if np.isscalar(sigma):                                                         # :1460-1473
+        s = float(sigma)
+    elif (len(sigma.shape) == 1) and (sigma.shape[0] == points.shape[0]):
+        s = 1.0 / np.repeat(sigma, points.shape[1])
+    elif (len(sigma.shape) == 2) and (sigma.shape[0] == points.shape[0]) and (sigma.shape[1] == points.shape[1]):
+        s = (1.0 / sigma.ravel())
+    else:
+        raise ValueError('Sigma must be of shape (P,) or (P,3).')
+    mesh.cg = None
+    j = 0
+    lams = [step_size * mesh.kc / 2.0, mesh.shrink_weight] if mesh.shrink_weight > 0 else [step_size * mesh.kc / 2.0]   # :1483-1486
+    n_iter = min(max_iter, getattr(mesh, 'truncate_at', max_iter))                 # :1490
+    while j < n_iter:
+        mesh.cg = OracleConjGrad(mesh, points)                                     # :1510
+        n_it = min(n_iter - j, rf)
+        mesh.cg.search(points, lams=lams, num_iters=n_it, sigma_inv=s, weights=weights)   # :1516
+        j += n_it
+        log.append(('block', j, n_it))
+        mesh.update_geometry()                                                     # :1524-1527 (normals, neighbours refreshed)
+        if r and ((j % rfq) == 0):                                                 # :1537
+            if (neck_first_iter > 0) and (j > neck_first_iter):
+                K = curvature_grad(mesh, kc=mesh.kc, kg=mesh.kg, c0=mesh.c0)['K']  # :1201-1213 (remove_necks up to the candidate list)
+                lo, hi = getattr(mesh, 'neck_threshold_low', -1e-4), getattr(mesh, 'neck_threshold_high', 1e-2)
+                log.append(('necks', j, np.flatnonzero((K < lo) | (K > hi))))
+            target_length = (initial_length + m * (j + 1))                         # :1545
+            log.append(('remesh', j, float(target_length)))
+            if remesh is not None:
+                remesh(mesh, target_length)
+            mesh.cg = None
+    return j

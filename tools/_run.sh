@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT
-python bench.py --steps 5 --warmup 5 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2_launches_c3.csv python bench.py --steps 5 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -c 300 gpurun_out/plain_bench.log; wc -l gpurun_out/r2_launches_c3.csv
-python tools/trace_probe.py c3 2 > gpurun_out/plain_tp.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_sweep1" -s 7 -c 2 -o gpurun_out/r2_prof_warm python tools/trace_probe.py c3 2 > gpurun_out/ncu_tp.log 2>&1; tail -2 gpurun_out/ncu_tp.log
+timeout 900 python -m pytest tests/test_gpu_golden.py -x -q -k "block_driver" 2>&1 | tail -15
