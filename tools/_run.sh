@@ -1,5 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py > gpurun_out/r2_gputest_10.txt 2>&1; tail -5 gpurun_out/r2_gputest_10.txt
-echo "== block search"; python tools/trace_probe.py c3 2 2>&1 | grep -E "it |total"
-echo "== climb only"; NANOWRAP_LIB=$PWD/ch_shrinkwrap_b200/libnanowrap_noblk.so python tools/trace_probe.py c3 2 2>&1 | grep -E "it |total"
-NW_PROFILE=3 python tools/trav_probe.py c3 2>&1 | grep "^iter"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+( time python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 ) > gpurun_out/r2_bench_reference_c3.json 2> gpurun_out/r2_bench_reference_c3.err; tail -c 1200 gpurun_out/r2_bench_reference_c3.json; tail -5 gpurun_out/r2_bench_reference_c3.err
