@@ -40,7 +40,7 @@ WORKLOADS = {
 }
 CPU_SAMPLE = 'c2'         # bounded CPU sample of the cpu_baseline leg: same shape, same 20 localisations per vertex, 1/10 of c3
 STAGES = ['refit', 'shift', 'sweep1', 'allreduce_acc', 'mesh_prior', 'sweep2', 'allreduce_scalars', 'solve_update', 'seed_leaders',
-          'topology_build']
+          'topology_build', 'adjoint']
 
 
 def build_workload(name, seed, points=None, rank=0, world=1):
@@ -361,8 +361,9 @@ def main():
         'mesh_prior': 120.0 * M,                           # _ncc
         'apply_A': 36.0 * P + 12.0 * M,
         'apply_AH': 36.0 * P + 12.0 * M,
+        'adjoint': 36.0 * P + 12.0 * M,                    # AH res + AH 1 in one pass (the scatter of the iteration)
     }
-    stage = {STAGES[k]: {'ms_total': stage_ms[k], 'launches': int(stage_l[k])} for k in range(10)}
+    stage = {STAGES[k]: {'ms_total': stage_ms[k], 'launches': int(stage_l[k])} for k in range(len(STAGES))}
     dom = max(('sweep1', 'sweep2', 'mesh_prior'), key=lambda k: stage[k]['ms_total'])
     dom_ms = stage[dom]['ms_total'] / K
     achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9
@@ -381,7 +382,7 @@ def main():
     # isolated single-operator kernels (device resident, CUDA events)
     kernels = {}
     ms = ctypes.c_float(0.0)
-    for name in ('apply_A', 'apply_AH', 'sweep2', 'mesh_prior', 'sweep1'):
+    for name in ('apply_A', 'apply_AH', 'adjoint', 'sweep2', 'mesh_prior', 'sweep1'):
         try:
             h.call('nw_bench_kernel', name.encode(), 10, ctypes.byref(ms))
             gbs = alg_bytes[name] / (ms.value * 1e-3) / 1e9

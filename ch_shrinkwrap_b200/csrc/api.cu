@@ -114,7 +114,8 @@ static int enqueue_iteration(nw_ctx *h, int it, int last_step) {
     NW_STAGE(1, nw_set_acc_shifts(h));             // vertex bbox -> fixed-point scales, rounding slack of the box tests
     NW_STAGE(0, nw_tree_refit(h));                 // centroids + boxes at the current f  (:443)
     if (h->seeds_cold) NW_STAGE(8, nw_launch_seed_leaders(h));   // first iteration after a topology upload only
-    NW_STAGE(2, nw_launch_sweep1(h, true));        // NN, weights, A f, residual, AH res, AH 1  (:222-253)
+    NW_STAGE(2, nw_launch_sweep1(h, true));        // NN, weights, A f, residual  (:222-253)
+    NW_STAGE(10, nw_launch_adjoint(h));            // AH res, AH 1: exact fixed-point scatter
     if (h->nranks > 1) NW_STAGE(3, nw_allreduce_acc(h));   // N>1: vertex-gradient allreduce
     NW_STAGE(4, nw_launch_mesh_prior(h, true));    // S0, ncc, prefs, S1, S^T S  (:224,253-258)
     NW_STAGE(5, nw_launch_sweep2(h));              // A S_k and Gram sums  (conj_grad.py:197-203)

@@ -12,8 +12,8 @@
 #ifndef NW_S2_PTS
 #define NW_S2_PTS 4      // k_sweep2: points per thread (their dependent load chains slot -> face -> S overlap); sizes its partials
 #endif
-#define NW_N_STAGES 10   // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders,
-                         // topology_build (device side of nw_set_topology*: feet, unpack, Hilbert sort, tables, frames)
+#define NW_N_STAGES 11   // refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars, solve_update, seed_leaders,
+                         // topology_build (device side of nw_set_topology*: feet, unpack, Hilbert sort, tables, frames), adjoint
 
 // Node bound = ORIENTED box: a surface patch is thin along its normal and tilted against the coordinate axes, so an
 // axis-aligned box is mostly empty space.  Axes n (patch normal), t1 = tangent_of(n), t2 = n x t1; one interval per axis.
@@ -266,6 +266,7 @@ __host__ __device__ __forceinline__ void hilbert_axes_to_transpose(U &x, U &y, U
 int nw_tree_build(nw_ctx *h);                 // after topology upload: Hilbert sort of faces, octree tables, frames
 int nw_tree_refit(nw_ctx *h);                 // every iteration: centroids + boxes at the current f
 int nw_launch_sweep1(nw_ctx *h, bool scatter);
+int nw_launch_adjoint(nw_ctx *h);
 int nw_launch_seed_leaders(nw_ctx *h);
 int nw_save_feet(nw_ctx *h);
 int nw_launch_sweep2(nw_ctx *h);

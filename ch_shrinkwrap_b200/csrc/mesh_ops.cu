@@ -58,13 +58,16 @@ __global__ void k_shift_final(float plo_x, float plo_y, float plo_z, float phi_x
         st->bbox[a] = 0x7fffffff; st->bbox[3 + a] = (int)0x80000000;      // ready for the next iteration
     }
     st->coord_l1 = l1;
-    // |w_j res_c| <= Wn_max * extent ; a vertex sums at most P_global of them
-    double bound = fmax(wn_max * ext, 1e-30) * fmax(p_global, 1.0);
-    int e;
-    frexp(bound, &e);
-    st->acc_shift = max(-60, min(60, 61 - e));
+    // |w_j res_c| <= Wn_max * extent ; a vertex sums at most P_global of them.  Two conditions on the scale 2^shift: the sum
+    // over all ranks stays below 2^61, and every single term below 2^38 (the warp scatter carries terms as five bytes,
+    // sweep.cu: warp_adjoint_scatter)
+    const double term = fmax(wn_max * ext, 1e-30);
+    int e, et;
+    frexp(term * fmax(p_global, 1.0), &e);
+    frexp(term, &et);
+    st->acc_shift = max(-100, min(60, min(61 - e, 38 - et)));
     frexp(fmax(p_global, 1.0), &e);
-    st->infl_shift = 61 - e;
+    st->infl_shift = min(61 - e, 37);             // weights are <= 1
 }
 
 #define NW_MSUM 14  // hw00 hw01 hw11 hw02 hw12 hw22 gw0 gw1 gw2 | s0.s1 s0.s0 s1.s1 | sum prefs32^2 | sum prefs64^2

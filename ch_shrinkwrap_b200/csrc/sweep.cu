@@ -5,7 +5,7 @@
 //              scatter of AH res and AH 1            (mesh_conj_grad.py:222-253, 433-516, 518-588)
 //   k_sweep2 : A applied to all search directions at once + Gram sums Hc, Gc, c0 in fp64, without
 //              materialising AS                                       (conj_grad.py:189-203)
-//   k_apply_A / k_apply_AH : the single-operator forms behind Afunc / Ahfunc.
+//   k_apply_A / k_adjoint : the single-operator forms behind Afunc / Ahfunc (k_adjoint<true> is also the scatter of the iteration).
 //
 // Determinism: the adjoint accumulates in 64-bit fixed point (integer atomics are order-independent,
 // float atomics are not); the Gram sums use a fixed thread->point assignment and a fixed two-stage tree.
@@ -349,29 +349,153 @@ __device__ __forceinline__ void red_fixed(unsigned long long *p, float v, double
     atomicAdd(p, (unsigned long long)to_fixed(v, scale));
 }
 
-// Sum of a 64-bit fixed-point value over the lanes in `mask` (all of which hold the same key): the value is
-// split into three limbs so the 32-bit REDUX unit can add them without overflow (<= 32 lanes x 22 bits);
-// recombination is exact modulo 2^64, i.e. exact two's-complement addition.
-__device__ __forceinline__ unsigned long long group_sum(unsigned mask, long long v) {
-    const unsigned long long u = (unsigned long long)v;
-    const unsigned l0 = __reduce_add_sync(mask, (unsigned)(u & 0x3fffffu));
-    const unsigned l1 = __reduce_add_sync(mask, (unsigned)((u >> 22) & 0x1fffffu));
-    const unsigned l2 = __reduce_add_sync(mask, (unsigned)(u >> 43));
-    return (unsigned long long)l0 + ((unsigned long long)l1 << 22) + ((unsigned long long)l2 << 43);
+// ---- deterministic adjoint scatter (a6): exact segmented sums of a warp on the tensor cores ------------------------
+// Every term w_j*r_c is a float32 product converted to 64-bit fixed point (|term| < 2^39 by the shift rule, k_shift_final),
+// so the result is an exact integer sum: independent of scheduling and of the number of GPUs.  The 32 points of a warp hit
+// ~8-10 distinct faces; their per-face sums used to be taken with MATCH + 18 REDUX per distinct face (the ADU pipe was 87 %
+// busy, ncu r02_ncu_full_c3_apply_AH_summary.csv).  Now a warp forms them as ONE small integer matrix product
+//      C[group][byte column] = G[group][lane] * V[lane][byte column]        (IMMA.16832.U8.U8, s32 accumulators)
+// G is the 0/1 membership matrix of the lanes' faces (built in registers from MATCH + a ballot), V holds each lane's twelve
+// biased 40-bit terms as five bytes each plus a column of ones (the group sizes): a byte column sums to <= 32*255, the
+// columns are recombined with shifts -- exact two's-complement arithmetic modulo 2^64 -- and one RED.64 per (face corner,
+// component) leaves the warp.  V goes through shared memory once: every lane stores its 64-byte row, and
+// ldmatrix.m16n16.trans.b8 (LDSM.8.MT1616, new on sm_100a) hands the bytes back transposed as the B fragments.
+// Column order: the C fragment gives thread (g = lane/4, t = lane%4) the columns 8 nt + 2 t + {0, 1} of rows g and g + 8,
+// so component t (x, y, z, influence) keeps its 16-byte stream [corner 0: b0..b4 | corner 1: b0..b4 | corner 2: b0..b4 | 1]
+// in exactly those columns and every thread recombines whole values without a shuffle.
+#define NW_ADJ_ROW 80      // bytes per lane row in shared memory: 64 used + 16 of padding (conflict-free 16-byte accesses)
+struct AdjWarpSmem {
+    unsigned char tile[32 * NW_ADJ_ROW];
+    int4 sf[32];            // corner ids of the face of every group (written by the group's first lane)
+    unsigned gid[8];        // group id of every lane, one byte each
+};
+
+__device__ __forceinline__ unsigned adj_eq4(unsigned x, unsigned r4) {     // bytes of x, r4 below 0x20: 0x01 where they are equal
+    return (~((x ^ r4) + 0x7f7f7f7fu) >> 7) & 0x01010101u;
+}
+__device__ __forceinline__ void adj_imma(int (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// term -> biased 40-bit fixed point: rn(v * 2^shift) + 2^39, low word and high byte (v * 2^shift is exact in float32)
+__device__ __forceinline__ void adj_fixed(float v, float scale, unsigned bias, unsigned &lo, unsigned &hi) {
+    const long long f = __float2ll_rn(__fmul_rn(v, scale));
+    lo = (unsigned)f;
+    hi = (unsigned)(f >> 32) + bias;
 }
 
-// Same for values known to satisfy |v| < 2^53 (true whenever the accumulators are scaled for >= 256 points: the scale
-// leaves room for P_global terms below 2^61): two limbs, 18 instead of 27 REDUX per vertex -- REDUX issues once per
-// ~29 cycles per scheduler and is what bounds the adjoint (measured: k_apply_AH 0.37 ms, 0.15 ms without the group sums,
-// and the same with or without the atomics that follow).
-__device__ __forceinline__ unsigned long long group_sum2(unsigned mask, long long v) {
-    const unsigned lo = __reduce_add_sync(mask, (unsigned)((unsigned long long)v & 0x7ffffffu));        // 27 bits x 32 lanes
-    const int hi = __reduce_add_sync(mask, (int)(v >> 27));                                            // |.| < 2^26 x 32 lanes
-    return (unsigned long long)(((long long)hi << 27) + (long long)lo);
+// One point per lane: key (sorted face slot; any negative value for an inactive lane, whose weights and residual must be zero), the face's
+// corner ids, the three weights and the residual.  INFL: component 3 accumulates the weights themselves (AH applied to ones).
+template <bool INFL>
+__device__ __forceinline__ void warp_adjoint_scatter(AdjWarpSmem &sm, bool active, int key, const int4 *__restrict__ sfaces,
+                                                     const float (&uw)[3], float r_x, float r_y, float r_z, float scale,
+                                                     float scale_i, unsigned long long *__restrict__ acc) {
+    const int lane = threadIdx.x & 31;
+    // ---- this lane's row of V ----
+    unsigned S[4][4];                      // [component][word of its 16-byte stream]
+    {
+        // an inactive lane comes with zero weights and residual: without the bias and the one its whole row is zero
+        const unsigned bias = active ? 0x80u : 0u, bias_one = active ? 0x180u : 0u;
+        const float rr[3] = {r_x, r_y, r_z};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t == 3 && !INFL) { S[3][0] = S[3][1] = S[3][2] = S[3][3] = 0u; continue; }
+            unsigned lo[3], hi[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                // (byte 1 of the last high word: the column of ones)
+                if (t < 3) adj_fixed(__fmul_rn(uw[q], rr[t]), scale, q == 2 ? bias_one : bias, lo[q], hi[q]);
+                else adj_fixed(uw[q], scale_i, q == 2 ? bias_one : bias, lo[q], hi[q]);
+            }
+            S[t][0] = lo[0];
+            S[t][1] = __byte_perm(hi[0], lo[1], 0x6540);           // c0.b4 c1.b0 c1.b1 c1.b2
+            S[t][2] = __byte_perm(__byte_perm(lo[1], hi[1], 0x0043), lo[2], 0x5410);   // c1.b3 c1.b4 c2.b0 c2.b1
+            S[t][3] = __byte_perm(lo[2], hi[2], 0x5432);           // c2.b2 c2.b3 c2.b4 1
+        }
+    }
+    {
+        uint4 *row = reinterpret_cast<uint4 *>(sm.tile + lane * NW_ADJ_ROW);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {      // 16-byte chunk j = n-tiles 2j, 2j+1: {S0,S1 | S2,S3} halves of stream word j
+            uint4 v;
+            v.x = __byte_perm(S[0][j], S[1][j], 0x5410); v.y = __byte_perm(S[2][j], S[3][j], 0x5410);
+            v.z = __byte_perm(S[0][j], S[1][j], 0x7632); v.w = __byte_perm(S[2][j], S[3][j], 0x7632);
+            row[j] = v;
+        }
+    }
+    // ---- groups: lanes with the same face ----
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(grp) - 1;
+    const unsigned leaders = __ballot_sync(0xffffffffu, lane == leader);
+    const int gid = __popc(leaders & ((1u << leader) - 1u));
+    const int ngroups = __popc(leaders);
+    reinterpret_cast<unsigned char *>(sm.gid)[lane] = (unsigned char)gid;
+    // the corner ids of a group's face: one gather per group, needed only by the epilogue -- its latency (the second of the
+    // dependent chain slot -> face) hides behind the product
+    int4 sf = make_int4(0, 0, 0, 0);
+    if (lane == leader && active) sf = __ldg(&sfaces[key]);
+    __syncwarp();
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned gw0 = sm.gid[t], gw1 = sm.gid[4 + t];         // group ids of lanes 4t..4t+3 and 16+4t..16+4t+3
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(sm.tile + lane * NW_ADJ_ROW);
+    // B fragments of n-tiles 2j, 2j+1: rows 0-15 come from the addresses of lanes 0-15, rows 16-31 from lanes 16-31
+    auto load_b = [&](int j, unsigned (&b)[2][2]) {
+        asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b[0][0]), "=r"(b[1][0]), "=r"(b[0][1]), "=r"(b[1][1]) : "r"(addr + 16 * j));
+    };
+    // stream byte k of a component sits in n-tile k / 2, accumulator register 2 half + k % 2
+    auto emit = [&](int q, int half, int ng, const int4 &f, unsigned s0, unsigned s1, unsigned s2, unsigned s3, unsigned s4) {
+        const int vid = q == 0 ? f.x : q == 1 ? f.y : f.z;
+        const unsigned long long v = (unsigned long long)(s0 + (s1 << 8) + (s2 << 16)) + ((unsigned long long)s3 << 24) +
+                                     ((unsigned long long)(s4 - ((unsigned)ng << 7)) << 32);      // minus ng * 2^39
+        atomicAdd(acc + 4 * (size_t)vid + t, v);
+    };
+    for (int m0 = 0; m0 < ngroups; m0 += 16) {                    // warp-uniform; a second pass only with > 16 distinct faces
+        const unsigned r0 = (unsigned)(m0 + g) * 0x01010101u, r1 = (unsigned)(m0 + g + 8) * 0x01010101u;
+        const unsigned a0 = adj_eq4(gw0, r0), a1 = adj_eq4(gw0, r1), a2 = adj_eq4(gw1, r0), a3 = adj_eq4(gw1, r1);
+        // two phases of four n-tiles each keep 16 accumulators live instead of 32: first the upper half of the streams
+        // (corner 2 and the group sizes), then the lower half (corners 0 and 1; corner 1 ends in n-tile 4, kept)
+        int c4[4], ng[2];
+        {
+            unsigned b23[2][2], b67[2][2];
+            load_b(2, b23); load_b(3, b67);
+            int c5[4] = {0, 0, 0, 0}, c6[4] = {0, 0, 0, 0}, c7[4] = {0, 0, 0, 0};
+            c4[0] = c4[1] = c4[2] = c4[3] = 0;
+            adj_imma(c7, a0, a1, a2, a3, b67[1][0], b67[1][1]);
+            adj_imma(c6, a0, a1, a2, a3, b67[0][0], b67[0][1]);
+            adj_imma(c5, a0, a1, a2, a3, b23[1][0], b23[1][1]);
+            adj_imma(c4, a0, a1, a2, a3, b23[0][0], b23[0][1]);
+            ng[0] = c7[1]; ng[1] = c7[3];                         // stream byte 15: the group size (0: no such group)
+            if (m0 == 0) {                                        // the corner ids are needed only from here on
+                if (lane == leader) sm.sf[gid] = sf;
+                __syncwarp();
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (ng[half] == 0 || (t == 3 && !INFL)) continue;
+                const int4 f = sm.sf[m0 + g + 8 * half];
+                emit(2, half, ng[half], f, c5[2 * half], c5[2 * half + 1], c6[2 * half], c6[2 * half + 1], c7[2 * half]);   // bytes 10..14
+            }
+        }
+        {
+            unsigned b01[2][2], b23[2][2];
+            load_b(0, b01); load_b(1, b23);
+            int c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, c3[4] = {0, 0, 0, 0};
+            adj_imma(c0, a0, a1, a2, a3, b01[0][0], b01[0][1]);
+            adj_imma(c1, a0, a1, a2, a3, b01[1][0], b01[1][1]);
+            adj_imma(c2, a0, a1, a2, a3, b23[0][0], b23[0][1]);
+            adj_imma(c3, a0, a1, a2, a3, b23[1][0], b23[1][1]);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (ng[half] == 0 || (t == 3 && !INFL)) continue;
+                const int4 f = sm.sf[m0 + g + 8 * half];
+                emit(0, half, ng[half], f, c0[2 * half], c0[2 * half + 1], c1[2 * half], c1[2 * half + 1], c2[2 * half]);   // bytes 0..4
+                emit(1, half, ng[half], f, c2[2 * half + 1], c3[2 * half], c3[2 * half + 1], c4[2 * half], c4[2 * half + 1]);   // bytes 5..9
+            }
+        }
+    }
 }
-__device__ __forceinline__ unsigned long long group_sum_sel(bool two, unsigned mask, long long v) {
-    return two ? group_sum2(mask, v) : group_sum(mask, v);
-}
+
 
 struct Sweep1Args {
     int64_t P;
@@ -382,7 +506,6 @@ struct Sweep1Args {
     float sinv_scalar, wmean;
     int *slot;
     float *w0, *w1, *w2, *rx, *ry, *rz;
-    int two_limbs;                 // 1: every fixed-point term is below 2^53 in magnitude (group_sum2)
     const int *order;              // block schedule (see build_block_order) or NULL
     const float4 *posq;
     const int4 *sfaces;
@@ -630,28 +753,6 @@ __global__ void __launch_bounds__(128, F64 ? (NW_S1_MINB > 12 ? 12 : NW_S1_MINB)
     if (!(fabsf(r_x) <= FLT_MAX && fabsf(r_y) <= FLT_MAX && fabsf(r_z) <= FLT_MAX)) a.st->nan_flag = 1;
     }
     }
-    if (MODE == 0) return;
-    // ---- deterministic adjoint: S0 += w_j res, influence += w_j, in 64-bit fixed point (conj_grad_utils.c:153-162).
-    // Lanes whose point landed on the same face are summed inside the warp first (exact integer sums), so a face
-    // costs 12 global RED.64 per warp instead of 12 per point and the lanes of a warp never collide on an address.
-    const double sc = pow2d(a.st->acc_shift), sci = pow2d(a.st->infl_shift);
-    const int key = active ? best.slot : -1 - (int)(threadIdx.x & 31);
-    const unsigned grp = __match_any_sync(0xffffffffu, key);
-    const bool lead = active && ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1));
-    const float uw[3] = {u0, u1, u2};
-    const int vid[3] = {sf.x, sf.y, sf.z};
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const bool two = a.two_limbs != 0 && a.st->acc_shift > -60;
-        const unsigned long long gx = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
-        const unsigned long long gy = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
-        const unsigned long long gz = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
-        const unsigned long long gi = group_sum_sel(two, grp, to_fixed(uw[j], sci));
-        if (lead) {
-            unsigned long long *dst = a.acc + 4 * (size_t)vid[j];
-            atomicAdd(dst + 0, gx); atomicAdd(dst + 1, gy); atomicAdd(dst + 2, gz); atomicAdd(dst + 3, gi);
-        }
-    }
 }
 
 // ---- single-operator forms ------------------------------------------------------------------------
@@ -669,36 +770,46 @@ __global__ void __launch_bounds__(256) k_apply_A(int64_t P, const int *__restric
     yz[i] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, u0), __fmul_rn(b.z, u1)), __fmul_rn(c.z, u2));
 }
 
-// out_v += sum w_pj r_p  (Ahfunc) into the fixed-point accumulators; acc.w untouched.  Same warp-level
-// pre-aggregation by face as k_sweep1.
-__global__ void __launch_bounds__(256) k_apply_AH(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
-                                                  const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
-                                                  const float *__restrict__ rx, const float *__restrict__ ry, const float *__restrict__ rz,
-                                                  unsigned long long *__restrict__ acc, int shift, bool two) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool active = i < P;
-    int sl = -1 - (int)(threadIdx.x & 31);
-    int4 sf = make_int4(0, 0, 0, 0);
-    float uw[3] = {0.f, 0.f, 0.f}, r_x = 0.f, r_y = 0.f, r_z = 0.f;
-    if (active) {
-        sl = slot[i];
-        sf = __ldg(&sfaces[sl]);
-        uw[0] = w0[i]; uw[1] = w1[i]; uw[2] = w2[i];
-        r_x = rx[i]; r_y = ry[i]; r_z = rz[i];
-    }
-    const double sc = pow2d(shift);
-    const unsigned grp = __match_any_sync(0xffffffffu, sl);
-    const bool lead = active && ((threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1));
-    const int vid[3] = {sf.x, sf.y, sf.z};
+// out_v += sum w_pj r_p  (Ahfunc, conj_grad_utils.c:123-167) into the fixed-point accumulators; INFL: channel 3 += sum w_pj
+// (AH applied to ones) in the same pass -- the form the CG iteration runs right after k_sweep1.  st != NULL: the shifts are
+// the device-side ones of this iteration (k_shift_final) and a raised stop flag makes the kernel a no-op.
+#ifndef NW_ADJ_TILES
+#define NW_ADJ_TILES 2      // points per thread: the loads of all of them are in flight before the first one is processed
+#endif
+#ifndef NW_ADJ_MINB
+#define NW_ADJ_MINB 4
+#endif
+template <bool INFL>
+__global__ void __launch_bounds__(256, NW_ADJ_MINB) k_adjoint(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
+                                                 const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
+                                                 const float *__restrict__ rx, const float *__restrict__ ry, const float *__restrict__ rz,
+                                                 unsigned long long *__restrict__ acc, const SolverState *__restrict__ st, int shift, int shift_i) {
+    __shared__ __align__(16) AdjWarpSmem sm[8];
+    int sl[NW_ADJ_TILES];
+    float uw[NW_ADJ_TILES][3], r[NW_ADJ_TILES][3];
+    bool active[NW_ADJ_TILES];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const unsigned long long gx = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_x), sc));
-        const unsigned long long gy = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_y), sc));
-        const unsigned long long gz = group_sum_sel(two, grp, to_fixed(__fmul_rn(uw[j], r_z), sc));
-        if (lead) {
-            unsigned long long *dst = acc + 4 * (size_t)vid[j];
-            atomicAdd(dst + 0, gx); atomicAdd(dst + 1, gy); atomicAdd(dst + 2, gz);
+    for (int k = 0; k < NW_ADJ_TILES; ++k) {
+        const int64_t i = ((int64_t)blockIdx.x * NW_ADJ_TILES + k) * blockDim.x + threadIdx.x;
+        active[k] = i < P;
+        sl[k] = -1;
+        uw[k][0] = uw[k][1] = uw[k][2] = r[k][0] = r[k][1] = r[k][2] = 0.f;
+        if (active[k]) {
+            uw[k][0] = w0[i]; uw[k][1] = w1[i]; uw[k][2] = w2[i];
+            r[k][0] = rx[i]; r[k][1] = ry[i]; r[k][2] = rz[i];
+            sl[k] = slot[i];
         }
+    }
+    if (st) {                          // all three loads in flight together with the points', then the branch
+        const int stop = st->stop, s0 = st->acc_shift, s1 = st->infl_shift;
+        if (stop) return;
+        shift = s0; shift_i = s1;
+    }
+    const float scale = (float)pow2d(shift), scale_i = (float)pow2d(shift_i);
+#pragma unroll
+    for (int k = 0; k < NW_ADJ_TILES; ++k) {
+        if (k) __syncwarp();           // the warp's shared-memory tile is reused
+        warp_adjoint_scatter<INFL>(sm[threadIdx.x >> 5], active[k], sl[k], sfaces, uw[k], r[k][0], r[k][1], r[k][2], scale, scale_i, acc);
     }
 }
 
@@ -894,7 +1005,6 @@ static Sweep1Args make_args(nw_ctx *h) {
     if (no_clear) a.tv.grid_inv = 0.f;
     a.acc = h->acc; a.st = h->st;
     a.order = nullptr;
-    a.two_limbs = h->P_global >= 256 ? 1 : 0;       // k_shift_final leaves 2^61 / P_global of headroom per term (its clamp at -60 only bites for absurd extents)
     return a;
 }
 
@@ -1040,6 +1150,15 @@ int nw_launch_sweep1(nw_ctx *h, bool scatter) {
     return NW_OK;
 }
 
+// AH res and AH 1 of the iteration: the scatter that follows k_sweep1 (stage "adjoint")
+int nw_launch_adjoint(nw_ctx *h) {
+    if (h->P == 0) return NW_OK;
+    k_adjoint<true><<<nw_grid(h->P, 256 * NW_ADJ_TILES), 256, 0, h->stream>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz,
+                                                                h->acc, h->st, 0, 0);
+    NW_LAUNCH_CHECK();
+    return NW_OK;
+}
+
 int nw_launch_sweep2(nw_ctx *h) {
     const int B = 256;
     const int G = h->n_partials;
@@ -1156,14 +1275,15 @@ int nw_apply_AH_device(nw_ctx *h, const float *rx, const float *ry, const float 
     // shift from an a-priori bound on |w r| summed over every rank's points
     const int B = 256;
     cudaStream_t s = h->stream;
+    // (the same rule as k_shift_final: the sum over all ranks stays below 2^61 and every term below 2^38)
     double tot = bound * (double)std::max<int64_t>(h->P_global, 1);
-    int e = 0;
+    int e = 0, et = 0;
     frexp(tot > 0 ? tot : 1.0, &e);
-    int shift = std::max(-60, std::min(40, 61 - e));
+    frexp(bound > 0 ? bound : 1.0, &et);
+    int shift = std::max(-100, std::min(40, std::min(61 - e, 38 - et)));
     NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * h->M, s));
     if (h->P) {
-        k_apply_AH<<<nw_grid(h->P, B), B, 0, s>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, rx, ry, rz, h->acc, shift,
-                                                   h->P_global >= 256 && shift > -60);
+        k_adjoint<false><<<nw_grid(h->P, B * NW_ADJ_TILES), B, 0, s>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, rx, ry, rz, h->acc, nullptr, shift, 0);
         NW_LAUNCH_CHECK();
     }
     NW_CHECK(nw_allreduce_acc(h));
@@ -1246,7 +1366,9 @@ int nw_bench_launch(nw_ctx *h, const char *name) {
         float *yx = h->scratchP, *yy = yx + P, *yz = yy + P;
         k_apply_A<<<nw_grid(P, B), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->posq, yx, yy, yz);
     } else if (n == "apply_AH") {
-        k_apply_AH<<<nw_grid(P, B), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->acc, 20, h->P_global >= 256);
+        k_adjoint<false><<<nw_grid(P, B * NW_ADJ_TILES), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->acc, nullptr, 20, 0);
+    } else if (n == "adjoint") {
+        return nw_launch_adjoint(h);
     } else if (n == "sweep1") {
         return nw_launch_sweep1(h, true);
     } else if (n == "nn_weights") {

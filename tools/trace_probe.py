@@ -32,3 +32,5 @@ for blk in range(nblk):
         print('   it %d: sweep1 %.3f refit %.3f sweep2 %.3f prior %.3f solve %.3f seeds %.3f shift %.3f' % (
             it, r.get(2, 0), r.get(0, 0), r.get(5, 0), r.get(4, 0), r.get(7, 0), r.get(8, 0), r.get(1, 0)))
 print('total search ms %.2f over %d iterations: %.3f ms/iter' % (tot, nblk * cfg['block'], tot / (nblk * cfg['block'])))
+import zlib
+print('crc of final vertices %08x' % zlib.crc32(np.ascontiguousarray(mesh._vertices['position']).tobytes()))
