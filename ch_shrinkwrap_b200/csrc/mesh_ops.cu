@@ -207,31 +207,34 @@ __global__ void __launch_bounds__(256, 3) k_mesh_prior(int M, unsigned long long
     }
 }
 
-// one CTA of 32 threads: fold mesh partials, solve, log, stop rule
-__global__ void k_solve(const double *__restrict__ mesh_partials, int n_mesh_blocks, SolverState *st, double *__restrict__ hist,
-                        int iter_index) {
+// fold the mesh partials: one CTA per quantity, fixed order (thread t sums partials t, t+256, ...; then a fixed tree)
+__global__ void __launch_bounds__(256) k_fold_mesh(const double *__restrict__ mesh_partials, int n_mesh_blocks, SolverState *st) {
     if (st->stop) return;
-    __shared__ double red[NW_MSUM];
     __shared__ double sh[256];
-    for (int k = 0; k < NW_MSUM; ++k) {         // fixed order: thread t sums partials t, t+256, ...; then a fixed tree
-        double v = 0.0;
-        for (int b = threadIdx.x; b < n_mesh_blocks; b += 256) v += mesh_partials[(size_t)b * NW_MSUM + k];
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 128; o; o >>= 1) {
-            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) red[k] = sh[0];
+    const int k = blockIdx.x;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < n_mesh_blocks; b += 256) v += mesh_partials[(size_t)b * NW_MSUM + k];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x == 0) {
+        const double t = sh[0];
+        if (k < 6) st->hw[k] = t;
+        else if (k < 9) st->gw[k - 6] = t;
+        else if (k < 12) st->tst[k - 9] = t;
+        else if (k == 12) st->prefs32_2 = t;
+        else st->prefs64_2 = t;
+    }
+}
+
+// one thread: solve, log, stop rule
+__global__ void k_solve(SolverState *st, double *__restrict__ hist, int iter_index) {
+    if (st->stop || threadIdx.x != 0) return;
     iter_index = st->n_done;          // == the host's loop index (n_done starts at 0 in nw_search and is bumped below); reading
                                       // it here leaves the launch without per-iteration arguments, so it can be replayed from a graph
-    for (int k = 0; k < 6; ++k) st->hw[k] = red[k];
-    for (int k = 0; k < 3; ++k) st->gw[k] = red[6 + k];
-    for (int k = 0; k < 3; ++k) st->tst[k] = red[9 + k];
-    st->prefs32_2 = red[12]; st->prefs64_2 = red[13];
     const int n = st->n_search;
     const double l2 = (double)st->lam * (double)st->lam;
     // symmetric index map (i<=j): 00->0 01->1 11->2 02->3 12->4 22->5
@@ -369,7 +372,9 @@ int nw_launch_mesh_prior(nw_ctx *h, bool write_dirs) {
 }
 
 int nw_launch_solve_update(nw_ctx *h, int iter_index, int last_step) {
-    k_solve<<<1, 256, 0, h->stream>>>(h->partials + (size_t)h->n_partials * 16, mesh_blocks(h), h->st, h->hist, iter_index);
+    k_fold_mesh<<<NW_MSUM, 256, 0, h->stream>>>(h->partials + (size_t)h->n_partials * 16, mesh_blocks(h), h->st);
+    NW_LAUNCH_CHECK();
+    k_solve<<<1, 32, 0, h->stream>>>(h->st, h->hist, iter_index);
     NW_LAUNCH_CHECK();
     k_update<<<mesh_blocks(h), 256, 0, h->stream>>>(h->M, h->st, h->posq, h->Sq, last_step, 0);
     NW_LAUNCH_CHECK();

@@ -902,28 +902,27 @@ __global__ void __launch_bounds__(256, NW_S2_MINB) k_sweep2(int64_t P, const int
     }
 }
 
-// fold the per-CTA partials in a fixed order into the solver state: one CTA, thread t sums partials t, t+256, ...
-// of each quantity, then a fixed shared-memory tree -- deterministic for a given P.
+// fold the per-CTA partials in a fixed order into the solver state: one CTA per quantity, thread t sums partials t, t+256, ...
+// of it, then a fixed shared-memory tree -- deterministic for a given P.  (One CTA looping over the quantities took 52 us at
+// C3: eleven dependent rounds of strided loads and barriers.)
 __global__ void __launch_bounds__(256) k_fold_partials(const double *__restrict__ partials, int n_blocks, SolverState *st) {
     if (st->stop) return;
     __shared__ double sh[256];
-    for (int k = 0; k < NW_NSUM; ++k) {
-        double v = 0.0;
-        for (int b = threadIdx.x; b < n_blocks; b += 256) v += partials[(size_t)b * NW_NSUM + k];
-        sh[threadIdx.x] = v;
+    const int k = blockIdx.x;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < n_blocks; b += 256) v += partials[(size_t)b * NW_NSUM + k];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
-        for (int o = 128; o; o >>= 1) {
-            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            const double t = sh[0];
-            if (k < 6) st->hc[k] = t;
-            else if (k < 9) st->gc[k - 6] = t;
-            else if (k == 9) st->c0 = t;
-            else st->res2 = t;
-        }
-        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double t = sh[0];
+        if (k < 6) st->hc[k] = t;
+        else if (k < 9) st->gc[k - 6] = t;
+        else if (k == 9) st->c0 = t;
+        else st->res2 = t;
     }
 }
 
@@ -1165,7 +1164,7 @@ int nw_launch_sweep2(nw_ctx *h) {
     k_sweep2<<<G, B, 0, h->stream>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->Sq,
                                       h->has_mask ? h->pmask : nullptr, h->st, h->partials);
     NW_LAUNCH_CHECK();
-    k_fold_partials<<<1, 256, 0, h->stream>>>(h->partials, G, h->st);
+    k_fold_partials<<<NW_NSUM, 256, 0, h->stream>>>(h->partials, G, h->st);
     NW_LAUNCH_CHECK();
     return NW_OK;
 }
