@@ -48,7 +48,8 @@ def test_product_path_fails_loudly_without_gpu():
 
 
 def test_sass_is_sm100a_and_has_no_float_atomics_in_the_adjoint():
-    """Cheap static evidence: the cubin targets sm_100a and the adjoint kernels use 64-bit integer REDs only."""
+    """Cheap static evidence: the cubin targets sm_100a, the adjoint kernels use 64-bit integer REDs only and form their
+    warp-level sums on the tensor cores."""
     from ch_shrinkwrap_b200 import build
     lib = build.build()
     r = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True)
@@ -56,10 +57,13 @@ def test_sass_is_sm100a_and_has_no_float_atomics_in_the_adjoint():
         pytest.skip('cuobjdump unavailable')
     assert 'sm_100a' in r.stdout
     blocks = r.stdout.split('Function : ')
-    adj = [b for b in blocks if 'k_apply_AH' in b.split('\n')[0] or 'k_sweep1' in b.split('\n')[0]]
+    adj = [b for b in blocks if 'k_adjoint' in b.split('\n')[0]]
     assert adj
     for b in adj:
-        assert '.F32' not in ''.join(l for l in b.split('\n') if 'RED' in l or 'ATOM' in l), 'float atomic in adjoint kernel'
-        name = b.split('\n')[0]
-        mode0 = 'k_sweep1' in name and 'ELi0E' in name          # nearest face + weights only: no adjoint in it
-        assert mode0 or any(('RED' in l or 'ATOM' in l) and '.64' in l for l in b.split('\n')), name
+        lines = b.split('\n')
+        assert '.F32' not in ''.join(l for l in lines if 'RED' in l or 'ATOM' in l), 'float atomic in adjoint kernel'
+        assert any(('RED' in l or 'ATOM' in l) and '.64' in l for l in lines), lines[0]
+        # the per-face sums of a warp are a u8 integer matrix product fed by the byte-transposing ldmatrix
+        assert any('IMMA.16832.U8.U8' in l for l in lines), lines[0]
+        assert any('LDSM' in l and 'MT1616' in l for l in lines), lines[0]
+        assert not any('REDUX' in l for l in lines), lines[0]

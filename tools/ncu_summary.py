@@ -23,7 +23,8 @@ WANT=['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','g
       'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
       'smsp__issue_active.avg.pct_of_peak_sustained_active','lts__t_sectors_op_red.sum','lts__t_sectors_op_atom.sum',
       'sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active','sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
-      'sm__cycles_active.avg','sm__cycles_active.max','sm__cycles_elapsed.avg']
+      'sm__cycles_active.avg','sm__cycles_active.max','sm__cycles_elapsed.avg',
+      'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active','l1tex__throughput.avg.pct_of_peak_sustained_elapsed','lts__throughput.avg.pct_of_peak_sustained_elapsed']
 
 def full(path):
     rows=list(csv.reader(open(path)))
