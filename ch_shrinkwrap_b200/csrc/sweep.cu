@@ -252,12 +252,35 @@ struct Traversal {
     // Depth-first search of the subtree rooted at node I.  First child and next sibling come from two small integer
     // tables, so no per-thread stack is needed.  Children are visited in index (= Hilbert) order: with a seed the bound
     // is already (nearly) exact, so nearest-first ordering would buy nothing.
+    // The node test of the walk: node_lb() in two stages.  Normal axis + first tangent axis need three of the node's four
+    // 16-byte quarters; if that partial sum (a lower bound of the full one: the third square only adds) already rules the
+    // node out for every lane, the fourth quarter is never loaded and the third axis never evaluated.  Otherwise the full
+    // bound is formed from the same partial sum, bit for bit what node_lb returns -- the walk opens exactly the same nodes.
+    __device__ __forceinline__ bool test_node(const Box *__restrict__ bp, int &link) {
+        const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), d4 = __ldg(&bp->d);
+        const float x = q.fx(), y = q.fy(), z = q.fz();
+        link = __float_as_int(d4.w);
+        const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
+        const float p1 = fmaf(d4.x, x, fmaf(d4.y, y, d4.z * z));
+        const float g0 = fmaxf(fmaxf(a.w - pn, pn - b.x), 0.f);
+        const float g1 = fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f);
+        const float s01 = __fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1));
+        if (!any(__fmul_rd(s01, 0.99999f) <= best.ub)) return false;
+        const float4 c = __ldg(&bp->c);
+        const float p2 = fmaf(c.y, x, fmaf(c.z, y, c.w * z));
+        const float g2 = fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f);
+        return any(__fmul_rd(__fadd_rd(s01, __fmul_rd(g2, g2)), 0.99999f) <= best.ub);
+    }
     __device__ __forceinline__ void dfs_subtree(int I) {
         int node = I;
         while (true) {
             int link;                                      // first child | (node is a last child) << 31, stored in the node itself
             if (tick()) return;
+#ifdef NW_ONE_STAGE_TEST
             const bool pass = any(node_lb(q, &tv.boxes[node], eps, &link) <= best.ub);
+#else
+            const bool pass = test_node(&tv.boxes[node], link);
+#endif
 #ifdef NW_LEVEL_STATS
             count_test(node, pass);
 #endif

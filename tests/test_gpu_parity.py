@@ -132,6 +132,41 @@ def test_forward_and_adjoint():
     assert np.allclose(g.point_influence(), pi_o, rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize('n_geo,n_points', [(1, 20000), (3, 20000), (6, 3000)])
+def test_adjoint_group_shapes(n_geo, n_points):
+    """The warp-level sums of the adjoint (csrc/sweep.cu: warp_adjoint_scatter) at their extremes: a coarse mesh puts all 32
+    points of a warp on one or two faces (one group, a 32-term byte column), a sparse cloud gives every lane its own face
+    (more than 16 groups: the second pass of the product).  Residuals are signed and span 12 orders of magnitude, so the
+    bias / byte split of negative and tiny terms is exercised.  Tolerance: the result is the exact sum of the fixed-point
+    terms rounded once to float32: |diff| <= 2^-23 |exact| + n_terms * 2^-37 * max|w r|  (terms are kept to 2^-38 of the
+    largest possible one, k_shift_final)."""
+    mesh, pts, sig = make_case(n_points=n_points, n_geo=n_geo, seed=40 + n_geo)
+    mo, mg = _clone(mesh), _clone(mesh)
+    oc = _oracle(mo, pts)
+    oc.f = oc.vertices.copy().ravel()
+    oc.w = oc.compute_weights(oc.f)
+    g = _gpu(mg, pts)
+    g.compute_weights()
+    rng = np.random.default_rng(n_geo)
+    r = (rng.standard_normal(3 * len(pts)) * 10.0 ** rng.uniform(-8, 4, 3 * len(pts))).astype(np.float32)
+    ah_g = g.Ahfunc(r).reshape(-1, 3).astype(np.float64)
+    v_idx, w = oc.w
+    prod = [(w[:, j][:, None] * r.reshape(-1, 3)).astype(np.float32).astype(np.float64) for j in range(3)]
+    ex = np.zeros((oc.M, 3))
+    cnt = np.zeros(oc.M)
+    for j in range(3):
+        np.add.at(ex, v_idx[:, j], prod[j])
+        np.add.at(cnt, v_idx[:, j], 1.0)
+    tol = 2.0 ** -23 * np.abs(ex) + (cnt[:, None] + 1.0) * 2.0 ** -37 * np.abs(r).max()
+    assert np.all(np.abs(ah_g - ex) <= tol)
+    # bitwise repeatable, and independent of the order the points were given in (integer sums)
+    assert np.array_equal(g.Ahfunc(r), g.Ahfunc(r))
+    perm = rng.permutation(len(pts))
+    g2 = _gpu(_clone(mesh), pts[perm])
+    g2.compute_weights()
+    assert np.array_equal(g2.Ahfunc(r.reshape(-1, 3)[perm].ravel()), g.Ahfunc(r))
+
+
 def test_determinism_adjoint_bitwise():
     mesh, pts, sig = make_case(n_points=30000, n_geo=6, seed=15)
     g = _gpu(mesh, pts)
