@@ -20,10 +20,18 @@
 // It only ever prunes: the answer never depends on how tight it is.  (A spherical shell fitted to each node, which
 // removes the sagitta of large curved patches, was implemented and measured at C3: -4 % node tests, +15 % per test.)
 struct Box {
-    float4 a;   // n.x n.y n.z | n-interval min
-    float4 b;   // n-interval max | t1-interval min, max | t2-interval min
-    float4 c;   // t2-interval max | t2.x t2.y t2.z
-    float4 d;   // t1.x t1.y t1.z | first child (leaf: first slot) | (node is a last child) << 31, as int bits
+    float4 a;   // n.x t1.x | n.y t1.y            the search decides most nodes from a, b, d alone (normal + first tangent axis,
+    float4 b;   // n.z t1.z | n-min t1-min        sweep.cu: test_node) and loads c only for the rest; the two axes are interleaved
+    float4 c;   // t2.x t2.y t2.z | t2-max        so that each (n, t1) pair is an aligned register pair (packed FFMA2 experiment)
+    float4 d;   // n-max t1-max | first child (leaf: first slot) | (node is a last child) << 31, as int bits | t2-min
+    __host__ __device__ __forceinline__ float3 normal() const { return make_float3(a.x, a.z, b.x); }
+    __host__ __device__ __forceinline__ float3 tan1() const { return make_float3(a.y, a.w, b.y); }
+    __host__ __device__ __forceinline__ float3 tan2() const { return make_float3(c.x, c.y, c.z); }
+    // interval ends: axis 0 = normal, 1 = t1, 2 = t2
+    __host__ __device__ __forceinline__ float *lo(int k) { return k == 0 ? &b.z : k == 1 ? &b.w : &d.w; }
+    __host__ __device__ __forceinline__ float *hi(int k) { return k == 0 ? &d.x : k == 1 ? &d.y : &c.w; }
+    __host__ __device__ __forceinline__ float lo(int k) const { return k == 0 ? b.z : k == 1 ? b.w : d.w; }
+    __host__ __device__ __forceinline__ float hi(int k) const { return k == 0 ? d.x : k == 1 ? d.y : c.w; }
 };              // 64 B
 
 // orthonormal completion of a unit vector (Duff et al. 2017, branchless): returns t1; t2 = n x t1 everywhere.

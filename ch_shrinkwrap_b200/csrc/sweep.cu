@@ -83,9 +83,34 @@ struct Nearest {
     int slot, face;
     __device__ __forceinline__ void offer(double v, int s, int f) {
         // strict minimum; exact fp64 ties -> lowest face index (contract of SURVEY 7.3)
-        if (v < d2 || (v == d2 && f < face)) { d2 = v; slot = s; face = f; ub = __double2float_ru(v); }
+        // ub carries the relative 1.1e-5 that the box tests owe to the float32 orthonormality of the node frames (it used to
+        // be a multiply by 0.99999 in every node test); a larger bound only ever prunes less
+        if (v < d2 || (v == d2 && f < face)) { d2 = v; slot = s; face = f; ub = __fmul_ru(__double2float_ru(v), 1.000011f); }
     }
 };
+
+// packed float32 pairs (sm_100a: FFMA2 / FMUL2 / FADD2 take an aligned 64-bit register pair and, for one source, a scalar
+// broadcast): two IEEE operations per instruction.  Only used with -DNW_PACKED_NODE_TEST (tools/build_variant.sh): measured at
+// C3, the packed stage-1 node test is 6 instructions shorter (23 instead of 29) and the warm sweep 3 % SLOWER (1.85 vs 1.79
+// ms) -- on B200 a packed instruction evidently occupies the FMA pipe for both halves, and the kernel's dependent chain per
+// step gets longer.  The box layout (both axes interleaved) is what that experiment needed; the scalar test does not care.
+__device__ __forceinline__ unsigned long long f2_pack(float2 v) { unsigned long long r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(v.x), "f"(v.y)); return r; }
+__device__ __forceinline__ float2 f2_unpack(unsigned long long v) { float2 r; asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ float2 f2_fma(float2 a, float s, float2 c) {          // a * s + c, one rounding per component
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(make_float2(s, s))), "l"(f2_pack(c)));
+    return f2_unpack(r);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float s) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(make_float2(s, s))));
+    return f2_unpack(r);
+}
+__device__ __forceinline__ float2 f2_sub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+}
 
 // Conservative lower bound of the squared distance from the query to anything inside a node: the sum over the three
 // box axes of (interval gap)^2.  Projections are float32, so every interval is widened by an absolute slack (>= 4x the worst-case rounding error of
@@ -98,19 +123,16 @@ struct Nearest {
 // them at every optimisation level; an opaque per-thread copy of the address does not change the allocation at 32 registers.)
 template <typename Q>
 __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps, int *link = nullptr) {
-    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
-    const float4 d4 = __ldg(&bp->d);                 // the fourth quarter of the node stores t1 ...
+    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c), d = __ldg(&bp->d);
     const float x = q.fx(), y = q.fy(), z = q.fz();
-    const float3 t1 = make_float3(d4.x, d4.y, d4.z);
-    if (link) *link = __float_as_int(d4.w);          // ... and first child | last-child flag (k_global_tables)
-    const float t2x = c.y, t2y = c.z, t2z = c.w;     // t2 = n x t1
-    const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
-    const float p1 = fmaf(t1.x, x, fmaf(t1.y, y, t1.z * z));
-    const float p2 = fmaf(t2x, x, fmaf(t2y, y, t2z * z));
+    if (link) *link = __float_as_int(d.z);           // first child | last-child flag (k_global_tables)
+    const float pn = fmaf(a.x, x, fmaf(a.z, y, b.x * z));
+    const float p1 = fmaf(a.y, x, fmaf(a.w, y, b.y * z));
+    const float p2 = fmaf(c.x, x, fmaf(c.y, y, c.z * z));      // t2 = n x t1
     // the stored intervals are already widened by the rounding slack (k_box_decode)
-    const float g0 = fmaxf(fmaxf(a.w - pn, pn - b.x), 0.f);
-    const float g1 = fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f);
-    const float g2 = fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f);
+    const float g0 = fmaxf(fmaxf(b.z - pn, pn - d.x), 0.f);
+    const float g1 = fmaxf(fmaxf(b.w - p1, p1 - d.y), 0.f);
+    const float g2 = fmaxf(fmaxf(d.w - p2, p2 - c.w), 0.f);
     const float lb = __fadd_rd(__fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1)), __fmul_rd(g2, g2));
     return __fmul_rd(lb, 0.99999f);
 }
@@ -119,16 +141,14 @@ __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp,
 // boxes can contain the query and all have bound 0)
 template <typename Q>
 __device__ __forceinline__ float node_score(const Q &q, const Box *__restrict__ bp, float eps) {
-    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c);
+    const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c), d = __ldg(&bp->d);
     const float x = q.fx(), y = q.fy(), z = q.fz();
-    const float3 t1 = nw_tangent_of(a.x, a.y, a.z);
-    const float t2x = a.y * t1.z - a.z * t1.y, t2y = a.z * t1.x - a.x * t1.z, t2z = a.x * t1.y - a.y * t1.x;
-    const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
-    const float p1 = fmaf(t1.x, x, fmaf(t1.y, y, t1.z * z));
-    const float p2 = fmaf(t2x, x, fmaf(t2y, y, t2z * z));
-    const float g0 = fmaxf(fmaxf(a.w - pn, pn - b.x), 0.f), g1 = fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f),
-                g2 = fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f);
-    const float c0 = pn - 0.5f * (a.w + b.x), c1 = p1 - 0.5f * (b.y + b.z), c2 = p2 - 0.5f * (b.w + c.x);
+    const float pn = fmaf(a.x, x, fmaf(a.z, y, b.x * z));
+    const float p1 = fmaf(a.y, x, fmaf(a.w, y, b.y * z));
+    const float p2 = fmaf(c.x, x, fmaf(c.y, y, c.z * z));
+    const float g0 = fmaxf(fmaxf(b.z - pn, pn - d.x), 0.f), g1 = fmaxf(fmaxf(b.w - p1, p1 - d.y), 0.f),
+                g2 = fmaxf(fmaxf(d.w - p2, p2 - c.w), 0.f);
+    const float c0 = pn - 0.5f * (b.z + d.x), c1 = p1 - 0.5f * (b.w + d.y), c2 = p2 - 0.5f * (d.w + c.w);
     return (g0 * g0 + g1 * g1 + g2 * g2) + 1e-4f * (c0 * c0 + c1 * c1 + c2 * c2);
 }
 
@@ -255,21 +275,27 @@ struct Traversal {
     // The node test of the walk: node_lb() in two stages.  Normal axis + first tangent axis need three of the node's four
     // 16-byte quarters; if that partial sum (a lower bound of the full one: the third square only adds) already rules the
     // node out for every lane, the fourth quarter is never loaded and the third axis never evaluated.  Otherwise the full
-    // bound is formed from the same partial sum, bit for bit what node_lb returns -- the walk opens exactly the same nodes.
+    // bound is formed from the same partial sum: the same nodes are opened as with a one-stage test.
     __device__ __forceinline__ bool test_node(const Box *__restrict__ bp, int &link) {
-        const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), d4 = __ldg(&bp->d);
+        const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), d = __ldg(&bp->d);
         const float x = q.fx(), y = q.fy(), z = q.fz();
-        link = __float_as_int(d4.w);
-        const float pn = fmaf(a.x, x, fmaf(a.y, y, a.z * z));
-        const float p1 = fmaf(d4.x, x, fmaf(d4.y, y, d4.z * z));
-        const float g0 = fmaxf(fmaxf(a.w - pn, pn - b.x), 0.f);
-        const float g1 = fmaxf(fmaxf(b.y - p1, p1 - b.z), 0.f);
-        const float s01 = __fadd_rd(__fmul_rd(g0, g0), __fmul_rd(g1, g1));
-        if (!any(__fmul_rd(s01, 0.99999f) <= best.ub)) return false;
+        link = __float_as_int(d.z);
+        // (pn, p1) = (n, t1) . q ; same operations and association as node_lb
+#ifdef NW_PACKED_NODE_TEST
+        const float2 p = f2_fma(make_float2(a.x, a.y), x, f2_fma(make_float2(a.z, a.w), y, f2_mul(make_float2(b.x, b.y), z)));
+        const float2 glo = f2_sub(make_float2(b.z, b.w), p), ghi = f2_sub(p, make_float2(d.x, d.y));
+        const float g0 = fmaxf(fmaxf(glo.x, ghi.x), 0.f), g1 = fmaxf(fmaxf(glo.y, ghi.y), 0.f);
+#else
+        const float pn = fmaf(a.x, x, fmaf(a.z, y, b.x * z));
+        const float p1 = fmaf(a.y, x, fmaf(a.w, y, b.y * z));
+        const float g0 = fmaxf(fmaxf(b.z - pn, pn - d.x), 0.f), g1 = fmaxf(fmaxf(b.w - p1, p1 - d.y), 0.f);
+#endif
+        const float s01 = __fmaf_rd(g1, g1, __fmul_rd(g0, g0));            // <= g0^2 + g1^2
+        if (!any(s01 <= best.ub)) return false;                     // (best.ub already holds the frames' 1e-5, Nearest::offer)
         const float4 c = __ldg(&bp->c);
-        const float p2 = fmaf(c.y, x, fmaf(c.z, y, c.w * z));
-        const float g2 = fmaxf(fmaxf(b.w - p2, p2 - c.x), 0.f);
-        return any(__fmul_rd(__fadd_rd(s01, __fmul_rd(g2, g2)), 0.99999f) <= best.ub);
+        const float p2 = fmaf(c.x, x, fmaf(c.y, y, c.z * z));
+        const float g2 = fmaxf(fmaxf(d.w - p2, p2 - c.w), 0.f);
+        return any(__fmaf_rd(g2, g2, s01) <= best.ub);
     }
     __device__ __forceinline__ void dfs_subtree(int I) {
         int node = I;

@@ -275,12 +275,12 @@ __global__ void k_node_frames(Box *__restrict__ boxes, const float *__restrict__
     const float nn = sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
     n = (nn > 1e-20f && nn <= FLT_MAX) ? make_float3(n.x / nn, n.y / nn, n.z / nn) : make_float3(0.f, 0.f, 1.f);
     Box *b = &boxes[first + j];
-    b->a = make_float4(n.x, n.y, n.z, NW_EMPTY_LO);
-    b->b = make_float4(NW_EMPTY_HI, NW_EMPTY_LO, NW_EMPTY_HI, NW_EMPTY_LO);
-    b->c = make_float4(NW_EMPTY_HI, 0.f, 0.f, 0.f);
     const float3 t1 = nw_tangent_of(n.x, n.y, n.z);
-    b->c.y = n.y * t1.z - n.z * t1.y; b->c.z = n.z * t1.x - n.x * t1.z; b->c.w = n.x * t1.y - n.y * t1.x;   // t2, exactly as project3 forms it
-    b->d = make_float4(t1.x, t1.y, t1.z, 0.f);       // d.w: the search's link, written by k_global_tables
+    b->a = make_float4(n.x, t1.x, n.y, t1.y);
+    b->b = make_float4(n.z, t1.z, NW_EMPTY_LO, NW_EMPTY_LO);
+    // t2 = n x t1, exactly as project3 forms it
+    b->c = make_float4(n.y * t1.z - n.z * t1.y, n.z * t1.x - n.x * t1.z, n.x * t1.y - n.y * t1.x, NW_EMPTY_HI);
+    b->d = make_float4(NW_EMPTY_HI, NW_EMPTY_HI, 0.f, NW_EMPTY_LO);      // d.z: the search's link, written by k_global_tables
 }
 
 // every iteration: intervals back to "empty" (frames are kept for the whole block)
@@ -288,7 +288,7 @@ __global__ void k_reset_extents(Box *__restrict__ boxes, int first, int count) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
     Box *b = &boxes[first + j];
-    b->a.w = NW_EMPTY_LO; b->b.x = NW_EMPTY_HI; b->b.y = NW_EMPTY_LO; b->b.z = NW_EMPTY_HI; b->b.w = NW_EMPTY_LO; b->c.x = NW_EMPTY_HI;
+    b->b.z = NW_EMPTY_LO; b->b.w = NW_EMPTY_LO; b->d.w = NW_EMPTY_LO; b->d.x = NW_EMPTY_HI; b->d.y = NW_EMPTY_HI; b->c.w = NW_EMPTY_HI;
 }
 
 // every iteration: each centroid projects onto the frame of every ancestor; lanes of a warp that
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent
         float p[3] = {0.f, 0.f, 0.f};
         if (live) {
             const float4 ba = b->a;
-            project3(make_float3(ba.x, ba.y, ba.z), c, p[0], p[1], p[2]);
+            project3(make_float3(ba.x, ba.z, b->b.x), c, p[0], p[1], p[2]);
         }
         unsigned mn[3], mx[3];
 #pragma unroll
@@ -326,13 +326,14 @@ __global__ void __launch_bounds__(256) k_extents(const float4 *__restrict__ cent
         if (live && lane == (unsigned)first && mn[0] <= mx[0]) {
             // the upper levels are hit by thousands of warps and all but the first few change nothing: look first
             // (an L2 read; a stale value only costs a redundant atomic, the atomics themselves are monotone)
-            const float4 ca = __ldcg(&b->a), cb = __ldcg(&b->b), cc = __ldcg(&b->c);
-            if (u2ord(mn[0]) < __float_as_int(ca.w)) atomicMin((int *)&b->a.w, u2ord(mn[0]));
-            if (u2ord(mx[0]) > __float_as_int(cb.x)) atomicMax((int *)&b->b.x, u2ord(mx[0]));
-            if (u2ord(mn[1]) < __float_as_int(cb.y)) atomicMin((int *)&b->b.y, u2ord(mn[1]));
-            if (u2ord(mx[1]) > __float_as_int(cb.z)) atomicMax((int *)&b->b.z, u2ord(mx[1]));
-            if (u2ord(mn[2]) < __float_as_int(cb.w)) atomicMin((int *)&b->b.w, u2ord(mn[2]));
-            if (u2ord(mx[2]) > __float_as_int(cc.x)) atomicMax((int *)&b->c.x, u2ord(mx[2]));
+            const float4 cb = __ldcg(&b->b), cd = __ldcg(&b->d);
+            const float ch2 = __ldcg(&b->c.w);
+            if (u2ord(mn[0]) < __float_as_int(cb.z)) atomicMin((int *)&b->b.z, u2ord(mn[0]));
+            if (u2ord(mx[0]) > __float_as_int(cd.x)) atomicMax((int *)&b->d.x, u2ord(mx[0]));
+            if (u2ord(mn[1]) < __float_as_int(cb.w)) atomicMin((int *)&b->b.w, u2ord(mn[1]));
+            if (u2ord(mx[1]) > __float_as_int(cd.y)) atomicMax((int *)&b->d.y, u2ord(mx[1]));
+            if (u2ord(mn[2]) < __float_as_int(cd.w)) atomicMin((int *)&b->d.w, u2ord(mn[2]));
+            if (u2ord(mx[2]) > __float_as_int(ch2)) atomicMax((int *)&b->c.w, u2ord(mx[2]));
         }
         if (live) node = par[tl.off[l] + node] & 0x7fffffff;
     }
@@ -345,9 +346,9 @@ __global__ void k_box_decode(Box *__restrict__ boxes, int first, int count, cons
     if (i >= count) return;
     const float w = st->coord_l1 * 1.9073486328125e-6f;
     Box *b = &boxes[first + i];
-    b->a.w = ord2f(__float_as_int(b->a.w)) - w; b->b.x = ord2f(__float_as_int(b->b.x)) + w;
-    b->b.y = ord2f(__float_as_int(b->b.y)) - w; b->b.z = ord2f(__float_as_int(b->b.z)) + w;
-    b->b.w = ord2f(__float_as_int(b->b.w)) - w; b->c.x = ord2f(__float_as_int(b->c.x)) + w;
+    b->b.z = ord2f(__float_as_int(b->b.z)) - w; b->d.x = ord2f(__float_as_int(b->d.x)) + w;
+    b->b.w = ord2f(__float_as_int(b->b.w)) - w; b->d.y = ord2f(__float_as_int(b->d.y)) + w;
+    b->d.w = ord2f(__float_as_int(b->d.w)) - w; b->c.w = ord2f(__float_as_int(b->c.w)) + w;
 }
 
 #define NW_NMOM 3        // floats per node of the build scratch (area-weighted normal sum)
@@ -385,7 +386,7 @@ extern "C" int nw_set_topology_records(nw_ctx *h, const void *vertex_records, co
 
 // The per-level tables (local indices, what the build and refit kernels use) rewritten with global node ids for the
 // search:  kids = {first child (global) or first slot, count};  parent_g = global parent | (the PARENT is the last child
-// of ITS parent) << 31, so that popping a level is one load;  and inside the node itself (Box::d.w) first child / first slot | (this node is a last child) << 31 -- what a search step needs next, whether the
+// of ITS parent) << 31, so that popping a level is one load;  and inside the node itself (Box::d.z) first child / first slot | (this node is a last child) << 31 -- what a search step needs next, whether the
 // node is pruned (next sibling or pop) or opened (first child), arrives with the box it has just loaded.
 __global__ void k_global_tables(const int *__restrict__ par, const int *__restrict__ cbegin_level, int count, int off, int off_parent,
                                 int off_child, bool is_leaf_level, int *__restrict__ parent_g, int2 *__restrict__ kids,
@@ -399,7 +400,7 @@ __global__ void k_global_tables(const int *__restrict__ par, const int *__restri
     const int c0 = cbegin_level[i], c1 = cbegin_level[i + 1];
     const int first = is_leaf_level ? c0 : off_child + c0;
     kids[off + i] = make_int2(first, c1 - c0);
-    boxes[off + i].d.w = __int_as_float((int)((unsigned)first | ((unsigned)pv & 0x80000000u)));
+    boxes[off + i].d.z = __int_as_float((int)((unsigned)first | ((unsigned)pv & 0x80000000u)));
 }
 
 // NW_TRACE_BUILD=1: wall-clock checkpoints (with a stream sync each) through nw_tree_build, on stderr

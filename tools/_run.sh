@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py 2>&1 | tail -3
-echo "== trace"; python tools/trace_probe.py c3 2 2>&1 | grep -E "it |total|crc"
-python tools/kernel_probe.py sweep1 curvature
+echo "== scalar, new layout"; python tools/trace_probe.py c3 2 2>&1 | grep -E "it |total|crc"
+echo "== packed"; NANOWRAP_LIB=$PWD/ch_shrinkwrap_b200/libnanowrap_packed.so python tools/trace_probe.py c3 2 2>&1 | grep -E "it |total|crc"

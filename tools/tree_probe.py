@@ -15,4 +15,5 @@ for lvl in range(1, min(nl.value,5)):
     print('level', lvl)
     for k in range(min(n,8)):
         r=b[k]
-        print('  n=(%.2f %.2f %.2f) ext n[%.0f,%.0f] t1[%.0f,%.0f] t2[%.0f,%.0f] o=(%.0f %.0f %.0f) r[%.1f,%.1f] shell=%d'%(r[0],r[1],r[2],r[3],r[4],r[5],r[6],r[7],r[8],r[9],r[10],r[11],r[12],min(r[13],1e9),r[14]))
+        # Box layout (csrc/common.cuh): a = n.x t1.x n.y t1.y | b = n.z t1.z n-min t1-min | c = t2.xyz t2-max | d = n-max t1-max link t2-min
+        print('  n=(%.2f %.2f %.2f) ext n[%.0f,%.0f] t1[%.0f,%.0f] t2[%.0f,%.0f]' % (r[0], r[2], r[4], r[6], r[12], r[7], r[13], r[15], r[11]))
