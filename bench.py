@@ -423,6 +423,12 @@ def main():
         allc = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allc, t)
         ranks_identical = bool(all(int(c.item()) == crc for c in allc))
+        # how evenly the sweep is spread: every rank's own total of the two per-point stages over the timed window
+        ts = torch.tensor([stage_ms[2] + stage_ms[10], stage_ms[5]], dtype=torch.float64, device='cuda')
+        allt = [torch.zeros_like(ts) for _ in range(world)]
+        dist.all_gather(allt, ts)
+        sweep_by_rank = [round(float(t[0].item()) / K, 4) for t in allt]
+        sweep2_by_rank = [round(float(t[1].item()) / K, 4) for t in allt]
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
@@ -447,6 +453,7 @@ def main():
     }
     if ranks_identical is not None:
         line['ranks_bit_identical'] = ranks_identical
+        line['per_rank_ms_per_step'] = {'sweep1_plus_adjoint': sweep_by_rank, 'sweep2': sweep2_by_rank}
     print(json.dumps(line))
 
 

@@ -94,6 +94,7 @@ struct Nearest {
 // C3, the packed stage-1 node test is 6 instructions shorter (23 instead of 29) and the warm sweep 3 % SLOWER (1.85 vs 1.79
 // ms) -- on B200 a packed instruction evidently occupies the FMA pipe for both halves, and the kernel's dependent chain per
 // step gets longer.  The box layout (both axes interleaved) is what that experiment needed; the scalar test does not care.
+#ifdef NW_PACKED_NODE_TEST
 __device__ __forceinline__ unsigned long long f2_pack(float2 v) { unsigned long long r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(v.x), "f"(v.y)); return r; }
 __device__ __forceinline__ float2 f2_unpack(unsigned long long v) { float2 r; asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
 __device__ __forceinline__ float2 f2_fma(float2 a, float s, float2 c) {          // a * s + c, one rounding per component
@@ -111,6 +112,7 @@ __device__ __forceinline__ float2 f2_sub(float2 a, float2 b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
     return f2_unpack(r);
 }
+#endif
 
 // Conservative lower bound of the squared distance from the query to anything inside a node: the sum over the three
 // box axes of (interval gap)^2.  Projections are float32, so every interval is widened by an absolute slack (>= 4x the worst-case rounding error of

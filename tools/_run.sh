@@ -1,3 +1,5 @@
 cd $GRAFT_REPO_ROOT
-echo "== scalar, new layout"; python tools/trace_probe.py c3 2 2>&1 | grep -E "it |total|crc"
-echo "== packed"; NANOWRAP_LIB=$PWD/ch_shrinkwrap_b200/libnanowrap_packed.so python tools/trace_probe.py c3 2 2>&1 | grep -E "it |total|crc"
+timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gputest_13.txt 2>&1; tail -3 gpurun_out/r2_gputest_13.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_c3_v3.json 2> gpurun_out/r2_bench_c3_v3.err; python -c "
+import json; d=json.load(open('gpurun_out/r2_bench_c3_v3.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['gpu_launches']); print({k:round(v['ms_total']/d['steps'],3) for k,v in d['stages'].items()}); print({k:(round(v.get('ms',0),4),round(v.get('frac',0),3)) for k,v in d['kernels'].items()})"
