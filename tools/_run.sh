@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-python tools/shard_probe3.py 2>&1 | grep -E "cubes|Error"
+python tools/deep_probe.py 2>&1 | grep -E "slab|without|quantiles|Error"
