@@ -1,6 +1,7 @@
 // api.cu -- handle lifetime and the search() driver: all kernels of all iterations are enqueued on
 // one stream without host round trips; the stop rule, NaN guard and histories live on the device and
 // are read back once at the end (the reference's loop is mesh_conj_grad.py:218-290).
+#include <nvtx3/nvToolsExt.h>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -90,8 +91,12 @@ static int upload_state(nw_ctx *h, const SolverState &s0) {
     return NW_OK;
 }
 
-// per-stage CUDA events (only when profiling is switched on)
+// per-stage NVTX ranges (profile bit 4: `ncu --nvtx --nvtx-include "sweep1/"` then selects a stage; without an attached tool
+// the header-only NVTX calls are no-ops) and per-stage CUDA events (profile bit 1)
+static const char *const kStageName[NW_N_STAGES] = {"refit", "shift", "sweep1", "allreduce_acc", "mesh_prior", "sweep2",
+                                                    "allreduce_scalars", "solve_update", "seed_leaders", "topology_build", "adjoint"};
 static int stage_begin(nw_ctx *h, int stage) {
+    if (h->profile & 4) nvtxRangePushA(kStageName[stage]);
     if (!(h->profile & 1)) return NW_OK;
     if (h->ev_used + 2 > h->ev_pool.size()) {
         for (int k = 0; k < 64; ++k) { cudaEvent_t e; NW_CUDA(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
@@ -102,6 +107,7 @@ static int stage_begin(nw_ctx *h, int stage) {
     return NW_OK;
 }
 static int stage_end(nw_ctx *h, int stage) {
+    if (h->profile & 4) nvtxRangePop();
     if (!(h->profile & 1)) return NW_OK;
     NW_CUDA(cudaEventRecord(h->ev_pool[h->ev_used++], h->stream));
     h->stage_launches[stage] += h->launches;

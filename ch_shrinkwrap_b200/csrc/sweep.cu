@@ -119,10 +119,9 @@ __device__ __forceinline__ float2 f2_sub(float2 a, float2 b) {
 // both the query's and the members' evaluation, DESIGN.md "exactness") and the squares by a relative 1e-5 (axes are
 // orthonormal only to float32 accuracy).  A node is skipped only if this bound exceeds the best exact fp64 distance,
 // so skipping can never change the answer.
-// (Measured dead ends for the instruction count of a step, ~38 in SASS: two 256-bit loads per 64-byte node,
-// ld.global.nc.v8.f32 = LDG.E.256 on sm_100a, would save six -- each of the four 128-bit loads also costs two moves of the
-// warp-uniform node address into the vector registers it is about to overwrite -- but ptxas 12.9 segfaults on this file with
-// them at every optimisation level; an opaque per-thread copy of the address does not change the allocation at 32 registers.)
+// (The walk itself uses the two-stage form of this test, Traversal::test_node.  Each 128-bit load of a node quarter also
+// costs two moves of the warp-uniform node address into the vector registers it is about to overwrite; an opaque per-thread
+// copy of the address does not change that allocation at 32 registers, and 256-bit loads do not pay either -- see test_node.)
 template <typename Q>
 __device__ __forceinline__ float node_lb(const Q &q, const Box *__restrict__ bp, float eps, int *link = nullptr) {
     const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), c = __ldg(&bp->c), d = __ldg(&bp->d);
@@ -279,7 +278,24 @@ struct Traversal {
     // node out for every lane, the fourth quarter is never loaded and the third axis never evaluated.  Otherwise the full
     // bound is formed from the same partial sum: the same nodes are opened as with a one-stage test.
     __device__ __forceinline__ bool test_node(const Box *__restrict__ bp, int &link) {
+#ifdef NW_LDG256
+        // quarters a and b with ONE 256-bit load (LDG.E.ENL2.256 on sm_100a; the v4.b64 spelling -- ptxas 12.9 segfaults on
+        // ld.global.nc.v8.f32 in this file).  Measured at C3: one instruction and two address moves less per test, and the
+        // warm sweep does not move (1.80 vs 1.80 ms); loading c and d the same way costs registers the kernel does not
+        // have (spills, 3.4 ms)
+        float4 a, b;
+        {
+            unsigned long long v0, v1, v2, v3;
+            asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(bp));
+            a.x = __uint_as_float((unsigned)v0); a.y = __uint_as_float((unsigned)(v0 >> 32));
+            a.z = __uint_as_float((unsigned)v1); a.w = __uint_as_float((unsigned)(v1 >> 32));
+            b.x = __uint_as_float((unsigned)v2); b.y = __uint_as_float((unsigned)(v2 >> 32));
+            b.z = __uint_as_float((unsigned)v3); b.w = __uint_as_float((unsigned)(v3 >> 32));
+        }
+        const float4 d = __ldg(&bp->d);
+#else
         const float4 a = __ldg(&bp->a), b = __ldg(&bp->b), d = __ldg(&bp->d);
+#endif
         const float x = q.fx(), y = q.fy(), z = q.fz();
         link = __float_as_int(d.z);
         // (pn, p1) = (n, t1) . q ; same operations and association as node_lb

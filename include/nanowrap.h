@@ -180,10 +180,11 @@ int nw_reset_seeds(nw_ctx *h);
 int nw_sync(nw_ctx *h);
 /* CUDA-event timing on the handle's stream: on & 1 brackets every stage of every iteration inside
  * nw_search and the device-side segments of nw_set_topology*.  nw_get_profile returns accumulated ms and kernel
- * launches per stage (10 stages: refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars,
+ * launches per stage (11 stages: refit, shift, sweep1, allreduce_acc, mesh_prior, sweep2, allreduce_scalars,
  * solve_update, seed_leaders, topology_build = foot points + record unpack + Hilbert sort + octree tables + frames of
- * every upload, host->device copies excluded) and the event-timed duration of the last nw_search call (first kernel to
- * last kernel). */
+ * every upload, host->device copies excluded, adjoint; the arrays must hold 16 entries) and the event-timed duration of
+ * the last nw_search call (first kernel to last kernel).  on & 2: traversal statistics (below).  on & 4: an NVTX range
+ * named after the stage around every stage of nw_search (for ncu --nvtx / nsys; no-ops without an attached tool). */
 int nw_set_profile(nw_ctx *h, int on);
 int nw_get_profile(nw_ctx *h, double *stage_ms, int64_t *stage_launches, double *search_ms);
 /* the stage intervals of the last profiled nw_search call in launch order: stage[k] (index into the list above), ms[k];
