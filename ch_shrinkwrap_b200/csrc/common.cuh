@@ -19,6 +19,16 @@
 // axis-aligned box is mostly empty space.  Axes n (patch normal), t1 = tangent_of(n), t2 = n x t1; one interval per axis.
 // It only ever prunes: the answer never depends on how tight it is.  (A spherical shell fitted to each node, which
 // removes the sagitta of large curved patches, was implemented and measured at C3: -4 % node tests, +15 % per test.)
+// -DNW_BOUNDS_CHECK (tools/build_variant.sh bounds "-DNW_BOUNDS_CHECK"): device-side assertions on every index the search
+// and the adjoint scatter form -- node ids, slots, vertex ids, shared-memory rows.  compute-sanitizer is closed on the GPU
+// pool this was developed on; the -m gpu suite run against that build is the memory-safety evidence (profiles/).
+#ifdef NW_BOUNDS_CHECK
+#include <cassert>
+#define NW_ASSERT(c) assert(c)
+#else
+#define NW_ASSERT(c) ((void)0)
+#endif
+
 struct Box {
     float4 a;   // n.x t1.x | n.y t1.y            the search decides most nodes from a, b, d alone (normal + first tangent axis,
     float4 b;   // n.z t1.z | n-min t1-min        sweep.cu: test_node) and loads c only for the rest; the two axes are interleaved

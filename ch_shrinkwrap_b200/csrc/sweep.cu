@@ -168,6 +168,7 @@ struct TreeView {
     float3 grid_lo;                        // the 1024^3 grid of those keys: g = (p - grid_lo) * grid_inv
     float grid_inv, grid_cellw;            // cells per nm, nm per cell (0 when the mesh has no extent)
     int leaf0, leaf_level;                 // global id of the first leaf; its level (= number of climb steps to the root)
+    int n_nodes, n_slots;                  // sizes of boxes[] / cent[] (bounds assertions only)
 };
 
 //
@@ -252,7 +253,9 @@ struct Traversal {
     }
 
     __device__ __forceinline__ void leaf(int node) {
+        NW_ASSERT(node >= tv.leaf0 && node < tv.n_nodes);
         const int2 k = __ldg(&tv.kids[node]);
+        NW_ASSERT(k.x >= 0 && k.y >= 0 && k.x + k.y <= tv.n_slots);
         if constexpr (COUNT) ++n_leaves;
         for (int s = k.x; s < k.x + k.y; ++s) {
             const float4 c = __ldg(&tv.cent[s]);
@@ -278,6 +281,7 @@ struct Traversal {
     // node out for every lane, the fourth quarter is never loaded and the third axis never evaluated.  Otherwise the full
     // bound is formed from the same partial sum: the same nodes are opened as with a one-stage test.
     __device__ __forceinline__ bool test_node(const Box *__restrict__ bp, int &link) {
+        NW_ASSERT(bp >= tv.boxes && bp < tv.boxes + tv.n_nodes);
 #ifdef NW_LDG256
         // quarters a and b with ONE 256-bit load (LDG.E.ENL2.256 on sm_100a; the v4.b64 spelling -- ptxas 12.9 segfaults on
         // ld.global.nc.v8.f32 in this file).  Measured at C3: one instruction and two address moves less per test, and the
@@ -456,7 +460,8 @@ __device__ __forceinline__ void adj_fixed(float v, float scale, unsigned bias, u
 template <bool INFL>
 __device__ __forceinline__ void warp_adjoint_scatter(AdjWarpSmem &sm, bool active, int key, const int4 *__restrict__ sfaces,
                                                      const float (&uw)[3], float r_x, float r_y, float r_z, float scale,
-                                                     float scale_i, unsigned long long *__restrict__ acc) {
+                                                     float scale_i, unsigned long long *__restrict__ acc, int n_vertices, int n_faces) {
+    NW_ASSERT(!active || (key >= 0 && key < n_faces));
     const int lane = threadIdx.x & 31;
     // ---- this lane's row of V ----
     unsigned S[4][4];                      // [component][word of its 16-byte stream]
@@ -500,6 +505,7 @@ __device__ __forceinline__ void warp_adjoint_scatter(AdjWarpSmem &sm, bool activ
     // the corner ids of a group's face: one gather per group, needed only by the epilogue -- its latency (the second of the
     // dependent chain slot -> face) hides behind the product
     int4 sf = make_int4(0, 0, 0, 0);
+    NW_ASSERT(gid >= 0 && gid < 32 && ngroups >= 1 && ngroups <= 32);
     if (lane == leader && active) sf = __ldg(&sfaces[key]);
     __syncwarp();
     const int g = lane >> 2, t = lane & 3;
@@ -513,6 +519,7 @@ __device__ __forceinline__ void warp_adjoint_scatter(AdjWarpSmem &sm, bool activ
     // stream byte k of a component sits in n-tile k / 2, accumulator register 2 half + k % 2
     auto emit = [&](int q, int half, int ng, const int4 &f, unsigned s0, unsigned s1, unsigned s2, unsigned s3, unsigned s4) {
         const int vid = q == 0 ? f.x : q == 1 ? f.y : f.z;
+        NW_ASSERT(vid >= 0 && vid < n_vertices);
         const unsigned long long v = (unsigned long long)(s0 + (s1 << 8) + (s2 << 16)) + ((unsigned long long)s3 << 24) +
                                      ((unsigned long long)(s4 - ((unsigned)ng << 7)) << 32);      // minus ng * 2^39
         atomicAdd(acc + 4 * (size_t)vid + t, v);
@@ -850,7 +857,8 @@ template <bool INFL>
 __global__ void __launch_bounds__(256, NW_ADJ_MINB) k_adjoint(int64_t P, const int *__restrict__ slot, const int4 *__restrict__ sfaces,
                                                  const float *__restrict__ w0, const float *__restrict__ w1, const float *__restrict__ w2,
                                                  const float *__restrict__ rx, const float *__restrict__ ry, const float *__restrict__ rz,
-                                                 unsigned long long *__restrict__ acc, const SolverState *__restrict__ st, int shift, int shift_i) {
+                                                 unsigned long long *__restrict__ acc, const SolverState *__restrict__ st, int shift, int shift_i,
+                                                 int n_vertices, int n_faces) {
     __shared__ __align__(16) AdjWarpSmem sm[8];
     int sl[NW_ADJ_TILES];
     float uw[NW_ADJ_TILES][3], r[NW_ADJ_TILES][3];
@@ -876,7 +884,7 @@ __global__ void __launch_bounds__(256, NW_ADJ_MINB) k_adjoint(int64_t P, const i
 #pragma unroll
     for (int k = 0; k < NW_ADJ_TILES; ++k) {
         if (k) __syncwarp();           // the warp's shared-memory tile is reused
-        warp_adjoint_scatter<INFL>(sm[threadIdx.x >> 5], active[k], sl[k], sfaces, uw[k], r[k][0], r[k][1], r[k][2], scale, scale_i, acc);
+        warp_adjoint_scatter<INFL>(sm[threadIdx.x >> 5], active[k], sl[k], sfaces, uw[k], r[k][0], r[k][1], r[k][2], scale, scale_i, acc, n_vertices, n_faces);
     }
 }
 
@@ -1065,6 +1073,7 @@ static Sweep1Args make_args(nw_ctx *h) {
     a.posq = h->posq; a.sfaces = h->sfaces; a.tl = h->tl; a.F = h->F;
     a.tv.cent = h->cent; a.tv.cent64 = h->points_mode ? h->cent64 : nullptr; a.tv.boxes = h->boxes; a.tv.parent = h->parent_g; a.tv.kids = h->kids; a.tv.leaf_of_slot = h->leaf_of_slot;
     a.tv.leaf_level = h->tl.n_levels - 1; a.tv.leaf0 = h->tl.n_levels > 0 ? h->tl.off[h->tl.n_levels - 1] : 0;
+    a.tv.n_nodes = h->tl.n_levels > 0 ? h->tl.off[h->tl.n_levels - 1] + h->tl.count[h->tl.n_levels - 1] : 0; a.tv.n_slots = h->F;
     a.tv.fcells = h->fcells; a.tv.grid_lo = make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]); a.tv.grid_inv = h->key_inv;
     a.tv.grid_cellw = h->key_inv > 0.f ? 1.f / h->key_inv : 0.f;
     static const bool no_clear = getenv("NW_NO_CELL_CLEARANCE") != nullptr;      // A/B switch for measurements
@@ -1220,7 +1229,7 @@ int nw_launch_sweep1(nw_ctx *h, bool scatter) {
 int nw_launch_adjoint(nw_ctx *h) {
     if (h->P == 0) return NW_OK;
     k_adjoint<true><<<nw_grid(h->P, 256 * NW_ADJ_TILES), 256, 0, h->stream>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz,
-                                                                h->acc, h->st, 0, 0);
+                                                                h->acc, h->st, 0, 0, h->M, h->F);
     NW_LAUNCH_CHECK();
     return NW_OK;
 }
@@ -1349,7 +1358,7 @@ int nw_apply_AH_device(nw_ctx *h, const float *rx, const float *ry, const float 
     int shift = std::max(-100, std::min(40, std::min(61 - e, 38 - et)));
     NW_CUDA(cudaMemsetAsync(h->acc, 0, sizeof(unsigned long long) * 4 * h->M, s));
     if (h->P) {
-        k_adjoint<false><<<nw_grid(h->P, B * NW_ADJ_TILES), B, 0, s>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, rx, ry, rz, h->acc, nullptr, shift, 0);
+        k_adjoint<false><<<nw_grid(h->P, B * NW_ADJ_TILES), B, 0, s>>>(h->P, h->slot, h->sfaces, h->w0, h->w1, h->w2, rx, ry, rz, h->acc, nullptr, shift, 0, h->M, h->F);
         NW_LAUNCH_CHECK();
     }
     NW_CHECK(nw_allreduce_acc(h));
@@ -1432,7 +1441,7 @@ int nw_bench_launch(nw_ctx *h, const char *name) {
         float *yx = h->scratchP, *yy = yx + P, *yz = yy + P;
         k_apply_A<<<nw_grid(P, B), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->posq, yx, yy, yz);
     } else if (n == "apply_AH") {
-        k_adjoint<false><<<nw_grid(P, B * NW_ADJ_TILES), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->acc, nullptr, 20, 0);
+        k_adjoint<false><<<nw_grid(P, B * NW_ADJ_TILES), B, 0, s>>>(P, h->slot, h->sfaces, h->w0, h->w1, h->w2, h->rx, h->ry, h->rz, h->acc, nullptr, 20, 0, h->M, h->F);
     } else if (n == "adjoint") {
         return nw_launch_adjoint(h);
     } else if (n == "sweep1") {

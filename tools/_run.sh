@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py 2>&1 | tail -2
-python tools/trace_probe.py c3 2 2>&1 | grep -E "it |total|crc"
-python tools/vorder_probe.py c3 2>&1 | grep -E "vertices|Error"
+NANOWRAP_LIB=$PWD/ch_shrinkwrap_b200/libnanowrap_bounds.so timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gputest_bounds.txt 2>&1; tail -3 gpurun_out/r2_gputest_bounds.txt
+NANOWRAP_LIB=$PWD/ch_shrinkwrap_b200/libnanowrap_bounds.so python tools/trace_probe.py c3 1 2>&1 | grep -E "total|crc"
+python tools/trace_probe.py c3 1 2>&1 | grep -E "total|crc"
