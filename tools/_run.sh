@@ -1,2 +1,4 @@
 cd $GRAFT_REPO_ROOT
-for r in 0 8 12 16 24 32 64; do echo -n "NW_SEED_WIDE=$r: "; NW_SEED_WIDE=$r python tools/trace_probe.py c3 1 2>&1 | grep -E "it 0:|total|crc" | sed -e 's/refit.*seeds/seeds/' -e 's/shift.*//' | tr '\n' ' '; echo; done
+timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py 2>&1 | tail -2
+NW_TRACE_BUILD=1 python tools/trace_probe.py c3 2 2>&1 | grep -E "normals|it 3|total|crc" | tail -6
+python tools/trace_probe.py c5 2 2>&1 | grep -E "block|total|crc"
