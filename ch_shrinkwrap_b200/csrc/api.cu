@@ -46,7 +46,7 @@ extern "C" void nw_destroy(nw_ctx *h) {
     nw_free(&h->px64); nw_free(&h->py64); nw_free(&h->pz64);
     nw_free(&h->sx); nw_free(&h->sy); nw_free(&h->sz);
     nw_free(&h->wx); nw_free(&h->wy); nw_free(&h->wz);
-    nw_free(&h->pmask); nw_free(&h->perm); nw_free(&h->slot); nw_free(&h->fx); nw_free(&h->fy); nw_free(&h->fz); nw_free(&h->fkeys);
+    nw_free(&h->pmask); nw_free(&h->perm); nw_free(&h->slot); nw_free(&h->fx); nw_free(&h->fy); nw_free(&h->fz); nw_free(&h->fkeys); nw_free(&h->fkey_tab);
     nw_free(&h->w0); nw_free(&h->w1); nw_free(&h->w2);
     nw_free(&h->rx); nw_free(&h->ry); nw_free(&h->rz);
     nw_free(&h->posq); nw_free(&h->nrmq); nw_free(&h->faces); nw_free(&h->nbrT); nw_free(&h->valence); nw_free(&h->valid); nw_free(&h->stage_nbr); nw_free(&h->stage_hev); nw_free(&h->tb_small); nw_free(&h->tb_i0); nw_free(&h->tb_i1); nw_free(&h->tb_u0); nw_free(&h->tb_u1); nw_free(&h->tb_u2); nw_free(&h->fcells); nw_free(&h->cent64); nw_free(&h->parent_g); nw_free(&h->kids);

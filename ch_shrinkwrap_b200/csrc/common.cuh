@@ -134,6 +134,7 @@ struct nw_ctx {
     float *fx = nullptr, *fy = nullptr, *fz = nullptr;   // foot points on the previous block's surface (seeds after a remesh)
     bool feet_valid = false;
     unsigned *fkeys = nullptr;                   // sorted Hilbert keys of the face centroids at upload time
+    int *fkey_tab = nullptr;                     // lower_bound(fkeys, b << 15) for b = 0 .. 2^15: first step of the foot-point lookup
     float key_lo[3] = {0, 0, 0}, key_inv = 0.f;  // quantisation used for those keys
     int *parent_g = nullptr; int2 *kids = nullptr;  // the same tree addressed by global node ids (what the search walks)
     unsigned *fcells = nullptr;                  // per sorted slot: grid cell of the centroid at upload time, x | y << 10 | z << 20

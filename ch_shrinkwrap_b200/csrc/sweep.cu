@@ -708,7 +708,8 @@ __device__ __forceinline__ unsigned spread10s(unsigned v) {
 // there polishes the seed.
 __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ Sweep1Args a, const float *__restrict__ fx,
                                                         const float *__restrict__ fy, const float *__restrict__ fz,
-                                                        const unsigned *__restrict__ fkeys, float3 klo, float kinv, unsigned budget) {
+                                                        const unsigned *__restrict__ fkeys, const int *__restrict__ fkey_tab,
+                                                        float3 klo, float kinv, unsigned budget) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= a.P || a.slot[i] >= 0) return;
     const float x = fx[i], y = fy[i], z = fz[i];
@@ -718,7 +719,7 @@ __global__ void __launch_bounds__(128) k_seed_from_feet(const __grid_constant__ 
     unsigned qz = (unsigned)fminf(fmaxf((z - klo.z) * kinv, 0.f), 1023.f);
     hilbert_axes_to_transpose(qx, qy, qz, 10);
     const unsigned key = (spread10s(qx) << 2) | (spread10s(qy) << 1) | spread10s(qz);
-    int lo = 0, hi = a.F;                               // lower_bound
+    int lo = __ldg(&fkey_tab[key >> 15]), hi = __ldg(&fkey_tab[(key >> 15) + 1]);   // lower_bound, bracketed by the prefix table (tree.cu: k_key_table)
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (__ldg(&fkeys[mid]) < key) lo = mid + 1; else hi = mid;
@@ -1101,7 +1102,7 @@ int nw_launch_seed_leaders(nw_ctx *h) {
         // foot points of the previous block exist: on-surface queries, individually good seeds (measured: the cold
         // iteration costs 8.3 ms instead of 27 ms at C3).  On the very first block the localisations themselves are
         // too far from the surface for this lookup to pay off (measured slower than the 1-in-32 root search below).
-        k_seed_from_feet<<<nw_grid(h->P, B), B, 0, h->stream>>>(a, h->fx, h->fy, h->fz, h->fkeys,
+        k_seed_from_feet<<<nw_grid(h->P, B), B, 0, h->stream>>>(a, h->fx, h->fy, h->fz, h->fkeys, h->fkey_tab,
                                                                 make_float3(h->key_lo[0], h->key_lo[1], h->key_lo[2]), h->key_inv,
                                                                 0u);   // measured (again with the packet search, also with feet 30 nm off the new surface): polishing the looked-up seed (budgets 12..48) does not make k_sweep1 any faster
         NW_LAUNCH_CHECK();

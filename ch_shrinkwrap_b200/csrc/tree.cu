@@ -257,6 +257,20 @@ __global__ void __launch_bounds__(256) k_up_normals(float *__restrict__ nsum, co
     d[0] = sx; d[1] = sy; d[2] = sz;
 }
 
+// lower_bound of every 15-bit key prefix in the sorted face keys: k_seed_from_feet starts its binary search from this table
+// (1 load + ~5 steps instead of 20 dependent steps through a 4 MB array)
+__global__ void k_key_table(const unsigned *__restrict__ fkeys, int F, int *__restrict__ tab) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > 32768) return;
+    const unsigned long long key = (unsigned long long)b << 15;
+    int lo = 0, hi = F;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((unsigned long long)fkeys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    tab[b] = lo;
+}
+
 // frames from the normal sums; intervals empty
 __global__ void k_node_frames(Box *__restrict__ boxes, const float *__restrict__ nsum, int first, int count) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -585,6 +599,8 @@ int nw_tree_build(nw_ctx *h) {
     NW_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, keys, keys2, idx, order, F, 0, 30, s));
     NW_CHECK(nw_alloc(h, &h->fkeys, (size_t)F));
     NW_CUDA(cudaMemcpyAsync(h->fkeys, keys2, sizeof(unsigned) * F, cudaMemcpyDeviceToDevice, s));
+    NW_CHECK(nw_alloc(h, &h->fkey_tab, (size_t)32769));
+    k_key_table<<<nw_grid(32769, B), B, 0, s>>>(h->fkeys, F, h->fkey_tab);
     h->key_lo[0] = lo[0]; h->key_lo[1] = lo[1]; h->key_lo[2] = lo[2]; h->key_inv = inv;
     k_sorted_faces<<<nw_grid(F, B), B, 0, s>>>(h->faces, order, F, h->sfaces, cells, h->fcells);
     h->launches += 7;

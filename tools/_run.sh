@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py 2>&1 | tail -2
-NW_TRACE_BUILD=1 python tools/trace_probe.py c3 2 2>&1 | grep -E "normals|it 3|total|crc" | tail -6
-python tools/trace_probe.py c5 2 2>&1 | grep -E "block|total|crc"
+timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py > gpurun_out/t.txt 2>&1; tail -2 gpurun_out/t.txt
+python tools/trace_probe.py c3 3 > gpurun_out/tp.txt 2>&1; grep -E "it 0|total|crc" gpurun_out/tp.txt
