@@ -356,7 +356,7 @@ def main():
     else:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     alg_bytes = {
-        'sweep1': 76.0 * P + 24.0 * F + 12.0 * M,          # NN + weights + residual fused
+        'sweep1': 76.0 * P + 24.0 * F + 12.0 * M,          # NN + weights + residual in one kernel
         'sweep2': 36.0 * P + 12.0 * 3 * M,                 # multi-RHS Gram pass, n = 3
         'mesh_prior': 120.0 * M,                           # _ncc
         'apply_A': 36.0 * P + 12.0 * M,

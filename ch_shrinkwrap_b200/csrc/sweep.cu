@@ -1,11 +1,12 @@
 // sweep.cu -- the per-point kernels of the hot loop.
 //
 //   k_sweep1 : exact nearest face centroid (fp64 compare, octree of Hilbert cells) -> inverse-distance
-//              weights -> A f -> weighted, distance-de-weighted residual -> deterministic adjoint
-//              scatter of AH res and AH 1            (mesh_conj_grad.py:222-253, 433-516, 518-588)
+//              weights -> A f -> weighted, distance-de-weighted residual   (mesh_conj_grad.py:222-253, 433-516, 518-551)
+//   k_adjoint: deterministic scatter of AH res and AH 1 (exact fixed-point sums; the per-face sums of a warp are formed
+//              on the tensor cores); without the influence channel it is Ahfunc     (mesh_conj_grad.py:553-588)
 //   k_sweep2 : A applied to all search directions at once + Gram sums Hc, Gc, c0 in fp64, without
 //              materialising AS                                       (conj_grad.py:189-203)
-//   k_apply_A / k_adjoint : the single-operator forms behind Afunc / Ahfunc (k_adjoint<true> is also the scatter of the iteration).
+//   k_apply_A: the single-operator form behind Afunc.
 //
 // Determinism: the adjoint accumulates in 64-bit fixed point (integer atomics are order-independent,
 // float atomics are not); the Gram sums use a fixed thread->point assignment and a fixed two-stage tree.
