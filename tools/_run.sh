@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-for o in 1.5 3 6 12; do echo -n "NW_LEAF_OCC=$o: "; NW_LEAF_OCC=$o python tools/trace_probe.py c3 2 2>&1 | grep -E "it 3|total" | sed -e 's/refit.*//' | tr '\n' ' '; echo; done
+for w in c3 c5; do python tools/kprobe_wl.py $w mesh_prior; for v in 2 4 5; do echo -n "minb$v: "; NANOWRAP_LIB=$PWD/ch_shrinkwrap_b200/libnanowrap_mp$v.so python tools/kprobe_wl.py $w mesh_prior; done; done

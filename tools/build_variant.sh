@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../ch_shrinkwrap_b200"
 python -m ch_shrinkwrap_b200.build >/dev/null 2>&1 || (cd .. && python -m ch_shrinkwrap_b200.build >/dev/null)
 mkdir -p build/var_$1
-for f in sweep tree api; do
+for f in sweep tree api mesh_ops; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr $2 -c csrc/$f.cu -o build/var_$1/$f.cu.o &
 done
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -fmad=false $2 -c csrc/curvature.cu -o build/var_$1/curvature.cu.o &
