@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-for w in c3 c5; do python tools/kprobe_wl.py $w mesh_prior; for v in 2 4 5; do echo -n "minb$v: "; NANOWRAP_LIB=$PWD/ch_shrinkwrap_b200/libnanowrap_mp$v.so python tools/kprobe_wl.py $w mesh_prior; done; done
+for n in 0 4 16 64 152; do echo -n "NW_COLD_SINGLE=$n: "; NW_COLD_SINGLE=$n python tools/trace_probe.py c3 1 2>&1 | grep -E "it 0:|total|crc" | sed -e 's/refit.*seeds/seeds/' -e 's/shift.*//' | tr '\n' ' '; echo; done
