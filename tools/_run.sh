@@ -1,2 +1,4 @@
 cd $GRAFT_REPO_ROOT
-for n in 0 4 16 64 152; do echo -n "NW_COLD_SINGLE=$n: "; NW_COLD_SINGLE=$n python tools/trace_probe.py c3 1 2>&1 | grep -E "it 0:|total|crc" | sed -e 's/refit.*seeds/seeds/' -e 's/shift.*//' | tr '\n' ' '; echo; done
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py 2>&1 | tail -2
+python tools/trace_probe.py c3 2 2>&1 | grep -E "total|crc"
