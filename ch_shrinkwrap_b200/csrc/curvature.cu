@@ -119,7 +119,10 @@ struct CurvOut { float *k0, *k1, *e0, *e1, *H, *K, *dH, *dK, *E, *pE, *dEnb, *dE
 #ifndef NW_CURV_MINB
 #define NW_CURV_MINB 4      // 128 registers, 16 warps per SM: measured at C3 0.285 ms (3 blocks, 152 registers) -> 0.242 ms; 5 blocks (96 registers, spills) 0.248 ms
 #endif
-__global__ void __launch_bounds__(128, NW_CURV_MINB) k_curvature(const VertRec *__restrict__ V, const FaceRec *__restrict__ F,
+#ifndef NW_CURV_BLOCK
+#define NW_CURV_BLOCK 128
+#endif
+__global__ void __launch_bounds__(NW_CURV_BLOCK, NW_CURV_MINB) k_curvature(const VertRec *__restrict__ V, const FaceRec *__restrict__ F,
                                                    const HeRec *__restrict__ HE, int M, float dN, float kc, float kg, float c0,
                                                    const double *__restrict__ jitter_u, const int *__restrict__ jitter_off,
                                                    unsigned long long seed, CurvOut o) {
@@ -294,7 +297,7 @@ int nw_curvature_relaunch(nw_ctx *h) {
     CurvOut co;
     size_t offs[12];
     curv_outputs(h, co, offs);
-    k_curvature<<<nw_grid(h->curvM, 128), 128, 0, h->stream>>>((const VertRec *)h->cvV, (const FaceRec *)h->cvF, (const HeRec *)h->cvH,
+    k_curvature<<<nw_grid(h->curvM, NW_CURV_BLOCK), NW_CURV_BLOCK, 0, h->stream>>>((const VertRec *)h->cvV, (const FaceRec *)h->cvF, (const HeRec *)h->cvH,
                                                                 h->curvM, h->cv_dN, h->cv_kc, h->cv_kg, h->cv_c0, h->cvJ, h->cvOff,
                                                                 h->cv_seed, co);
     NW_LAUNCH_CHECK();

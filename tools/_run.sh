@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_scale.py 2>&1 | tail -2
-python tools/trace_probe.py c3 2 2>&1 | grep -E "total|crc"
+python tools/kernel_probe.py curvature
+for v in cb64 cb32 cb256; do echo -n "$v: "; NANOWRAP_LIB=$PWD/ch_shrinkwrap_b200/libnanowrap_$v.so python tools/kernel_probe.py curvature; done
